@@ -1,0 +1,149 @@
+"""CPU: the oracle (oracle/smc_oracle.c + oracle/smc_oracle.py) against fixtures produced by the
+UNMODIFIED reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import philox
+from oracle import smc_oracle as O
+from oracle.models import make_target
+
+RTOL = 1e-10
+
+
+def test_philox_kat():
+    for ctr, key, exp in philox.KAT:
+        out = philox.philox4x32_10(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))
+        assert [int(v) for v in out] == list(exp)
+        import ctypes
+        c = (ctypes.c_uint32 * 4)(*ctr); k = (ctypes.c_uint32 * 2)(*key); o = (ctypes.c_uint32 * 4)()
+        O.lib().orc_philox(c, k, o)
+        assert list(o) == list(exp)
+
+
+def test_c_streams_match_numpy_definition():
+    p = np.arange(5, 37)
+    for draw in (0, 1, 2, 7):
+        assert np.array_equal(O.uniforms(10, 3, 2, 5, 32, draw), philox.uniform(10, 3, 2, p, draw))
+    np.testing.assert_allclose(O.normals(10, 3, 1, 5, 32, 13), philox.normals(10, 3, 1, p, 13), rtol=1e-14, atol=1e-15)
+
+
+@pytest.mark.parametrize("name,tname,kw", [("arma", "arma", {}), ("PRMwCD", "PRMwCD", {}),
+                                           ("gauss", "gauss", {"dim": 8}), ("gauss100", "gauss", {"dim": 100})])
+def test_c_models_match_numpy_and_mpmath(golden, name, tname, kw):
+    g = golden("models")
+    t = O.COracleTarget(tname, **kw)
+    X = g[f"{name}_X"]
+    A, B, gA, gB = t.split(X)
+    ok = np.isfinite(g[f"{name}_A"]) & np.isfinite(g[f"{name}_B"])
+    np.testing.assert_allclose(A[ok], g[f"{name}_A"][ok], rtol=1e-13)
+    np.testing.assert_allclose(B[ok], g[f"{name}_B"][ok], rtol=1e-12)
+    np.testing.assert_allclose(gA[ok], g[f"{name}_gA"][ok], rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(gB[ok], g[f"{name}_gB"][ok], rtol=1e-11, atol=1e-9)
+    for phi in (0.0, 0.37, 1.0):
+        lp, gr = t.logpdf(X, phi), t.logpdfgrad(X, phi)
+        ref_lp, ref_g = g[f"{name}_lp_{phi}"], g[f"{name}_grad_{phi}"]
+        assert np.array_equal(np.isneginf(lp), np.isneginf(ref_lp))
+        fin = np.isfinite(ref_lp)
+        np.testing.assert_allclose(lp[fin], ref_lp[fin], rtol=1e-12)
+        np.testing.assert_allclose(gr[fin], ref_g[fin], rtol=1e-10, atol=1e-9)
+        assert np.all(np.isneginf(gr[~fin]))
+    if f"{name}_mp_lp_0.37" in g:
+        np.testing.assert_allclose(t.logpdf(X[:8], 0.37), g[f"{name}_mp_lp_0.37"], rtol=1e-13)
+
+
+def test_tempering_identity():
+    """logpdf(x,phi) = logpdf(x,0) + phi*(logpdf(x,1)-logpdf(x,0))  (adaptive_tempering.py:38-43)."""
+    for name in ("arma", "PRMwCD"):
+        t = O.COracleTarget(name)
+        x = np.random.default_rng(0).normal(size=(64, t.dim)) * 0.3
+        l0, l1 = t.logpdf(x, 0.0), t.logpdf(x, 1.0)
+        np.testing.assert_allclose(t.logpdf(x, 0.3), l0 + 0.3 * (l1 - l0), rtol=1e-12)
+
+
+NUTS_CASES = ["arma", "arma_tempered", "arma_prior", "PRMwCD", "PRMwCD_tempered", "gauss8", "gauss100"]
+
+
+@pytest.mark.parametrize("case", NUTS_CASES)
+def test_c_nuts_matches_reference_transitions(golden, case):
+    """One NUTS transition per particle: same x0, r0, same Philox draws -> same (x', r'), same tree size."""
+    g = golden("nuts")
+    tname = case.split("_")[0]
+    kw = {}
+    if tname.startswith("gauss"):
+        kw, tname = {"dim": int(tname[5:])}, "gauss"
+    t = O.COracleTarget(tname, **kw)
+    x0, r0 = g[f"{case}_x0"], g[f"{case}_r0"]
+    out = t.nuts_batch(x0, r0, float(g[f"{case}_eps"]), float(g[f"{case}_phi"]), 10, int(g[f"{case}_seed"]),
+                       int(g[f"{case}_iteration"]), 0, accrej=False)
+    assert np.array_equal(out["n_leapfrog"], g[f"{case}_n_leapfrog"])
+    np.testing.assert_allclose(out["x_new"], g[f"{case}_x_new"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(out["r_new"], g[f"{case}_r_new"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(out["lp_new"], t.logpdf(out["x_new"], float(g[f"{case}_phi"])), rtol=1e-12)
+    out2 = t.nuts_batch(x0, r0, float(g[f"{case}_eps"]), float(g[f"{case}_phi"]), 10, int(g[f"{case}_seed"]),
+                        int(g[f"{case}_iteration"]), 0, accrej=True)
+    acc = g[f"{case}_accepted"]
+    assert np.array_equal(out2["accepted"].astype(bool), acc)
+    np.testing.assert_allclose(out2["x_new"][acc], g[f"{case}_x_new"][acc], rtol=1e-9, atol=1e-11)
+    assert np.array_equal(out2["x_new"][~acc], x0[~acc]) and np.array_equal(out2["r_new"][~acc], r0[~acc])
+
+
+def test_choice_restatement(golden):
+    g = golden("choice")
+    for flavour in ("RandomState", "Generator"):
+        for N in (1, 2, 7, 100, 4096):
+            idx = O.multinomial_ancestors(g[f"{flavour}_{N}_wn"], g[f"{flavour}_{N}_u"])
+            assert np.array_equal(idx, g[f"{flavour}_{N}_idx"])
+    assert np.array_equal(O.multinomial_ancestors(g["dyadic_wn"], g["dyadic_u"]), g["dyadic_idx"])
+
+
+def test_lkernels_weights_estimates(golden):
+    g = golden("lkernel_weights")
+    for D in (4, 13, 100):
+        r_new, x_new = g[f"gaussL_{D}_r_new"], g[f"gaussL_{D}_x_new"]
+        np.testing.assert_allclose(O.gaussian_lkernel(r_new, x_new), g[f"gaussL_{D}_L"], rtol=1e-9)
+        np.testing.assert_allclose(O.forward_lkernel(r_new), g[f"fwdL_{D}"], rtol=1e-13)
+        np.testing.assert_allclose(O.std_normal_logpdf(r_new), g[f"qlogpdf_{D}"], rtol=1e-13)
+    for tag, tname in (("a", "arma"), ("b", "PRMwCD")):
+        wn, logZ = O.normalise_weights(g[f"weights_{tag}_logw"])
+        assert np.array_equal(wn, g[f"weights_{tag}_wn"]) and logZ == g[f"weights_{tag}_logZ"]
+        assert O.calculate_ess(wn) == g[f"weights_{tag}_ess"]
+        x = g[f"weights_{tag}_x"]
+        m, v = O.estimate(make_target(tname).constrain(x), wn)
+        np.testing.assert_allclose(m, g[f"weights_{tag}_mean_c"], rtol=1e-14)
+        np.testing.assert_allclose(v, g[f"weights_{tag}_var_c"], rtol=1e-14)
+        m, v = O.estimate(x, wn)
+        np.testing.assert_allclose(m, g[f"weights_{tag}_mean_u"], rtol=1e-14)
+
+
+def test_tempering_bisect(golden):
+    g = golden("tempering")
+    for j in range(4):
+        phi = O.calculate_phi(g[f"temper_{j}_loglik"], g[f"temper_{j}_logpri"], g[f"temper_{j}_lp_old"],
+                              float(g[f"temper_{j}_old_phi"]), len(g[f"temper_{j}_loglik"]))
+        assert phi == float(g[f"temper_{j}_phi"])          # bit-exact restatement of scipy bisect
+    for a, root in zip(g["bisect_a"], g["bisect_root"]):
+        assert O.bisect(lambda p: np.tanh(3 * (a - p)) + 0.1 * (a - p), 0.0, 1.0) == root
+
+
+RUNS = [("arma_forward", "arma", {}, "forwardsLKernel"), ("arma_gauss", "arma", {}, "GaussianApproxLKernel"),
+        ("arma_asymptotic", "arma", {}, "asymptoticLKernel"), ("arma_forward_tempered", "arma", {}, "forwardsLKernel"),
+        ("PRMwCD_asymptotic", "PRMwCD", {}, "asymptoticLKernel"),
+        ("gauss8_gaussL", "gauss", {"dim": 8}, "GaussianApproxLKernel")]
+
+
+@pytest.mark.parametrize("name,tname,kw,lk", RUNS)
+def test_full_run_matches_reference(golden, name, tname, kw, lk):
+    """Whole SMCSampler runs: oracle loop vs the unmodified reference driven with the same Philox streams."""
+    g = golden("runs")
+    N, K, eps, temp = g[f"{name}_cfg"]
+    s = O.OracleSMC(int(K), int(N), tname, float(eps), lk, bool(temp), seed=10, target_kw=kw, nthreads=4).run()
+    assert np.array_equal(s.n_leapfrog, g[f"{name}_leapfrogs"])
+    np.testing.assert_allclose(s.x_saved[0], g[f"{name}_x_first"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(s.phi, g[f"{name}_phi"], rtol=1e-9)
+    np.testing.assert_allclose(s.ess, g[f"{name}_ess"], rtol=1e-7)
+    np.testing.assert_allclose(s.log_likelihood, g[f"{name}_log_likelihood"], rtol=1e-8)
+    np.testing.assert_allclose(s.acceptance_rate, g[f"{name}_acceptance_rate"])
+    np.testing.assert_allclose(s.x_saved[int(K)], g[f"{name}_x_final"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(s.logw_saved[int(K)], g[f"{name}_logw_final"], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(s.mean_estimate, g[f"{name}_mean_estimate"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(s.variance_estimate, g[f"{name}_variance_estimate"], rtol=1e-5, atol=1e-10)
