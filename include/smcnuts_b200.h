@@ -1,0 +1,153 @@
+/* smcnuts_b200 -- C-ABI of the B200-native SMC-NUTS particle hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.  Every entry point
+ *   - takes DEVICE pointers unless the parameter name starts with `host_`,
+ *   - enqueues its work on `stream` (a cudaStream_t passed as void*) and does not synchronise,
+ *   - never allocates device memory except smcb_model_create (scratch comes from the caller via the
+ *     *_workspace_bytes queries), never throws,
+ *   - returns 0 on success, <0 on error (message via smcb_last_error()).
+ * Particle arrays are row-major [N, D] float64, exactly the reference's numpy layout.
+ *
+ * Each function names the reference code it replaces (paths relative to the SMC-NUTS checkout).
+ * The reference has no FFI of its own for this path: its only native crossing is
+ * Python -> ctypes -> BridgeStan per particle per leapfrog (smcnuts/model/bridgestan.py:46,78);
+ * INTEGRATION.md shows the ctypes binding a maintainer adds to call these instead.
+ */
+#ifndef SMCNUTS_B200_H
+#define SMCNUTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMCB_MODEL_ARMA 0   /* stan_models/arma/arma.stan       host blob: y[T]                                   */
+#define SMCB_MODEL_PRMWCD 1 /* stan_models/PRMwCD/PRMwCD.stan   host blob: q, y[NO], lgamma(y+1)[NO], X[NO*11]    */
+#define SMCB_MODEL_GAUSS 2  /* synthetic Gaussian (config 4)    host blob: P[D*D] precision, row-major            */
+
+#define SMCB_STREAM_NUTS 0
+#define SMCB_STREAM_MOMENTUM 1
+#define SMCB_STREAM_ACCREJ 2
+#define SMCB_STREAM_RESAMPLE 3
+#define SMCB_STREAM_INIT 4
+#define SMCB_STREAM_ESTIMATE 5
+
+#define SMCB_CONSTRAIN_NONE 0      /* estimate.py:34-36 (_unconstrained_target)                             */
+#define SMCB_CONSTRAIN_EXP_LAST 1  /* bridgestan.py:93-120 for arma / PRMwCD: exp() on the last coordinate  */
+
+int smcb_version(void);
+const char* smcb_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+long long smcb_launch_count(void);
+
+/* ---- model (replaces StanModel.__init__, bridgestan.py:13-26; phi is an argument, not a reload :122-146) */
+int smcb_model_create(int kind, const double* host_data, long long n, int dim, void** handle);
+int smcb_model_destroy(void* handle);
+int smcb_model_dim(void* handle);
+
+/* StanModel.logpdf / logpdfgrad (bridgestan.py:28-90): A = log prior + Jacobian, B = log likelihood,
+ * grad = d(A + phi*B)/dx with the failure mapping (non-finite logp -> grad row of -inf).  Any output may be NULL. */
+int smcb_logp_grad(void* handle, const double* x, long long N, double phi, double* A, double* B, double* grad,
+                   void* stream);
+/* out = A + phi*B, non-finite -> -inf (bridgestan.py:47-49) */
+int smcb_combine_logp(const double* A, const double* B, double phi, long long N, double* out, void* stream);
+
+/* ---- NUTS proposal (NUTSProposal.rvs nuts.py:34-175; accrej != 0: NUTSProposalWithAccRej.rvs nuts_acc_rej.py:27-52) */
+int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long long* bytes);
+int smcb_nuts_transition(void* handle, const double* x, const double* r, long long N, double eps, double phi,
+                         int max_depth, int accrej, uint64_t seed, uint32_t iteration, uint64_t particle0,
+                         double* x_new, double* r_new, double* A_old, double* B_old, double* A_new, double* B_new,
+                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth, void* workspace,
+                         long long workspace_bytes, void* stream);
+
+/* ---- Philox streams (momentum_proposal.rvs samples.py:155; sample_proposal.rvs samples.py:77) */
+int smcb_normals(uint64_t seed, uint32_t iteration, uint32_t stream_id, uint64_t particle0, long long N, int D,
+                 double* out, void* stream);
+int smcb_uniforms(uint64_t seed, uint32_t iteration, uint32_t stream_id, uint64_t particle0, long long N,
+                  uint32_t draw, double* out, void* stream);
+
+/* ---- weights */
+/* out[i] = 0.5*|r_i|^2  (momentum_proposal.logpdf(r) = -out - D/2 log 2pi, nuts.py:177-189) */
+int smcb_row_half_sqnorm(const double* r, long long N, int D, double* out, void* stream);
+/* out[i] = N(x_i; 0, I).logpdf = -0.5*|x_i|^2 - D/2 log 2pi  (momentum / q0 density, nuts.py:189, forward_lkernel.py:35) */
+int smcb_std_normal_logpdf(const double* x, long long N, int D, double* out, void* stream);
+/* out[i] = logZ[0] - log(N_total): the weights after resampling (samples.py:143) */
+int smcb_uniform_logw(const double* logZ, long long N_total, long long N, double* out, void* stream);
+/* out[i] = a*in[i] + b (small helper: mean = sums / N) */
+int smcb_affine(const double* in, long long N, double a, double b, double* out, void* stream);
+/* logw = lp - N(x; 0, I).logpdf  (samples.py:85 with q0 = N(0, I)) */
+int smcb_init_logw(const double* lp, const double* x, long long N, int D, double* logw, void* stream);
+/* samples.py:183-196 with ForwardLKernel (forward_lkernel.py:35): logw + lp_xnew - lp_x - 0.5|r_new|^2 + 0.5|r|^2 */
+int smcb_reweight_forward(const double* logw, const double* lp_x, const double* lp_xnew, const double* r,
+                          const double* r_new, long long N, int D, double* out, void* stream);
+/* same, from the kinetic energies K2 already emitted (40 B/particle instead of 16D+24) */
+int smcb_reweight_forward_ke(const double* logw, const double* lp_x, const double* lp_xnew, const double* ke_old,
+                             const double* ke_new, long long N, double* out, void* stream);
+/* samples.py:196 for any L-kernel: logw + lp_xnew - lp_x + L - q */
+int smcb_reweight_general(const double* logw, const double* lp_x, const double* lp_xnew, const double* L,
+                          const double* q, long long N, double* out, void* stream);
+/* samples.py:169-180: logw + logp(x, phi_new) - logp(x, phi_old) from the split at the pre-move x */
+int smcb_reweight_asymptotic(const double* logw, const double* A, const double* B, double phi_new, double phi_old,
+                             long long N, double* out, void* stream);
+
+/* samples.py:96-98 + :113, pass 1: out3 = (m, sum exp(logw-m), sum exp(2(logw-m))) over finite-or-+inf entries
+ * (-inf ignored).  workspace: smcb_reduce_workspace_bytes(). */
+long long smcb_reduce_workspace_bytes(void);
+int smcb_lse_partial(const double* logw, long long N, double* out3, void* workspace, void* stream);
+/* merge P rank triples -> out2 = (logZ, ESS)   (single GPU: P = 1) */
+int smcb_lse_finalize(const double* triples, int P, double* out2, void* stream);
+/* samples.py:101-102: wn = exp(logw - logZ), 0 where logw = -inf; logZ read from device memory */
+int smcb_normalise(const double* logw, long long N, const double* logZ, double* wn, void* stream);
+
+/* ---- adaptive tempering (adaptive_tempering.py:18-63) */
+/* logpri = A, loglik = (A+B) - A, c = A + phi_old*B, each with the -inf failure mapping (:38-39, samples.py:207) */
+int smcb_tempering_arrays(const double* A, const double* B, double phi_old, long long N, double* logpri,
+                          double* loglik, double* c, void* stream);
+/* for each of m candidate phi: triple (max, sum exp, sum exp^2) of phi*loglik + logpri - c  (:41-54); out[m*3] */
+int smcb_ess_multi_phi(const double* loglik, const double* logpri, const double* c, long long N,
+                       const double* phis, int m, double* out, void* workspace, void* stream);
+
+/* ---- resampling (samples.py:116-146; `rng.choice` == searchsorted(cumsum(wn)/total, u, 'right')) */
+long long smcb_scan_workspace_bytes(long long N);
+/* cdf = inclusive_scan(wn) / total; total -> total_out[0].  offset_in (nullable, device) is added to every
+ * prefix before normalisation and total_in (nullable) replaces the local total: the multi-GPU global scan. */
+int smcb_cdf(const double* wn, long long N, const double* offset_in, const double* total_in, double* cdf,
+             double* total_out, void* workspace, void* stream);
+int smcb_ancestors_multinomial(const double* cdf, long long N, const double* u, long long M, int64_t* idx,
+                               void* stream);
+/* systematic: positions (j0 + j + u0)/M_total, j = 0..M-1 (north_star; not in the reference) */
+int smcb_ancestors_systematic(const double* cdf, long long N, double u0, long long j0, long long M_total,
+                              long long M, int64_t* idx, void* stream);
+/* out[j, :] = x[idx[j], :]  (samples.py:140) */
+int smcb_gather_rows(const double* x, const int64_t* idx, long long M, int D, double* out, void* stream);
+
+/* ---- estimators (estimate.py:79-95 with constrain fused, bridgestan.py:93-120) */
+/* out[d] = sum_i wn_i * (c(x_i)_d - center_d)^power ; center may be NULL (0), power in {1, 2} */
+int smcb_weighted_moment(const double* x, const double* wn, long long N, int D, int constrain, const double* center,
+                         int power, double* out, void* workspace, void* stream);
+/* smc_sampler.py:97: number of rows with ALL coordinates changed -> out_count[0] (double) */
+int smcb_count_moved(const double* x, const double* x_new, long long N, int D, double* out_count, void* workspace,
+                     void* stream);
+
+/* ---- Gaussian-approximation optimal L-kernel (gaussian_lkernel.py:24-84) */
+/* sums[2D] = column sums of X = [-r_new, x_new] */
+int smcb_gaussL_sums(const double* r_new, const double* x_new, long long N, int D, double* sums, void* stream);
+/* gram[2D*2D] += sum_i (X_i - mean)(X_i - mean)'   (gram must be zeroed by the caller) */
+int smcb_gaussL_gram(const double* r_new, const double* x_new, long long N, int D, const double* mean, double* gram,
+                     void* stream);
+/* cov = gram/(N_total-1) -> S = C_rr - C_rx C_xx^-1 C_xr + ridge*I = L L';  G = L^-1 [I, -C_rx C_xx^-1] (D x 2D);
+ * out_logdet[0] = log det S.  scratch: 6*D*D doubles. */
+int smcb_gaussL_factor(const double* gram, long long N_total, int D, double ridge, double* G, double* out_logdet,
+                       double* scratch, void* stream);
+/* out_i = -0.5*(D log 2pi + logdet + |G (X_i - mean)|^2) */
+int smcb_gaussL_logpdf(const double* r_new, const double* x_new, long long N, int D, const double* mean,
+                       const double* G, const double* logdet, double* out, void* stream);
+
+/* ---- measurement helper: dependent-chain-free DFMA loop; out_flops[0] = FLOPs executed (device double) */
+int smcb_probe_fp64(int blocks, int threads, int iters, double* out_sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

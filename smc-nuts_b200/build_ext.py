@@ -1,0 +1,57 @@
+"""Build libsmcnuts_b200.so (hand-written sm_100a CUDA behind the C-ABI of include/smcnuts_b200.h) in-tree.
+
+    python smc-nuts_b200/build_ext.py [--force]
+
+nvcc cross-compiles without a GPU.  The shared object lands in smc-nuts_b200/smcnuts/_lib/ (git-ignored,
+but it travels to the GPU box with the repo snapshot).
+"""
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+OUT_DIR = HERE / "smcnuts" / "_lib"
+OUT = OUT_DIR / "libsmcnuts_b200.so"
+SOURCES = ["nuts_kernel.cu", "weights.cu", "resample.cu", "gauss_lkernel.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+              "--use_fast_math=false"]
+NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]  # IEEE FP64 everywhere; no fast-math
+
+
+def _stale(target, deps):
+    return (not target.exists()) or target.stat().st_mtime < max(p.stat().st_mtime for p in deps)
+
+
+def build(force=False, verbose=False):
+    OUT_DIR.mkdir(parents=True, exist_ok=True)
+    obj_dir = HERE / "build"
+    obj_dir.mkdir(exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "smcnuts_b200.h"]
+
+    def compile_one(src):
+        obj = obj_dir / (src[:-3] + ".o")
+        if force or _stale(obj, [CSRC / src] + headers):
+            cmd = ["nvcc", *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+            if verbose:
+                print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    if force or _stale(OUT, objs):
+        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(OUT), *map(str, objs)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

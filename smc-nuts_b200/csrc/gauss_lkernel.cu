@@ -1,0 +1,261 @@
+// K6 -- Gaussian-approximation optimal L-kernel.
+//
+// Replaces /root/reference/smcnuts/lkernel/gaussian_lkernel.py:24-84, which estimates the unweighted mean
+// and covariance of X = [-r_new, x_new] (N x 2D), forms the conditional Gaussian of -r_new given x_new and
+// evaluates it per particle in a Python loop that recomputes pinv(C_xx) and an eigendecomposition for
+// every particle (35 ms/particle at D = 100).  Here:
+//   gaussL_sums    column sums (one coalesced sweep)                       -> allreduce when sharded
+//   gaussL_gram    centred Gram matrix, register-tiled FP64 outer products -> allreduce when sharded
+//   gaussL_factor  one CTA: Cholesky(C_xx), W = C_rx C_xx^-1, S = C_rr - W C_xr + ridge I = L L',
+//                  G = L^-1 [I, -W], log det S
+//   gaussL_logpdf  per particle: z = G (X_i - mean), -0.5 (D log 2pi + log det S + |z|^2)
+// which is algebraically the reference's multivariate_normal.logpdf(-r_i; mu_i, S) with
+// mu_i = mu_r + W (x_i - mu_x)  (hoisted form checked to ~1e-13 against the reference loop in tests/golden).
+#include "capi.cuh"
+
+namespace smcb {
+
+// X_ic for the virtual matrix X = [-r_new, x_new]
+__device__ __forceinline__ double xval(const double* __restrict__ r, const double* __restrict__ x, long long i, int c,
+                                       int D) {
+    return (c < D) ? -r[i * D + c] : x[i * D + (c - D)];
+}
+
+__global__ void __launch_bounds__(256) gaussL_sums_kernel(const double* __restrict__ r, const double* __restrict__ x,
+                                                          long long N, int D, double* sums, int used) {
+    __shared__ double sh[256];
+    const long long total = N * D;
+    const long long gstride = (long long)gridDim.x * used;
+    const int col = threadIdx.x % D;
+    double ar = 0.0, ax = 0.0;
+    if ((int)threadIdx.x < used)
+        for (long long e = (long long)blockIdx.x * used + threadIdx.x; e < total; e += gstride) {
+            ar -= r[e];
+            ax += x[e];
+        }
+    for (int pass = 0; pass < 2; ++pass) {
+        sh[threadIdx.x] = pass ? ax : ar;
+        __syncthreads();
+        if ((int)threadIdx.x < D) {
+            double s = 0.0;
+            for (int t = threadIdx.x; t < used; t += D) s += sh[t];
+            atomicAdd(&sums[pass * D + col], s);
+        }
+        __syncthreads();
+    }
+}
+
+// Centred Gram: each CTA owns one TB x TB output tile and a slab of rows; 16 x 16 threads, 4 x 4 micro-tiles.
+constexpr int kTB = 64, kTM = 4, kRK = 32;
+__global__ void __launch_bounds__(256) gaussL_gram_kernel(const double* __restrict__ r, const double* __restrict__ x,
+                                                          long long N, int D, const double* __restrict__ mean,
+                                                          double* gram, int tiles, long long rows_per_block) {
+    __shared__ double smA[kRK][kTB + 2], smB[kRK][kTB + 2];
+    const int D2 = 2 * D;
+    const int ti = blockIdx.y / tiles, tj = blockIdx.y % tiles;
+    if (tj < ti) return;  // symmetric: only the upper block-triangle is accumulated, mirrored in gaussL_factor
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long row_begin = (long long)blockIdx.x * rows_per_block;
+    const long long row_end = min(N, row_begin + rows_per_block);
+    double acc[kTM][kTM];
+#pragma unroll
+    for (int a = 0; a < kTM; ++a)
+#pragma unroll
+        for (int b = 0; b < kTM; ++b) acc[a][b] = 0.0;
+    for (long long row0 = row_begin; row0 < row_end; row0 += kRK) {
+        for (int e = threadIdx.x; e < kRK * kTB; e += 256) {
+            const int k = e / kTB, c = e % kTB;
+            const long long i = row0 + k;
+            const int ca = ti * kTB + c, cb = tj * kTB + c;
+            smA[k][c] = (i < row_end && ca < D2) ? xval(r, x, i, ca, D) - mean[ca] : 0.0;
+            smB[k][c] = (i < row_end && cb < D2) ? xval(r, x, i, cb, D) - mean[cb] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < kRK; ++k) {
+            double a[kTM], b[kTM];
+#pragma unroll
+            for (int m = 0; m < kTM; ++m) { a[m] = smA[k][ty * kTM + m]; b[m] = smB[k][tx * kTM + m]; }
+#pragma unroll
+            for (int m = 0; m < kTM; ++m)
+#pragma unroll
+                for (int n = 0; n < kTM; ++n) acc[m][n] += a[m] * b[n];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < kTM; ++m)
+#pragma unroll
+        for (int n = 0; n < kTM; ++n) {
+            const int gi = ti * kTB + ty * kTM + m, gj = tj * kTB + tx * kTM + n;
+            if (gi < D2 && gj < D2) atomicAdd(&gram[(size_t)gi * D2 + gj], acc[m][n]);
+        }
+}
+
+// In-place lower Cholesky of the n x n row-major matrix a (only the lower triangle is read).  One CTA.
+__device__ void chol_inplace(double* a, int n) {
+    for (int j = 0; j < n; ++j) {
+        __syncthreads();
+        if (threadIdx.x == 0) a[j * n + j] = sqrt(a[j * n + j]);
+        __syncthreads();
+        const double dj = a[j * n + j];
+        for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) a[i * n + j] /= dj;
+        __syncthreads();
+        // trailing update of the lower triangle
+        const int rem = n - j - 1;
+        for (int t = threadIdx.x; t < rem * rem; t += blockDim.x) {
+            const int i = j + 1 + t / rem, k = j + 1 + t % rem;
+            if (k <= i) a[i * n + k] -= a[i * n + j] * a[k * n + j];
+        }
+    }
+    __syncthreads();
+}
+
+// Solve L Y = B in place (B is n x m row-major, L lower-triangular n x n).  One thread per column of B.
+__device__ void trsm_lower(const double* L, double* B, int n, int m) {
+    for (int c = threadIdx.x; c < m; c += blockDim.x)
+        for (int i = 0; i < n; ++i) {
+            double s = B[i * m + c];
+            for (int k = 0; k < i; ++k) s -= L[i * n + k] * B[k * m + c];
+            B[i * m + c] = s / L[i * n + i];
+        }
+    __syncthreads();
+}
+// Solve L' Y = B in place.
+__device__ void trsm_lower_t(const double* L, double* B, int n, int m) {
+    for (int c = threadIdx.x; c < m; c += blockDim.x)
+        for (int i = n - 1; i >= 0; --i) {
+            double s = B[i * m + c];
+            for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * B[k * m + c];
+            B[i * m + c] = s / L[i * n + i];
+        }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) gaussL_factor_kernel(const double* __restrict__ gram, long long N_total, int D,
+                                                            double ridge, double* G, double* out_logdet,
+                                                            double* scratch) {
+    const int D2 = 2 * D, DD = D * D;
+    double* Lx = scratch;           // C_xx -> chol
+    double* Wt = scratch + DD;      // C_xr (D x D) -> C_xx^-1 C_xr = W'
+    double* S = scratch + 2 * DD;   // S -> chol
+    const double inv = 1.0 / (double)(N_total - 1);  // np.cov ddof = 1 (gaussian_lkernel.py:49)
+    auto cov = [&](int i, int j) { return (i <= j ? gram[(size_t)i * D2 + j] : gram[(size_t)j * D2 + i]) * inv; };
+    for (int t = threadIdx.x; t < DD; t += blockDim.x) {
+        const int i = t / D, j = t % D;
+        Lx[t] = cov(D + i, D + j);
+        Wt[t] = cov(D + i, j);  // C_xr[i][j]
+    }
+    __syncthreads();
+    chol_inplace(Lx, D);
+    trsm_lower(Lx, Wt, D, D);
+    trsm_lower_t(Lx, Wt, D, D);  // Wt = C_xx^-1 C_xr, i.e. W = Wt'
+    for (int t = threadIdx.x; t < DD; t += blockDim.x) {
+        const int i = t / D, j = t % D;
+        double s = cov(i, j);
+        for (int k = 0; k < D; ++k) s -= cov(i, D + k) * Wt[k * D + j];  // C_rx[i][k] * (C_xx^-1 C_xr)[k][j]
+        S[t] = s + (i == j ? ridge : 0.0);
+    }
+    __syncthreads();
+    // symmetrise the lower triangle that the factorisation reads
+    for (int t = threadIdx.x; t < DD; t += blockDim.x) {
+        const int i = t / D, j = t % D;
+        if (j < i) S[t] = 0.5 * (S[t] + S[j * D + i]);
+    }
+    __syncthreads();
+    chol_inplace(S, D);
+    if (threadIdx.x == 0) {
+        double ld = 0.0;
+        for (int i = 0; i < D; ++i) ld += log(S[i * D + i]);
+        out_logdet[0] = 2.0 * ld;
+    }
+    // G = L^-1 [I, -W]   (D x 2D)
+    for (int t = threadIdx.x; t < D * D2; t += blockDim.x) {
+        const int i = t / D2, c = t % D2;
+        G[t] = (c < D) ? (i == c ? 1.0 : 0.0) : -Wt[(c - D) * D + i];  // -W[i][c-D] = -Wt[c-D][i]
+    }
+    __syncthreads();
+    trsm_lower(S, G, D, D2);
+}
+
+constexpr int kGDmax = 128;
+__global__ void __launch_bounds__(128) gaussL_logpdf_kernel(const double* __restrict__ r, const double* __restrict__ x,
+                                                            long long N, int D, const double* __restrict__ mean,
+                                                            const double* __restrict__ G,
+                                                            const double* __restrict__ logdet, double* __restrict__ out,
+                                                            int g_in_smem) {
+    extern __shared__ double sm[];
+    const int D2 = 2 * D;
+    const double* Gs = G;
+    if (g_in_smem) {
+        for (int t = threadIdx.x; t < D * D2; t += blockDim.x) sm[t] = G[t];
+        __syncthreads();
+        Gs = sm;
+    }
+    const double c0 = D * kLog2Pi + logdet[0];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        double v[2 * kGDmax];
+        for (int c = 0; c < D2; ++c) v[c] = xval(r, x, i, c, D) - mean[c];
+        double maha = 0.0;
+        for (int row = 0; row < D; ++row) {
+            const double* g = Gs + (size_t)row * D2;
+            double z = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < D2; ++c) z += g[c] * v[c];
+            maha += z * z;
+        }
+        out[i] = -0.5 * (c0 + maha);
+    }
+}
+
+}  // namespace smcb
+
+using namespace smcb;
+
+extern "C" {
+
+int smcb_gaussL_sums(const double* r_new, const double* x_new, long long N, int D, double* sums, void* stream) {
+    SMCB_REQUIRE(r_new && x_new && sums && N >= 1 && D >= 1 && D <= kGDmax, "bad argument (D <= 128)");
+    cudaStream_t st = (cudaStream_t)stream;
+    SMCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * D, st));
+    const int used = (256 / D) * D;
+    gaussL_sums_kernel<<<stride_grid(N * D, 256, 4), 256, 0, st>>>(r_new, x_new, N, D, sums, used);
+    return check_launch("gaussL_sums_kernel");
+}
+
+int smcb_gaussL_gram(const double* r_new, const double* x_new, long long N, int D, const double* mean, double* gram,
+                     void* stream) {
+    SMCB_REQUIRE(r_new && x_new && mean && gram && N >= 1 && D >= 1 && D <= kGDmax, "bad argument (D <= 128)");
+    const int tiles = (2 * D + kTB - 1) / kTB;
+    const int active_tiles = tiles * (tiles + 1) / 2;
+    long long slabs = (long long)device_sm_count() * 4 / active_tiles;
+    if (slabs < 1) slabs = 1;
+    long long rows_per_block = (N + slabs - 1) / slabs;
+    rows_per_block = ((rows_per_block + kRK - 1) / kRK) * kRK;
+    slabs = (N + rows_per_block - 1) / rows_per_block;
+    dim3 grid((unsigned)slabs, (unsigned)(tiles * tiles));
+    gaussL_gram_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_new, x_new, N, D, mean, gram, tiles, rows_per_block);
+    return check_launch("gaussL_gram_kernel");
+}
+
+int smcb_gaussL_factor(const double* gram, long long N_total, int D, double ridge, double* G, double* out_logdet,
+                       double* scratch, void* stream) {
+    SMCB_REQUIRE(gram && G && out_logdet && scratch && N_total >= 2 && D >= 1 && D <= kGDmax, "bad argument (D <= 128)");
+    gaussL_factor_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(gram, N_total, D, ridge, G, out_logdet, scratch);
+    return check_launch("gaussL_factor_kernel");
+}
+
+int smcb_gaussL_logpdf(const double* r_new, const double* x_new, long long N, int D, const double* mean,
+                       const double* G, const double* logdet, double* out, void* stream) {
+    SMCB_REQUIRE(r_new && x_new && mean && G && logdet && out && N >= 0 && D >= 1 && D <= kGDmax, "bad argument (D <= 128)");
+    if (N == 0) return 0;
+    const size_t smem = sizeof(double) * (size_t)D * 2 * D;
+    const int in_smem = smem <= 200 * 1024;
+    if (in_smem && smem > 48 * 1024)
+        SMCB_CUDA(cudaFuncSetAttribute(gaussL_logpdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gaussL_logpdf_kernel<<<stride_grid(N, 128, in_smem && smem > 100 * 1024 ? 1 : 4), 128, in_smem ? smem : 0,
+                           (cudaStream_t)stream>>>(r_new, x_new, N, D, mean, G, logdet, out, in_smem);
+    return check_launch("gaussL_logpdf_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// K1 -- fused tempered log-posterior + gradient device functions.
+//
+// Replaces the per-particle BridgeStan calls of /root/reference/smcnuts/model/bridgestan.py:28-90
+// (log_density / log_density_gradient, one ctypes call per particle per leapfrog, and a JSON rewrite +
+// model reload per phi change, :122-146).  Every model returns the split
+//     logp(x, phi) = A(x) + phi * B(x),   A = log prior + log Jacobian,  B = log likelihood
+// (the identity adaptive_tempering.py:38-43 relies on), so phi is a plain kernel argument and one
+// evaluation serves NUTS (at phi_new), the phi=1 reweight (samples.py:190-191) and the tempering
+// bisection (adaptive_tempering.py:38-39) at once.
+//
+//   ArmaModel   /root/reference/stan_models/arma/arma.stan:16-30        x = (mu, beta, theta, log sigma)
+//   PrmModel    /root/reference/stan_models/PRMwCD/PRMwCD.stan:17-39    x = (Beta_1..12, log Gamma)
+//   GaussModel  synthetic correlated Gaussian of BASELINE.json config 4
+//
+// Arithmetic order follows oracle/smc_oracle.c statement by statement (device FMA contraction is the
+// only difference), so device and oracle agree to ~1e-15 relative.
+#pragma once
+#include "common.cuh"
+
+namespace smcb {
+
+// Plain-old-data descriptor handed to kernels by value; `data` points at the packed device blob.
+struct ModelDesc {
+    int kind;
+    int dim;
+    int n_data;          // doubles in `data`
+    int T;               // arma: series length; PRMwCD: number of observations
+    double q;            // PRMwCD: exponent of the exponential-power prior
+    const double* data;  // device (or, in tests/hostsim, host) pointer
+};
+
+// ---------------------------------------------------------------------------------------------- arma
+struct ArmaModel {
+    static constexpr int DMAX = 4;
+    static constexpr int STATIC_D = 4;
+    const double* y;
+    int T;
+    SMCB_HD explicit ArmaModel(const ModelDesc& d, const double* staged) : y(staged), T(d.T) {}
+    SMCB_HD static constexpr int dim_of(const ModelDesc&) { return 4; }
+    SMCB_HD constexpr int dim() const { return 4; }
+    static int staged_doubles(const ModelDesc& d) { return d.T; }
+
+    // A, B and g = grad A + phi * grad B
+    SMCB_HD void eval(const double (&x)[DMAX], double phi, double& A, double& B, double (&g)[DMAX]) const {
+        const double mu = x[0], beta = x[1], theta = x[2], s = x[3];
+        const double sigma = exp(s), sig2 = sigma * sigma, q = sig2 / 6.25;
+        A = (-0.5 * kLog2Pi - 2.3025850929940456840 - mu * mu / 200.0) +
+            (-0.5 * kLog2Pi - 0.69314718055994530942 - beta * beta / 8.0) +
+            (-0.5 * kLog2Pi - 0.69314718055994530942 - theta * theta / 8.0) +
+            (-kLogPi - 0.91629073187415506518 - log1p(q)) + s;
+        double ylag = y[0];
+        double e = ylag - (mu + beta * mu);
+        double dm = -(1.0 + beta), db = -mu, dt = 0.0;
+        double S = e * e, Sm = e * dm, Sb = e * db, St = e * dt;
+#pragma unroll 4
+        for (int t = 1; t < T; ++t) {
+            const double yt = y[t];
+            const double en = yt - (mu + beta * ylag + theta * e);
+            const double dmn = -1.0 - theta * dm, dbn = -ylag - theta * db, dtn = -e - theta * dt;
+            e = en; dm = dmn; db = dbn; dt = dtn; ylag = yt;
+            S += e * e; Sm += e * dm; Sb += e * db; St += e * dt;
+        }
+        const double inv = 1.0 / sig2;
+        B = -0.5 * T * kLog2Pi - T * s - 0.5 * S * inv;
+        if (!is_finite(sigma) || sigma <= 0.0) A = neg_inf();
+        g[0] = -mu / 100.0 + phi * (-Sm * inv);
+        g[1] = -beta / 4.0 + phi * (-Sb * inv);
+        g[2] = -theta / 4.0 + phi * (-St * inv);
+        g[3] = (1.0 - 2.0 * q / (1.0 + q)) + phi * (-T + S * inv);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- PRMwCD
+// Packed device layout (built by smcb_model_create from the host blob [q, y(NO), lgamma(y+1)(NO), X(NO x 11)]):
+//   per observation i, 14 doubles: X_i0..X_i10, 0 (pad), y_i, lgamma(y_i+1)      -> 16-byte aligned rows
+struct PrmModel {
+    static constexpr int DMAX = 13;
+    static constexpr int STATIC_D = 13;
+    static constexpr int M = 12, C = 11, ROW = 14;
+    const double* rows;
+    int NO;
+    double q;
+    SMCB_HD explicit PrmModel(const ModelDesc& d, const double* staged) : rows(staged), NO(d.T), q(d.q) {}
+    SMCB_HD static constexpr int dim_of(const ModelDesc&) { return 13; }
+    SMCB_HD constexpr int dim() const { return 13; }
+    static int staged_doubles(const ModelDesc& d) { return d.T * ROW; }
+
+    SMCB_HD void eval(const double (&x)[DMAX], double phi, double& A, double& B, double (&g)[DMAX]) const {
+        const double gg = x[M];
+        double b = 0.0;
+        double gb[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) gb[j] = 0.0;
+#pragma unroll 2
+        for (int i = 0; i < NO; ++i) {
+            const double* row = rows + i * ROW;
+            double xr[C];
+#pragma unroll
+            for (int j = 0; j < C; ++j) xr[j] = row[j];
+            const double yi = row[12], lgi = row[13];
+            double eta = x[0];
+#pragma unroll
+            for (int j = 0; j < C; ++j) eta += x[j + 1] * xr[j];
+            const double lam = exp(eta);
+            double term = yi * eta - lam - lgi;
+            if (lam == 0.0 && yi > 0.0) term = neg_inf();
+            b += term;
+            const double d = yi - lam;
+            gb[0] += d;
+#pragma unroll
+            for (int j = 0; j < C; ++j) gb[j + 1] += d * xr[j];
+        }
+        B = b;
+        const double ig = exp(-gg);
+        double sum = 0.0;
+        g[0] = phi * gb[0];
+#pragma unroll
+        for (int i = 1; i < M; ++i) {
+            const double a = fabs(x[i]) * ig;
+            const double aq = (q == 0.5) ? sqrt(a) : pow(a, q);
+            sum += aq;
+            g[i] = -q * aq / x[i] + phi * gb[i];
+        }
+        A = (2.0 * 0.26236426446749105204 - 0.0 - 3.0 * gg - 1.3 * ig) + gg + (-(M - 1) * gg - sum);
+        g[M] = -3.0 + 1.3 * ig + 1.0 - (M - 1) + q * sum;
+        const double Gam = exp(gg);
+        if (!is_finite(Gam) || Gam <= 0.0) A = neg_inf();
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- Gaussian
+// data = P (D x D row-major, symmetric).  A = 0, B = -x'Px/2, grad B = -P x.  One thread per particle,
+// state in local memory (runtime D <= DMAX); P is read through L1/L2 (all lanes read the same address).
+struct GaussModel {
+    static constexpr int DMAX = 128;
+    static constexpr int STATIC_D = 0;  // runtime dimension
+    const double* P;
+    int D;
+    SMCB_HD explicit GaussModel(const ModelDesc& d, const double* staged) : P(staged), D(d.dim) {}
+    SMCB_HD static int dim_of(const ModelDesc& d) { return d.dim; }
+    SMCB_HD int dim() const { return D; }
+    static int staged_doubles(const ModelDesc&) { return 0; }  // too large for smem at D = 100 with state; use L1/L2
+
+    SMCB_HD void eval(const double (&x)[DMAX], double phi, double& A, double& B, double (&g)[DMAX]) const {
+        double qf = 0.0;
+        for (int i = 0; i < D; ++i) {
+            double acc = 0.0;
+            const double* row = P + (size_t)i * D;
+#pragma unroll 4
+            for (int k = 0; k < D; ++k) acc += row[k] * x[k];
+            g[i] = phi * (-acc);
+            qf += x[i] * acc;
+        }
+        A = 0.0;
+        B = -0.5 * qf;
+    }
+};
+
+}  // namespace smcb

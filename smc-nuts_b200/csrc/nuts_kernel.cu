@@ -1,0 +1,288 @@
+// K1 + K2 + K3 kernels and their C-ABI: model handles, batched logp/grad, the persistent work-queue NUTS
+// transition.  See nuts_lane.cuh for the per-lane algorithm and models.cuh for the densities.
+//
+// Launch shape: persistent grid = (#SMs x resident CTAs) so every SM keeps its FP64 pipe fed; each lane
+// owns one particle at a time and pulls the next index from a global atomic queue (warp-aggregated)
+// when its tree ends, which absorbs the 1..2047-leapfrog raggedness of NUTS trees
+// (/root/reference/smcnuts/proposal/nuts.py:50-53 loops particles serially instead).
+#include <cstring>
+#include <vector>
+
+#include "capi.cuh"
+#include "nuts_lane.cuh"
+
+namespace smcb {
+
+std::string& last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+std::atomic<long long> g_launches{0};
+
+int device_sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <class M> struct LaunchCfg;
+template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 3; };
+template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2; };
+template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1; };
+
+// Model data (y[200]; the 100 x 14 PRMwCD table) is staged once per CTA into shared memory, where every lane
+// reads the same address each step (broadcast, conflict-free).  The Gaussian precision matrix stays in L1/L2.
+template <class M>
+__device__ __forceinline__ const double* stage_model(const ModelDesc& d, double* smem, int staged) {
+    if constexpr (M::STATIC_D != 0) {
+        for (int i = threadIdx.x; i < staged; i += blockDim.x) smem[i] = d.data[i];
+        __syncthreads();
+        return smem;
+    } else {
+        return d.data;
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(LaunchCfg<M>::NT, LaunchCfg<M>::MIN_BLOCKS)
+nuts_transition_kernel(NutsArgs a, int staged, int rec_doubles) {
+    extern __shared__ double smem[];
+    M model(a.model, stage_model<M>(a.model, smem, staged));
+    Lane<M> lane;
+    lane.phase = kIdle;
+    double* ws = a.ws + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * rec_doubles;
+    const unsigned lane_id = threadIdx.x & 31u;
+    bool drained = false;
+    for (;;) {
+        // ---- refill finished lanes from the particle work queue (warp-aggregated atomic)
+        const bool want = (lane.phase == kIdle) && !drained;
+        const unsigned m = __ballot_sync(0xffffffffu, want);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane_id == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) {
+                const long long p = (long long)base + __popc(m & ((1u << lane_id) - 1u));
+                if (p < a.N) lane.begin(a, model, p, ws);
+                else drained = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, lane.phase == kIdle)) break;
+        // ---- one model evaluation per lane per trip: the initial point or one leapfrog
+        if (lane.phase != kIdle) {
+            lane.pre_eval(a);
+            double A, B, g[M::DMAX];
+            model.eval(lane.xa, a.phi, A, B, g);
+            lane.post_eval(a, A, B, g);
+        }
+    }
+}
+
+// Batched value + gradient (one thread per particle).
+template <class M>
+__global__ void __launch_bounds__(128) logp_grad_kernel(ModelDesc md, const double* __restrict__ x, long long N,
+                                                        double phi, double* __restrict__ Aout,
+                                                        double* __restrict__ Bout, double* __restrict__ grad,
+                                                        int staged) {
+    extern __shared__ double smem[];
+    M model(md, stage_model<M>(md, smem, staged));
+    const int D = M::STATIC_D ? M::STATIC_D : model.dim();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        double xv[M::DMAX], g[M::DMAX], A, B;
+#pragma unroll
+        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : D); ++d) xv[d] = x[i * D + d];
+        model.eval(xv, phi, A, B, g);
+        if (Aout) Aout[i] = A;
+        if (Bout) Bout[i] = B;
+        if (grad) {
+            const bool bad = !is_finite(A + phi * B);
+#pragma unroll
+            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : D); ++d) grad[i * D + d] = bad ? neg_inf() : g[d];
+        }
+    }
+}
+
+__global__ void combine_logp_kernel(const double* __restrict__ A, const double* __restrict__ B, double phi,
+                                    long long N, double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double lp = A[i] + phi * B[i];
+        out[i] = is_finite(lp) ? lp : neg_inf();
+    }
+}
+
+template <class M>
+static int launch_nuts(const Model* mdl, NutsArgs a, long long ws_bytes, cudaStream_t st) {
+    const int NT = LaunchCfg<M>::NT;
+    const int D = M::dim_of(mdl->desc);
+    const int staged = M::staged_doubles(mdl->desc);
+    const size_t smem = sizeof(double) * (size_t)staged;
+    auto kern = nuts_transition_kernel<M>;
+    if (smem > 48 * 1024) SMCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) return fail("smcb_nuts_transition", "kernel does not fit on an SM");
+    long long blocks = (long long)device_sm_count() * occ;
+    const long long need = (a.N + NT - 1) / NT;
+    if (blocks > need) blocks = need;
+    const int rec = nuts_ws_doubles(D, a.max_depth);
+    const long long ws_need = (long long)sizeof(double) * rec * blocks * NT + 256;
+    if (ws_bytes < ws_need) return fail("smcb_nuts_transition", "workspace too small (see smcb_nuts_workspace_bytes)");
+    // queue head lives in the last 256 bytes of the workspace
+    a.queue = (unsigned long long*)((char*)a.ws + (ws_need - 256));
+    SMCB_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), st));
+    kern<<<(int)blocks, NT, smem, st>>>(a, staged, rec);
+    return check_launch("nuts_transition_kernel");
+}
+
+template <class M>
+static long long nuts_ws_bytes(const Model* mdl, long long N, int max_depth) {
+    const int NT = LaunchCfg<M>::NT;
+    const int D = M::dim_of(mdl->desc);
+    const size_t smem = sizeof(double) * (size_t)M::staged_doubles(mdl->desc);
+    auto kern = nuts_transition_kernel<M>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) return -1;
+    long long blocks = (long long)device_sm_count() * occ;
+    const long long need = (N + NT - 1) / NT;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    return (long long)sizeof(double) * nuts_ws_doubles(D, max_depth) * blocks * NT + 256;
+}
+
+template <class M>
+static int launch_logp(const Model* mdl, const double* x, long long N, double phi, double* A, double* B, double* g,
+                       cudaStream_t st) {
+    const int staged = M::staged_doubles(mdl->desc);
+    const size_t smem = sizeof(double) * (size_t)staged;
+    const int grid = stride_grid(N, 128, 8);
+    logp_grad_kernel<M><<<grid, 128, smem, st>>>(mdl->desc, x, N, phi, A, B, g, staged);
+    return check_launch("logp_grad_kernel");
+}
+
+}  // namespace smcb
+
+using namespace smcb;
+
+extern "C" {
+
+int smcb_version(void) { return 100; }
+const char* smcb_last_error(void) { return last_error_ref().c_str(); }
+long long smcb_launch_count(void) { return g_launches.load(); }
+
+int smcb_model_create(int kind, const double* host_data, long long n, int dim, void** handle) {
+    SMCB_REQUIRE(handle && host_data && n > 0, "null argument");
+    std::vector<double> packed;
+    ModelDesc d{};
+    d.kind = kind;
+    if (kind == SMCB_MODEL_ARMA) {
+        d.dim = 4; d.T = (int)n;
+        packed.assign(host_data, host_data + n);
+    } else if (kind == SMCB_MODEL_PRMWCD) {
+        SMCB_REQUIRE((n - 1) % 13 == 0, "PRMwCD blob must be [q, y(NO), lgamma(y+1)(NO), X(NO*11)]");
+        const int NO = (int)((n - 1) / 13);
+        d.dim = 13; d.T = NO; d.q = host_data[0];
+        const double *y = host_data + 1, *lg = y + NO, *X = lg + NO;
+        packed.assign((size_t)NO * PrmModel::ROW, 0.0);
+        for (int i = 0; i < NO; ++i) {
+            for (int j = 0; j < 11; ++j) packed[(size_t)i * PrmModel::ROW + j] = X[i * 11 + j];
+            packed[(size_t)i * PrmModel::ROW + 12] = y[i];
+            packed[(size_t)i * PrmModel::ROW + 13] = lg[i];
+        }
+    } else if (kind == SMCB_MODEL_GAUSS) {
+        SMCB_REQUIRE(dim >= 1 && dim <= GaussModel::DMAX && (long long)dim * dim == n, "gauss: need P[D*D], D <= 128");
+        d.dim = dim;
+        packed.assign(host_data, host_data + n);
+    } else {
+        return fail("smcb_model_create", "unknown model kind");
+    }
+    d.n_data = (int)packed.size();
+    Model* m = new Model{d, nullptr};
+    if (cudaMalloc(&m->d_data, sizeof(double) * packed.size()) != cudaSuccess) {
+        delete m;
+        return fail("smcb_model_create", "cudaMalloc failed (is a CUDA device present?)");
+    }
+    SMCB_CUDA(cudaMemcpy(m->d_data, packed.data(), sizeof(double) * packed.size(), cudaMemcpyHostToDevice));
+    m->desc.data = m->d_data;
+    *handle = m;
+    return 0;
+}
+
+int smcb_model_destroy(void* handle) {
+    if (!handle) return 0;
+    Model* m = (Model*)handle;
+    cudaFree(m->d_data);
+    delete m;
+    return 0;
+}
+
+int smcb_model_dim(void* handle) { return handle ? ((Model*)handle)->desc.dim : -1; }
+
+int smcb_logp_grad(void* handle, const double* x, long long N, double phi, double* A, double* B, double* grad,
+                   void* stream) {
+    SMCB_REQUIRE(handle && x && N >= 0, "bad argument");
+    if (N == 0) return 0;
+    const Model* m = (const Model*)handle;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (m->desc.kind) {
+        case kArma: return launch_logp<ArmaModel>(m, x, N, phi, A, B, grad, st);
+        case kPRMwCD: return launch_logp<PrmModel>(m, x, N, phi, A, B, grad, st);
+        default: return launch_logp<GaussModel>(m, x, N, phi, A, B, grad, st);
+    }
+}
+
+int smcb_combine_logp(const double* A, const double* B, double phi, long long N, double* out, void* stream) {
+    SMCB_REQUIRE(A && B && out && N >= 0, "bad argument");
+    if (N == 0) return 0;
+    combine_logp_kernel<<<stride_grid(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(A, B, phi, N, out);
+    return check_launch("combine_logp_kernel");
+}
+
+int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long long* bytes) {
+    SMCB_REQUIRE(handle && bytes && N >= 0, "bad argument");
+    SMCB_REQUIRE(max_depth >= 1 && max_depth <= 10, "max_depth must be in [1, 10] (reference: MAX_TREE_DEPTH = 10)");
+    const Model* m = (const Model*)handle;
+    long long b;
+    switch (m->desc.kind) {
+        case kArma: b = nuts_ws_bytes<ArmaModel>(m, N, max_depth); break;
+        case kPRMwCD: b = nuts_ws_bytes<PrmModel>(m, N, max_depth); break;
+        default: b = nuts_ws_bytes<GaussModel>(m, N, max_depth); break;
+    }
+    if (b < 0) return fail("smcb_nuts_workspace_bytes", "occupancy query failed");
+    *bytes = b;
+    return 0;
+}
+
+int smcb_nuts_transition(void* handle, const double* x, const double* r, long long N, double eps, double phi,
+                         int max_depth, int accrej, uint64_t seed, uint32_t iteration, uint64_t particle0,
+                         double* x_new, double* r_new, double* A_old, double* B_old, double* A_new, double* B_new,
+                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth, void* workspace,
+                         long long workspace_bytes, void* stream) {
+    SMCB_REQUIRE(handle && x && r && x_new && r_new && workspace, "null argument");
+    SMCB_REQUIRE(x != x_new && r != r_new, "x_new/r_new must not alias x/r");
+    SMCB_REQUIRE(max_depth >= 1 && max_depth <= 10, "max_depth must be in [1, 10] (reference: MAX_TREE_DEPTH = 10)");
+    SMCB_REQUIRE(iteration < (1u << 24), "iteration must be < 2^24");
+    if (N <= 0) return N == 0 ? 0 : fail("smcb_nuts_transition", "negative N");
+    const Model* m = (const Model*)handle;
+    NutsArgs a{};
+    a.model = m->desc;
+    a.x = x; a.r = r; a.N = N; a.eps = eps; a.phi = phi; a.max_depth = max_depth; a.accrej = accrej;
+    a.seed = seed; a.iteration = iteration; a.particle0 = particle0;
+    a.x_new = x_new; a.r_new = r_new; a.A_old = A_old; a.B_old = B_old; a.A_new = A_new; a.B_new = B_new;
+    a.ke_old = ke_old; a.ke_new = ke_new; a.n_leapfrog = n_leapfrog; a.accepted = accepted; a.depth = depth;
+    a.ws = (double*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (m->desc.kind) {
+        case kArma: return launch_nuts<ArmaModel>(m, a, workspace_bytes, st);
+        case kPRMwCD: return launch_nuts<PrmModel>(m, a, workspace_bytes, st);
+        default: return launch_nuts<GaussModel>(m, a, workspace_bytes, st);
+    }
+}
+
+}  // extern "C"

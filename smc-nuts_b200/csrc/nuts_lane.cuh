@@ -1,0 +1,312 @@
+// K2/K3 -- one lane of the batched iterative NUTS transition.
+//
+// Re-derivation (not a translation) of the recursive sampler in
+//   /root/reference/smcnuts/proposal/nuts.py:58-112 (generate_nuts_samples), :114-150 (build_tree),
+//   :152-160 (stop_criterion), :162-175 (NUTSLeapfrog) and the endpoint MH step of
+//   /root/reference/smcnuts/proposal/nuts_acc_rej.py:42-49 + utils.py:22-34
+// as an explicit state machine that advances ONE leapfrog per step, so that 32 lanes holding 32
+// different particles at different tree positions stay converged on the expensive model evaluation
+// and a finished lane can be refilled from the particle work queue.
+//
+// Tree bookkeeping without recursion (per lane):
+//   * registers hold the ACTIVE edge (x, r, g) = the end of the trajectory that the current doubling
+//     extends (side `dir`); the other edge, the U-turn checkpoints and the candidate store live in the
+//     lane's workspace record in global memory (L1/L2 resident; touched O(1) times per leapfrog).
+//   * U-turn checkpoints: the first state of every pending sub-tree is written once, at the even
+//     0-based leaf f that starts it, into slot popc(f); the sub-tree of 2^(l+1) leaves that ends at
+//     0-based leaf i reads slot popc(i - 2^(l+1) + 1).  Slots of live sub-trees never collide.
+//   * candidates: pending first children keep (count, slot-reference) per level, packed into two
+//     64-bit registers; a candidate is materialised in the store only when it survives its merges.
+//   * merges happen in post-order after leaf i for levels 0..ctz(i)-1, consuming one uniform each,
+//     exactly the draw order of the recursion (nuts.py:142); any stop (divergence nuts.py:125 or
+//     sub-tree U-turn nuts.py:148) ends the transition at once, because the reference then never
+//     reads the sub-tree's candidate nor draws again from this particle's stream.
+//
+// The selected sample is written straight into the caller's x_new/r_new row (owned by this lane).
+#pragma once
+#include "common.cuh"
+#include "models.cuh"
+#include "philox.cuh"
+
+namespace smcb {
+
+struct NutsArgs {
+    ModelDesc model;
+    const double* x;      // [N, D] current positions
+    const double* r;      // [N, D] current momenta
+    long long N;
+    double eps, phi;
+    int max_depth;        // reference: MAX_TREE_DEPTH = 10 (nuts.py:4) -> at most max_depth+1 doublings
+    int accrej;           // fuse the endpoint MH step (NUTSProposalWithAccRej)
+    uint64_t seed;
+    uint32_t iteration;
+    uint64_t particle0;   // global index of local particle 0 (multi-GPU sharding)
+    double* x_new;        // [N, D]
+    double* r_new;        // [N, D]
+    double* A_old;        // [N] log prior + Jacobian at x           (nullable)
+    double* B_old;        // [N] log likelihood at x                 (nullable)
+    double* A_new;        // [N] same at the returned x_new          (nullable)
+    double* B_new;        // [N]                                     (nullable)
+    double* ke_old;       // [N] 0.5*|r|^2                           (nullable)
+    double* ke_new;       // [N] 0.5*|r_new|^2                       (nullable)
+    int* n_leapfrog;      // [N] leapfrog steps = gradient evaluations excluding the initial one (nullable)
+    int* accepted;        // [N] MH outcome (1 when accrej == 0)     (nullable)
+    int* depth;           // [N] number of doublings                 (nullable)
+    double* ws;           // workspace: lanes * ws_doubles(D, max_depth)
+    unsigned long long* queue;  // work-queue head, zeroed before launch
+};
+
+SMCB_HD int nuts_ws_doubles(int D, int L) { return 3 * D + 2 * D * L + (2 * D + 2) * (L + 1); }
+
+enum LanePhase : int { kIdle = 0, kInit = 1, kLeaf = 2 };
+
+template <class M>
+struct Lane {
+    static constexpr int DM = M::DMAX;
+    double xa[DM], ra[DM], ga[DM];  // active edge
+    double logu, A0, B0, As, Bs, ke0;
+    long long pid;
+    double* ws;
+    int phase, dir, depth, D, L;
+    uint32_t leaf, n_tot, n_leapfrog, free_mask;
+    uint64_t pend_n, pend_ref;
+    StreamReader rng;
+
+    // ---- workspace views
+    SMCB_HD double* other() const { return ws; }                                   // x, r, g of the inactive edge
+    SMCB_HD double* ckpt(int slot) const { return ws + 3 * D + 2 * D * slot; }      // x, r
+    SMCB_HD double* cand(int slot) const { return ws + 3 * D + 2 * D * L + (2 * D + 2) * slot; }  // x, r, A, B
+
+    // ---- packed per-level pending counts: level l occupies bits [l(l+1)/2, +l+1)
+    SMCB_HD uint32_t get_n(int l) const { return (uint32_t)(pend_n >> (l * (l + 1) / 2)) & ((2u << l) - 1u); }
+    SMCB_HD void set_n(int l, uint32_t v) {
+        const int sh = l * (l + 1) / 2;
+        const uint64_t mask = (uint64_t)((2u << l) - 1u) << sh;
+        pend_n = (pend_n & ~mask) | ((uint64_t)v << sh);
+    }
+    SMCB_HD int get_ref(int l) const { return (int)((pend_ref >> (4 * l)) & 15u); }
+    SMCB_HD void set_ref(int l, int s) { pend_ref = (pend_ref & ~((uint64_t)15 << (4 * l))) | ((uint64_t)s << (4 * l)); }
+
+    SMCB_HD int dimension(const M& m) const { return M::STATIC_D ? M::STATIC_D : m.dim(); }
+
+    SMCB_HD void begin(const NutsArgs& a, const M& m, long long p, double* ws_) {
+        pid = p; ws = ws_; D = dimension(m); L = a.max_depth;
+        const int d_ = D;
+#pragma unroll
+        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
+            xa[d] = a.x[p * d_ + d];
+            ra[d] = a.r[p * d_ + d];
+        }
+        rng.reset(a.seed, a.iteration, kStreamNuts, a.particle0 + (uint64_t)p);
+        n_leapfrog = 0;
+        phase = kInit;
+    }
+
+    // first half of the leapfrog (nuts.py:169-170); nothing to do before the initial evaluation
+    SMCB_HD void pre_eval(const NutsArgs& a) {
+        if (phase != kLeaf) return;
+        const double half = dir * a.eps / 2, full = dir * a.eps;
+        const int d_ = D;
+#pragma unroll
+        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
+            ra[d] = ra[d] + half * ga[d];
+            xa[d] = xa[d] + full * ra[d];
+        }
+    }
+
+    SMCB_HD void start_doubling(bool first) {
+        const int nd = (rng.next() < 0.5) ? 1 : -1;  // nuts.py:91
+        if (!first && nd != dir) {                   // bring the other edge into registers
+            double* o = other();
+            const int d_ = D;
+#pragma unroll
+            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
+                double t;
+                t = o[d]; o[d] = xa[d]; xa[d] = t;
+                t = o[d_ + d]; o[d_ + d] = ra[d]; ra[d] = t;
+                t = o[2 * d_ + d]; o[2 * d_ + d] = ga[d]; ga[d] = t;
+            }
+        }
+        dir = nd;
+        leaf = 0; pend_n = 0; pend_ref = 0;
+        free_mask = (2u << L) - 1u;
+    }
+
+    // U-turn test between a stored edge (xc, rc) and the active edge (nuts.py:152-160); the edge order
+    // (minus, plus) is restored through `dir`.
+    SMCB_HD bool uturn(const double* xc, const double* rc) const {
+        double s1 = 0.0, s2 = 0.0;
+        const int d_ = D;
+#pragma unroll
+        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
+            const double dx = xa[d] - xc[d];
+            s1 += dx * rc[d];
+            s2 += dx * ra[d];
+        }
+        return (dir * s1 < 0) || (dir * s2 < 0);
+    }
+
+    SMCB_HD void write_sample_from_active(const NutsArgs& a, double A, double B) {
+        const int d_ = D;
+#pragma unroll
+        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
+            a.x_new[pid * d_ + d] = xa[d];
+            a.r_new[pid * d_ + d] = ra[d];
+        }
+        As = A; Bs = B;
+    }
+
+    // Consume the model evaluation at xa.  Returns true when the transition is complete.
+    SMCB_HD bool post_eval(const NutsArgs& a, double A, double B, const double (&gn)[DM]) {
+        const int d_ = D;
+        double lp = A + a.phi * B;
+        const bool bad = !is_finite(lp);  // bridgestan.py:47-49,79-80: failure -> logp = -inf, grad = -inf
+        if (bad) lp = neg_inf();
+#pragma unroll
+        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) ga[d] = bad ? neg_inf() : gn[d];
+
+        if (phase == kInit) {  // nuts.py:66-87
+            double rr = 0.0;
+#pragma unroll
+            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) rr += ra[d] * ra[d];
+            ke0 = 0.5 * rr;
+            A0 = A; B0 = B;
+            const double H0 = lp - ke0;
+            logu = H0 - (-log1p(-rng.next()));
+            write_sample_from_active(a, A, B);
+            double* o = other();
+#pragma unroll
+            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
+                o[d] = xa[d]; o[d_ + d] = ra[d]; o[2 * d_ + d] = ga[d];
+            }
+            n_tot = 1; depth = 0;
+            start_doubling(true);
+            phase = kLeaf;
+            return false;
+        }
+
+        // ---- leaf: second half-kick, slice and divergence tests (nuts.py:121-125,173)
+        const double half = dir * a.eps / 2;
+        double rr = 0.0;
+#pragma unroll
+        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
+            ra[d] = ra[d] + half * ga[d];
+            rr += ra[d] * ra[d];
+        }
+        ++n_leapfrog;
+        ++leaf;
+        const double joint = lp - 0.5 * rr;
+        if ((logu - 100.) >= joint) { ++depth; return finish(a); }
+        uint32_t run_n = (logu < joint) ? 1u : 0u;
+        int run_ref = -1;  // -1: the candidate is the leaf in registers
+        const uint32_t nleaves = 1u << depth;
+        if (nleaves > 1u) {
+            const uint32_t i0 = leaf - 1u;
+            if ((i0 & 1u) == 0u) {
+                double* c = ckpt(popc32(i0));
+#pragma unroll
+                for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) { c[d] = xa[d]; c[d_ + d] = ra[d]; }
+            } else {
+                const int tz = ctz32(leaf);
+                for (int l = 0; l < tz; ++l) {  // nuts.py:136-148, second child = running node
+                    const uint32_t n1 = get_n(l);
+                    const int ref1 = get_ref(l);
+                    const uint32_t tot = n1 + run_n;
+                    const double u = rng.next();
+                    const double denom = (double)tot > 1. ? (double)tot : 1.;
+                    if (u < ((double)run_n / denom)) {
+                        free_mask |= 1u << ref1;
+                    } else {
+                        if (run_ref >= 0) free_mask |= 1u << run_ref;
+                        run_ref = ref1;
+                    }
+                    run_n = tot;
+                    const double* c = ckpt(popc32(i0 - (2u << l) + 1u));
+                    if (uturn(c, c + d_)) { ++depth; return finish(a); }
+                }
+            }
+        }
+        if (leaf == nleaves) {  // doubling complete and not stopped: nuts.py:99-110
+            const double ratio = (double)run_n / (double)n_tot;
+            if (rng.next() < (ratio < 1. ? ratio : 1.)) {
+                if (run_ref < 0) {
+                    write_sample_from_active(a, A, B);
+                } else {
+                    const double* c = cand(run_ref);
+#pragma unroll
+                    for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
+                        a.x_new[pid * d_ + d] = c[d];
+                        a.r_new[pid * d_ + d] = c[d_ + d];
+                    }
+                    As = c[2 * d_]; Bs = c[2 * d_ + 1];
+                }
+            }
+            n_tot += run_n;
+            const double* o = other();
+            const bool stop = uturn(o, o + d_);
+            ++depth;
+            if (stop || depth > L) return finish(a);
+            start_doubling(false);
+            return false;
+        }
+        // park the running node as the pending first child of level ctz(leaf)
+        const int lv = ctz32(leaf);
+        if (run_ref < 0) {
+            run_ref = ctz32(free_mask);
+            free_mask &= ~(1u << run_ref);
+            double* c = cand(run_ref);
+#pragma unroll
+            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) { c[d] = xa[d]; c[d_ + d] = ra[d]; }
+            c[2 * d_] = A; c[2 * d_ + 1] = B;
+        }
+        set_n(lv, run_n);
+        set_ref(lv, run_ref);
+        return false;
+    }
+
+    // End of transition: optional endpoint MH step (nuts_acc_rej.py:42-49, utils.py:22-34) and outputs.
+    SMCB_HD bool finish(const NutsArgs& a) {
+        const int d_ = D;
+        double rr = 0.0;
+        bool anyinf = false;
+#pragma unroll 4
+        for (int d = 0; d < d_; ++d) {
+            const double rv = a.r_new[pid * d_ + d], xv = a.x_new[pid * d_ + d];
+            rr += rv * rv;
+            anyinf |= (xv == -neg_inf()) || (xv == neg_inf());
+        }
+        double ken = 0.5 * rr;
+        int acc = 1;
+        if (a.accrej) {
+            double lps = As + a.phi * Bs, lp0 = A0 + a.phi * B0;
+            if (!is_finite(lps)) lps = neg_inf();
+            if (!is_finite(lp0)) lp0 = neg_inf();
+            const double H1 = lps - ken, H0 = lp0 - ke0;
+            const double ratio = exp(H1 - H0);
+            const double prob = (ratio < 1.) ? ratio : 1.;  // python min(1., ratio): nan -> 1.
+            const double u = stream_uniform(a.seed, a.iteration, kStreamAccRej, a.particle0 + (uint64_t)pid, 0);
+            if (u > prob || anyinf) {
+                acc = 0;
+#pragma unroll 4
+                for (int d = 0; d < d_; ++d) {
+                    a.x_new[pid * d_ + d] = a.x[pid * d_ + d];
+                    a.r_new[pid * d_ + d] = a.r[pid * d_ + d];
+                }
+                As = A0; Bs = B0; ken = ke0;
+            }
+        }
+        if (a.A_old) a.A_old[pid] = A0;
+        if (a.B_old) a.B_old[pid] = B0;
+        if (a.A_new) a.A_new[pid] = As;
+        if (a.B_new) a.B_new[pid] = Bs;
+        if (a.ke_old) a.ke_old[pid] = ke0;
+        if (a.ke_new) a.ke_new[pid] = ken;
+        if (a.n_leapfrog) a.n_leapfrog[pid] = (int)n_leapfrog;
+        if (a.accepted) a.accepted[pid] = acc;
+        if (a.depth) a.depth[pid] = depth;
+        phase = kIdle;
+        return true;
+    }
+};
+
+}  // namespace smcb

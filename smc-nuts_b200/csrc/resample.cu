@@ -1,0 +1,233 @@
+// K9, K10, K11 -- resampling: block-scan prefix sum of the normalised weights, ancestor search,
+// coalesced particle gather.
+//
+// Replaces `rng.choice(arange(N), N, p=wn)` + `x[i_new]` (/root/reference/smcnuts/samples/samples.py:138-140,
+// estimate_from_tempered.py:42-44).  numpy's choice is cdf = cumsum(p); cdf /= cdf[-1];
+// searchsorted(cdf, uniforms, side='right') -- verified bit-identical in tests/golden/make_golden.py --
+// so given the same cdf and the same uniforms the ancestor indices here are bit-exact.
+// The scan is reduce-then-scan over 2048-element tiles with a fixed summation tree (deterministic).
+#include "capi.cuh"
+
+namespace smcb {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ double warp_incl_scan(double v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// inclusive block scan of one value per thread; returns the thread's inclusive prefix and the block total
+__device__ __forceinline__ double block_incl_scan(double v, double* total) {
+    __shared__ double wsum[kScanThreads / 32];
+    __shared__ double btotal;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double incl = warp_incl_scan(v);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        double w = (lane < kScanThreads / 32) ? wsum[lane] : 0.0;
+        const double wi = warp_incl_scan(w);
+        if (lane < kScanThreads / 32) wsum[lane] = wi - w;  // exclusive warp offsets
+        if (lane == kScanThreads / 32 - 1) btotal = wi;
+    }
+    __syncthreads();
+    const double r = incl + wsum[warp];
+    *total = btotal;
+    __syncthreads();
+    return r;
+}
+
+// phase 1: per-tile sums.  Threads own kScanItems CONSECUTIVE elements (blocked arrangement via smem transpose).
+__global__ void __launch_bounds__(kScanThreads) tile_sum_kernel(const double* __restrict__ w, long long N,
+                                                                 double* __restrict__ tile_sums, long long ntiles) {
+    __shared__ double sm[kTile + kTile / 32];
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * kTile;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = k * kScanThreads + threadIdx.x;
+            sm[e + e / 32] = (base + e < N) ? w[base + e] : 0.0;
+        }
+        __syncthreads();
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = threadIdx.x * kScanItems + k;
+            s += sm[e + e / 32];
+        }
+        double total;
+        block_incl_scan(s, &total);
+        if (threadIdx.x == 0) tile_sums[tile] = total;
+    }
+}
+
+// phase 2: exclusive scan of the tile sums by one block (sequential carry across chunks), grand total
+__global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(double* tile_sums, long long ntiles,
+                                                                  const double* __restrict__ offset_in,
+                                                                  const double* __restrict__ total_in,
+                                                                  double* total_out, double* norm_total) {
+    double carry = offset_in ? *offset_in : 0.0;
+    const double carry0 = carry;
+    for (long long c0 = 0; c0 < ntiles; c0 += kScanThreads) {
+        const long long i = c0 + threadIdx.x;
+        const double v = (i < ntiles) ? tile_sums[i] : 0.0;
+        double total;
+        const double incl = block_incl_scan(v, &total);
+        if (i < ntiles) tile_sums[i] = carry + (incl - v);
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        total_out[0] = carry - carry0;                    // this rank's local weight total
+        norm_total[0] = total_in ? *total_in : carry;     // normaliser: global total when sharded
+    }
+}
+
+// phase 3: scan each tile, add its offset, normalise: cdf = prefix / total  (numpy: cdf /= cdf[-1])
+__global__ void __launch_bounds__(kScanThreads) tile_cdf_kernel(const double* __restrict__ w, long long N,
+                                                                 const double* __restrict__ tile_offsets,
+                                                                 const double* __restrict__ norm_total,
+                                                                 double* __restrict__ cdf, long long ntiles) {
+    __shared__ double sm[kTile + kTile / 32];
+    const double tot = *norm_total;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * kTile;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = k * kScanThreads + threadIdx.x;
+            sm[e + e / 32] = (base + e < N) ? w[base + e] : 0.0;
+        }
+        __syncthreads();
+        double v[kScanItems], s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = threadIdx.x * kScanItems + k;
+            s += sm[e + e / 32];
+            v[k] = s;
+        }
+        double total;
+        const double incl = block_incl_scan(s, &total);
+        const double off = tile_offsets[tile] + (incl - s);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = threadIdx.x * kScanItems + k;
+            sm[e + e / 32] = (off + v[k]) / tot;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = k * kScanThreads + threadIdx.x;
+            if (base + e < N) cdf[base + e] = sm[e + e / 32];
+        }
+        __syncthreads();
+    }
+}
+
+// first index with cdf[idx] > u  (numpy searchsorted side='right'), clamped to N-1
+__device__ __forceinline__ long long upper_bound(const double* __restrict__ cdf, long long N, double u) {
+    long long lo = 0, hi = N;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (u < cdf[mid]) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo < N ? lo : N - 1;
+}
+
+__global__ void ancestors_multinomial_kernel(const double* __restrict__ cdf, long long N, const double* __restrict__ u,
+                                             long long M, int64_t* __restrict__ idx) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x)
+        idx[j] = upper_bound(cdf, N, u[j]);
+}
+
+__global__ void ancestors_systematic_kernel(const double* __restrict__ cdf, long long N, double u0, long long j0,
+                                            long long M_total, long long M, int64_t* __restrict__ idx) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x) {
+        const double pos = ((double)(j0 + j) + u0) / (double)M_total;
+        idx[j] = upper_bound(cdf, N, pos);
+    }
+}
+
+// out[j, :] = x[idx[j], :].  VEC doubles per thread (16-byte accesses when D is even).
+template <int VEC>
+__global__ void gather_rows_kernel(const double* __restrict__ x, const int64_t* __restrict__ idx, long long M, int D,
+                                   double* __restrict__ out) {
+    const int cpr = D / VEC;  // chunks per row
+    const long long total = M * cpr;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long j = t / cpr;
+        const int c = (int)(t - j * cpr);
+        const long long src = idx[j];
+        if (VEC == 2) {
+            const double2 v = *reinterpret_cast<const double2*>(x + src * D + 2 * c);
+            *reinterpret_cast<double2*>(out + j * D + 2 * c) = v;
+        } else {
+            out[j * D + c] = x[src * D + c];
+        }
+    }
+}
+
+}  // namespace smcb
+
+using namespace smcb;
+
+extern "C" {
+
+long long smcb_scan_workspace_bytes(long long N) {
+    const long long ntiles = (N + kTile - 1) / kTile;
+    return (ntiles + 8) * 8;
+}
+
+int smcb_cdf(const double* wn, long long N, const double* offset_in, const double* total_in, double* cdf,
+             double* total_out, void* workspace, void* stream) {
+    SMCB_REQUIRE(wn && cdf && total_out && workspace && N >= 1, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ntiles = (N + kTile - 1) / kTile;
+    double* tile_sums = (double*)workspace;
+    double* norm_total = tile_sums + ntiles;
+    const long long cap = (long long)device_sm_count() * 8;
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    tile_sum_kernel<<<grid, kScanThreads, 0, st>>>(wn, N, tile_sums, ntiles);
+    if (check_launch("tile_sum_kernel")) return -1;
+    tile_scan_kernel<<<1, kScanThreads, 0, st>>>(tile_sums, ntiles, offset_in, total_in, total_out, norm_total);
+    if (check_launch("tile_scan_kernel")) return -1;
+    tile_cdf_kernel<<<grid, kScanThreads, 0, st>>>(wn, N, tile_sums, norm_total, cdf, ntiles);
+    return check_launch("tile_cdf_kernel");
+}
+
+int smcb_ancestors_multinomial(const double* cdf, long long N, const double* u, long long M, int64_t* idx,
+                               void* stream) {
+    SMCB_REQUIRE(cdf && u && idx && N >= 1 && M >= 0, "bad argument");
+    if (M == 0) return 0;
+    ancestors_multinomial_kernel<<<stride_grid(M, 256, 8), 256, 0, (cudaStream_t)stream>>>(cdf, N, u, M, idx);
+    return check_launch("ancestors_multinomial_kernel");
+}
+
+int smcb_ancestors_systematic(const double* cdf, long long N, double u0, long long j0, long long M_total,
+                              long long M, int64_t* idx, void* stream) {
+    SMCB_REQUIRE(cdf && idx && N >= 1 && M >= 0 && M_total >= 1, "bad argument");
+    if (M == 0) return 0;
+    ancestors_systematic_kernel<<<stride_grid(M, 256, 8), 256, 0, (cudaStream_t)stream>>>(cdf, N, u0, j0, M_total, M, idx);
+    return check_launch("ancestors_systematic_kernel");
+}
+
+int smcb_gather_rows(const double* x, const int64_t* idx, long long M, int D, double* out, void* stream) {
+    SMCB_REQUIRE(x && idx && out && M >= 0 && D >= 1, "bad argument");
+    SMCB_REQUIRE(x != out, "gather cannot run in place");
+    if (M == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec2 = (D % 2 == 0) && (((uintptr_t)x | (uintptr_t)out) % 16 == 0);
+    if (vec2) gather_rows_kernel<2><<<stride_grid(M * (D / 2), 256, 8), 256, 0, st>>>(x, idx, M, D, out);
+    else gather_rows_kernel<1><<<stride_grid(M * D, 256, 8), 256, 0, st>>>(x, idx, M, D, out);
+    return check_launch("gather_rows_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""Device plumbing: torch owns memory and streams, the C-ABI gets raw pointers.
+
+Nothing here computes; every numeric operation is a call into libsmcnuts_b200.so.
+"""
+import numpy as np
+import torch
+
+from . import _cabi
+
+F64 = torch.float64
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise _cabi.SmcbError("smcnuts device path needs a CUDA device (no CPU fallback exists)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def is_host(a):
+    return not isinstance(a, torch.Tensor)
+
+
+def to_device(a, dtype=F64):
+    """numpy / torch(any device) -> contiguous CUDA tensor (no copy if already there)."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device(), dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device())
+
+
+def like_input(t, ref):
+    """Return `t` in the container type of `ref` (numpy in -> numpy out)."""
+    if is_host(ref):
+        return t.cpu().numpy()
+    return t
+
+
+def empty(*shape, dtype=F64):
+    return torch.empty(*shape, dtype=dtype, device=device())
+
+
+def zeros(*shape, dtype=F64):
+    return torch.zeros(*shape, dtype=dtype, device=device())
+
+
+_WS = {}
+
+
+def workspace(tag, nbytes):
+    """Grow-only scratch buffers keyed by purpose (the library never allocates)."""
+    key = (tag, torch.cuda.current_device())
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device())
+        _WS[key] = buf
+    return buf
+
+
+def reduce_ws():
+    return workspace("reduce", _cabi.lib().smcb_reduce_workspace_bytes())
+
+
+def seed_from_rng(rng):
+    """Map the reference's `rng` argument to a 64-bit Philox seed.
+
+    int -> used as is; numpy Generator / RandomState -> one draw from it (so runs stay reproducible
+    from the caller's seed); anything with a `.seed` int attribute -> that; None -> 0.
+    """
+    if rng is None:
+        return 0
+    if isinstance(rng, (int, np.integer)):
+        return int(rng) & (2 ** 64 - 1)
+    if isinstance(rng, np.random.Generator):
+        return int(rng.integers(0, 2 ** 63 - 1))
+    if isinstance(rng, np.random.RandomState):
+        return int(rng.randint(0, 2 ** 31 - 1)) | (int(rng.randint(0, 2 ** 31 - 1)) << 31)
+    if hasattr(rng, "seed") and isinstance(getattr(rng, "seed"), (int, np.integer)):
+        return int(rng.seed)
+    raise TypeError(f"cannot derive a Philox seed from rng={rng!r}")
+
+
+def is_std_normal(dist, dim):
+    """True for N(0, I_dim): our StdNormal or a scipy frozen multivariate_normal with mean 0, cov I."""
+    from .distributions import StdNormal
+    if isinstance(dist, StdNormal):
+        return dist.dim == dim
+    mean, cov = getattr(dist, "mean", None), getattr(dist, "cov", None)
+    if mean is None or cov is None or callable(mean):
+        return False
+    mean, cov = np.atleast_1d(np.asarray(mean, dtype=float)), np.atleast_2d(np.asarray(cov, dtype=float))
+    return mean.shape == (dim,) and cov.shape == (dim, dim) and not mean.any() and np.array_equal(cov, np.eye(dim))

@@ -1,0 +1,37 @@
+"""Estimate -- importance-sampling mean/variance (reference: smcnuts/estimate/estimate.py).
+
+mean = wn' c(x), var = wn' (c(x) - mean)^2 in constrained space when the target has `constrained_dim`
+(estimate.py:25-28,91-95); the constrain transform (bridgestan.py:93-120: exp on the last coordinate for
+the shipped models) is fused into the moment kernel instead of N BridgeStan calls.
+"""
+from .. import _cabi, _device as dev
+from ..parallel import ShardContext
+
+
+class Estimate:
+    def __init__(self, target, shard: ShardContext = None):
+        self.target = target
+        self.shard = shard or ShardContext()
+        if hasattr(self.target, "constrained_dim"):
+            self._constrain = getattr(self.target, "constrain_kind", _cabi.CONSTRAIN_EXP_LAST)
+        else:
+            self._constrain = _cabi.CONSTRAIN_NONE
+
+    def return_estimate(self, x, wn):
+        return self._estimate(x, wn, self._constrain)
+
+    def return_estimate_unconstrained(self, x, wn):
+        return self._estimate(x, wn, _cabi.CONSTRAIN_NONE)
+
+    def _estimate(self, x, wn, constrain=_cabi.CONSTRAIN_NONE):
+        xd, wd = dev.to_device(x), dev.to_device(wn)
+        N, D = xd.shape
+        mean, var = dev.empty(D), dev.empty(D)
+        ws, st = dev.reduce_ws(), dev.stream_ptr()
+        _cabi.call("smcb_weighted_moment", dev.ptr(xd), dev.ptr(wd), N, D, constrain, 0, 1, dev.ptr(mean),
+                   dev.ptr(ws), st)
+        self.shard.all_reduce_sum_(mean)
+        _cabi.call("smcb_weighted_moment", dev.ptr(xd), dev.ptr(wd), N, D, constrain, dev.ptr(mean), 2, dev.ptr(var),
+                   dev.ptr(ws), st)
+        self.shard.all_reduce_sum_(var)
+        return dev.like_input(mean, x), dev.like_input(var, x)

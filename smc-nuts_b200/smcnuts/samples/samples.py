@@ -1,0 +1,326 @@
+"""Samples -- the device-resident particle set and its per-iteration operations.
+
+Mirrors smcnuts/samples/samples.py of the reference (same constructor, same method names, same
+attributes), with every array a float64 CUDA tensor in the reference's row-major [N, D] layout and every
+operation a kernel behind include/smcnuts_b200.h.  When a torch.distributed process group exists the
+particle set is sharded (rank p owns [p*N/P, (p+1)*N/P)); `N` is always the GLOBAL particle count.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .. import _cabi, _device as dev
+from ..lkernel.forward_lkernel import ForwardLKernel
+from ..lkernel.gaussian_lkernel import GaussianApproxLKernel
+from ..parallel import ShardContext, split_counts, systematic_slot_bounds
+from ..tempering.adaptive_tempering import ESSTempering
+
+
+def normalise(logw, shard):
+    """samples.py:91-113 -> (wn, stats) where stats is a device tensor [logZ, ESS] (global when sharded)."""
+    n = logw.shape[0]
+    st = dev.stream_ptr()
+    tri = dev.empty(3)
+    _cabi.call("smcb_lse_partial", dev.ptr(logw), n, dev.ptr(tri), dev.ptr(dev.reduce_ws()), st)
+    tris = shard.all_gather_vec(tri).contiguous()
+    stats = dev.empty(2)
+    _cabi.call("smcb_lse_finalize", dev.ptr(tris), shard.world, dev.ptr(stats), st)
+    wn = dev.empty(n)
+    _cabi.call("smcb_normalise", dev.ptr(logw), n, dev.ptr(stats), dev.ptr(wn), st)
+    return wn, stats, tris
+
+
+class Resampler:
+    """Ancestor selection + particle gather (samples.py:125-146).
+
+    scheme "multinomial": numpy `rng.choice` semantics (cdf + upper-bound search of one uniform per slot).
+    scheme "systematic" : positions (j + u0)/N (north_star; not in the reference).
+    Sharded: global exclusive scan of the rank weight totals, then all-to-all-v migration of particle rows.
+    """
+
+    def __init__(self, N, seed, shard, stream=_cabi.STREAM_RESAMPLE, scheme="multinomial"):
+        if scheme not in ("multinomial", "systematic"):
+            raise ValueError("resampling scheme must be 'multinomial' or 'systematic'")
+        self.N, self.seed, self.shard, self.stream, self.scheme = N, seed, shard, stream, scheme
+        self.n_local = shard.local_count(N)
+        self.offset = shard.offset(N)
+        self.last_idx = None          # ancestors of the last resample (global indices for this rank's slots)
+        self.last_migrated_rows = 0   # rows this rank received from other ranks (diagnostic)
+
+    def _cdf(self, wn):
+        n, st, sh = wn.shape[0], dev.stream_ptr(), self.shard
+        ws = dev.workspace("scan", _cabi.lib().smcb_scan_workspace_bytes(n))
+        cdf, total = dev.empty(n), dev.empty(1)
+        if sh.world == 1:
+            _cabi.call("smcb_cdf", dev.ptr(wn), n, 0, 0, dev.ptr(cdf), dev.ptr(total), dev.ptr(ws), st)
+            return cdf
+        # rank totals -> exclusive offsets (sequential fp64 sum in rank order, identical on every rank)
+        tmp = dev.empty(n)
+        _cabi.call("smcb_cdf", dev.ptr(wn), n, 0, 0, dev.ptr(tmp), dev.ptr(total), dev.ptr(ws), st)
+        totals = sh.all_gather_vec(total).view(-1).cpu().numpy()
+        off = np.concatenate([[0.0], np.cumsum(totals)])
+        off_t = torch.tensor([off[sh.rank], off[-1]], dtype=torch.float64).to(wn.device)
+        _cabi.call("smcb_cdf", dev.ptr(wn), n, off_t.data_ptr(), off_t.data_ptr() + 8, dev.ptr(cdf), dev.ptr(total),
+                   dev.ptr(ws), st)
+        return cdf
+
+    def resample_rows(self, x, wn, iteration):
+        """Returns the resampled rows for this rank's output slots."""
+        sh, st = self.shard, dev.stream_ptr()
+        n, D = x.shape
+        cdf = self._cdf(wn)
+        if sh.world == 1:
+            idx = dev.empty(n, dtype=torch.int64)
+            if self.scheme == "multinomial":
+                u = dev.empty(n)
+                _cabi.call("smcb_uniforms", self.seed, iteration, self.stream, 0, n, 0, dev.ptr(u), st)
+                _cabi.call("smcb_ancestors_multinomial", dev.ptr(cdf), n, dev.ptr(u), n, dev.ptr(idx), st)
+            else:
+                _cabi.call("smcb_ancestors_systematic", dev.ptr(cdf), n, self._u0(iteration), 0, n, n, dev.ptr(idx), st)
+            out = dev.empty(n, D)
+            _cabi.call("smcb_gather_rows", dev.ptr(x), dev.ptr(idx), n, D, dev.ptr(out), st)
+            self.last_idx = idx
+            return out
+        if self.scheme == "systematic":
+            return self._systematic_sharded(x, cdf, iteration)
+        return self._multinomial_sharded(x, cdf, iteration)
+
+    def _u0(self, iteration):
+        u = dev.empty(1)
+        _cabi.call("smcb_uniforms", self.seed, iteration, self.stream, 0, 1, 0, dev.ptr(u), dev.stream_ptr())
+        return float(u.item())
+
+    def _systematic_sharded(self, x, cdf, iteration):
+        """Sorted positions -> every source rank serves one contiguous slot range; rows travel by all-to-all-v."""
+        sh, st = self.shard, dev.stream_ptr()
+        n, D = x.shape
+        u0 = self._u0(iteration)
+        lasts = sh.all_gather_vec(cdf[-1:].contiguous()).view(-1).cpu().numpy()
+        bounds = systematic_slot_bounds(np.concatenate([[0.0], lasts]), u0, self.N)
+        lo, hi = int(bounds[sh.rank]), int(bounds[sh.rank + 1])
+        m = hi - lo
+        idx = dev.empty(max(m, 1), dtype=torch.int64)
+        send = dev.empty(max(m, 1), D)
+        if m:
+            _cabi.call("smcb_ancestors_systematic", dev.ptr(cdf), n, u0, lo, self.N, m, dev.ptr(idx), st)
+            _cabi.call("smcb_gather_rows", dev.ptr(x), dev.ptr(idx), m, D, dev.ptr(send), st)
+        send_counts = split_counts(lo, hi, self.n_local, sh.world)
+        mylo, myhi = sh.rank * self.n_local, (sh.rank + 1) * self.n_local
+        recv_counts = [max(0, min(myhi, int(bounds[q + 1])) - max(mylo, int(bounds[q]))) for q in range(sh.world)]
+        self.last_migrated_rows = sum(c for q, c in enumerate(recv_counts) if q != sh.rank)
+        self.last_idx = idx[:m] + self.offset
+        return sh.all_to_all_rows(send[:m], send_counts, recv_counts)
+
+    def _multinomial_sharded(self, x, cdf, iteration):
+        """Unsorted uniforms: all-gather the cdf (8N bytes), search locally, fetch rows from their owners with a
+        request/response all-to-all-v pair."""
+        import torch.distributed as dist
+        sh, st = self.shard, dev.stream_ptr()
+        n, D = x.shape
+        full = torch.empty(self.N, dtype=torch.float64, device=x.device)
+        dist.all_gather_into_tensor(full, cdf, group=sh.group)
+        u, idx = dev.empty(n), dev.empty(n, dtype=torch.int64)
+        _cabi.call("smcb_uniforms", self.seed, iteration, self.stream, self.offset, n, 0, dev.ptr(u), st)
+        _cabi.call("smcb_ancestors_multinomial", dev.ptr(full), self.N, dev.ptr(u), n, dev.ptr(idx), st)
+        self.last_idx = idx
+        owner = torch.div(idx, self.n_local, rounding_mode="floor")
+        order = torch.argsort(owner, stable=True)
+        req_counts = torch.bincount(owner, minlength=sh.world)
+        got_counts = torch.empty_like(req_counts)
+        dist.all_to_all_single(got_counts, req_counts, group=sh.group)
+        rc, gc = req_counts.tolist(), got_counts.tolist()
+        want = (idx[order] - owner[order] * self.n_local).contiguous()
+        asked = sh.all_to_all_rows(want.view(-1, 1), rc, gc).view(-1).contiguous()
+        rows = dev.empty(max(asked.numel(), 1), D)
+        if asked.numel():
+            _cabi.call("smcb_gather_rows", dev.ptr(x), dev.ptr(asked), asked.numel(), D, dev.ptr(rows), st)
+        back = sh.all_to_all_rows(rows[:asked.numel()], gc, rc)
+        out = dev.empty(n, D)
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(n, device=order.device)
+        _cabi.call("smcb_gather_rows", dev.ptr(back), dev.ptr(inv), n, D, dev.ptr(out), st)
+        self.last_migrated_rows = n - rc[sh.rank]
+        return out
+
+
+class Samples:
+    def __init__(self, N, D, sample_proposal, target, forward_kernel, lkernel, tempering, rng,
+                 resampling="multinomial", shard: ShardContext = None) -> None:
+        """
+        N: GLOBAL number of samples; D: dimension; sample_proposal: q0; target: device model;
+        forward_kernel: the NUTS proposal plugin; lkernel: "GaussianApproxLKernel" | "forwardsLKernel" |
+        "asymptoticLKernel" (or an L-kernel plugin instance); tempering: bool; rng: seed source.
+        """
+        self.N = N
+        self.D = D
+        self.sample_proposal = sample_proposal
+        self.forward_kernel = forward_kernel
+        self.target = target
+        self.rng = rng
+        self.shard = shard or ShardContext()
+        self.n_local = self.shard.local_count(N)
+        self.offset = self.shard.offset(N)
+        self.seed = forward_kernel.seed if hasattr(forward_kernel, "seed") else dev.seed_from_rng(rng)
+        self.iteration = 0
+        self.resampler = Resampler(N, self.seed, self.shard, scheme=resampling)
+        self.resampled_last = False
+
+        # L-kernel selection by string, as the reference (samples.py:39-48); plugin instances are accepted too
+        if lkernel == "GaussianApproxLKernel":
+            self.lkernel = GaussianApproxLKernel(target=self.target, N=self.N, shard=self.shard)
+            self.reweight_strategy = self._non_asympototic_reweight
+        elif lkernel == "forwardsLKernel":
+            mp = self.forward_kernel.momentum_proposal if self.forward_kernel is not None else None
+            self.lkernel = ForwardLKernel(target=self.target, momentum_proposal=mp)
+            self.reweight_strategy = self._non_asympototic_reweight
+        elif lkernel == "asymptoticLKernel":
+            self.lkernel = None
+            self.reweight_strategy = self._asymptotic_reweight
+        elif hasattr(lkernel, "calculate_L"):
+            self.lkernel = lkernel
+            self.reweight_strategy = self._non_asympototic_reweight
+        else:
+            raise Exception("Unknown L-kernel supplied")
+
+        if tempering:
+            self.TemperingScheme = ESSTempering(self.N, self.target, alpha=0.5, shard=self.shard)
+            self.update_temperature = self._tempering
+            self.phi_old = 0.0
+            self.phi_new = 0.0
+        else:
+            self.TemperingScheme = None
+            self.update_temperature = lambda: 1.0
+            self.phi_old = 1.0
+            self.phi_new = 1.0
+        self._stats = None
+        self._split_new = None   # (A, B) at x_new from the last transition
+        self._split_x = None     # (A, B) at x (pre-move), from the last transition
+        self._ke = None
+
+    # ------------------------------------------------------------------ helpers
+    def _draw_std_normal(self, dist, stream, iteration):
+        if dev.is_std_normal(dist, self.D):
+            out = dev.empty(self.n_local, self.D)
+            _cabi.call("smcb_normals", self.seed, iteration, stream, self.offset, self.n_local, self.D, dev.ptr(out),
+                       dev.stream_ptr())
+            return out
+        z = np.asarray(dist.rvs(self.N)).reshape(self.N, self.D)   # generic plugin: host draw, then upload
+        return dev.to_device(z[self.offset:self.offset + self.n_local])
+
+    def _logpdf_q0(self, x):
+        if dev.is_std_normal(self.sample_proposal, self.D):
+            out = dev.empty(x.shape[0])
+            _cabi.call("smcb_std_normal_logpdf", dev.ptr(x), x.shape[0], self.D, dev.ptr(out), dev.stream_ptr())
+            return out
+        return dev.to_device(self.sample_proposal.logpdf(x.cpu().numpy()))
+
+    # ------------------------------------------------------------------ reference API
+    def initialise_samples(self):
+        """samples.py:63-88."""
+        self.x = self._draw_std_normal(self.sample_proposal, _cabi.STREAM_INIT, 0)
+        self.x_new = self.x
+        self.ess = 0
+        self.r = dev.zeros(self.n_local, self.D)
+        self.r_new = dev.zeros(self.n_local, self.D)
+        A, B = self.target.split(self.x)
+        self._split_new = (A, B)
+        self.phi_new = self.update_temperature()
+        self.phi_old = self.phi_new
+        lp = self.target.combine(A, B, self.phi_new)
+        if dev.is_std_normal(self.sample_proposal, self.D):
+            self.logw = dev.empty(self.n_local)
+            _cabi.call("smcb_init_logw", dev.ptr(lp), dev.ptr(self.x), self.n_local, self.D, dev.ptr(self.logw),
+                       dev.stream_ptr())
+        else:
+            self.logw = lp - self._logpdf_q0(self.x)
+        self.logw_new = dev.zeros(self.n_local)
+        self.wn = dev.zeros(self.n_local)
+
+    def normalise_weights(self):
+        """samples.py:91-105 (+ the sums calculate_ess needs, from the same pass)."""
+        self.wn, self._stats, _ = normalise(self.logw, self.shard)
+        self._stats_host = None
+
+    def _host_stats(self):
+        if self._stats_host is None:
+            self._stats_host = self._stats.cpu().numpy()
+        return self._stats_host
+
+    @property
+    def log_likelihood(self):
+        return float(self._host_stats()[0])
+
+    def calculate_ess(self):
+        """samples.py:108-113: 1 / sum(wn^2) = (sum e)^2 / sum e^2 of the same online pass."""
+        self.ess = float(self._host_stats()[1])
+
+    def resample_if_required(self):
+        """samples.py:116-122 (threshold hard coded to 1/2)."""
+        self.resampled_last = False
+        if self.ess < self.N / 2:
+            self._resample(self.x, self.wn, self.log_likelihood)
+            self.resampled_last = True
+
+    def _resample(self, x, wn, log_likelihood):
+        """samples.py:125-146."""
+        self.x = self.resampler.resample_rows(x, wn, self.iteration)
+        self.logw = dev.empty(self.n_local)
+        _cabi.call("smcb_uniform_logw", dev.ptr(self._stats), self.N, self.n_local, dev.ptr(self.logw), dev.stream_ptr())
+
+    def propose_samples(self):
+        """samples.py:149-158."""
+        fk = self.forward_kernel
+        self.r = self._draw_std_normal(fk.momentum_proposal, _cabi.STREAM_MOMENTUM, self.iteration)
+        if hasattr(fk, "transition"):
+            fk.particle0 = self.offset
+            o = fk.transition(self.x, self.r, self.phi_new, iteration=self.iteration)
+            self.x_new, self.r_new = o["x_new"], o["r_new"]
+            self._split_x, self._split_new = (o["A_old"], o["B_old"]), (o["A_new"], o["B_new"])
+            self._ke = (o["ke_old"], o["ke_new"])
+            self.n_leapfrog = o["n_leapfrog"]
+        else:  # foreign proposal plugin: only the reference contract is available
+            self.x_new, self.r_new = (dev.to_device(t) for t in fk.rvs(self.x, self.r, phi=self.phi_new))
+            self._split_x, self._split_new, self._ke = self.target.split(self.x), self.target.split(self.x_new), None
+
+    def reweight(self):
+        self.logw_new = self.reweight_strategy()
+
+    def _asymptotic_reweight(self):
+        """samples.py:169-180: logw + logp(x, phi_new) - logp(x, phi_old) at the PRE-move x."""
+        A, B = self._split_x
+        out = dev.empty(self.n_local)
+        _cabi.call("smcb_reweight_asymptotic", dev.ptr(self.logw), dev.ptr(A), dev.ptr(B), float(self.phi_new),
+                   float(self.phi_old), self.n_local, dev.ptr(out), dev.stream_ptr())
+        return out
+
+    def _non_asympototic_reweight(self):
+        """samples.py:183-196: logp at phi = 1 regardless of tempering."""
+        st, n = dev.stream_ptr(), self.n_local
+        lp_x = self.target.combine(*self._split_x, 1.0)
+        lp_xnew = self.target.combine(*self._split_new, 1.0)
+        out = dev.empty(n)
+        fused = isinstance(self.lkernel, ForwardLKernel) and self._ke is not None and \
+            dev.is_std_normal(self.forward_kernel.momentum_proposal, self.D)
+        if fused:  # L(r_new) - q(r) = -ke_new + ke_old, both emitted by the NUTS kernel
+            _cabi.call("smcb_reweight_forward_ke", dev.ptr(self.logw), dev.ptr(lp_x), dev.ptr(lp_xnew),
+                       dev.ptr(self._ke[0]), dev.ptr(self._ke[1]), n, dev.ptr(out), st)
+            return out
+        L = dev.to_device(self.lkernel.calculate_L(self.r_new, self.x_new))
+        q = dev.to_device(self.forward_kernel.logpdf(self.r))
+        _cabi.call("smcb_reweight_general", dev.ptr(self.logw), dev.ptr(lp_x), dev.ptr(lp_xnew), dev.ptr(L), dev.ptr(q),
+                   n, dev.ptr(out), st)
+        return out
+
+    def _tempering(self):
+        """samples.py:199-212 -> adaptive_tempering.py:18-63, on the split at x_new."""
+        A, B = self._split_new
+        self.phi_new = self.TemperingScheme.calculate_phi_from_split(A, B, float(self.phi_old))
+        return self.phi_new
+
+    def update_samples(self):
+        """samples.py:215-222."""
+        self.phi_old = self.phi_new
+        self.x = self.x_new
+        self.logw = self.logw_new
+        self.iteration += 1

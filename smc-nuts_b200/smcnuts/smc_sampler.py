@@ -1,0 +1,158 @@
+"""SMCSampler -- the K-iteration SMC loop with a NUTS proposal (reference: smcnuts/smc_sampler.py).
+
+Same constructor, same result attributes, same per-iteration order of operations (smc_sampler.py:109-140);
+all particle state lives on the GPU.  Accepts both the constructor in the reference code
+    SMCSampler(K, N, target, step_size, sample_proposal, momentum_proposal, lkernel, tempering=False, rng=...)
+and the README form
+    SMCSampler(K, N, target, forward_kernel, sample_proposal, tempering, lkernel, rng=...)
+"""
+from time import time
+
+import numpy as np
+import torch
+from tqdm import tqdm
+
+from . import _cabi, _device as dev
+from .estimate.estimate import Estimate
+from .estimate.estimate_from_tempered import EstimateFromTempered
+from .parallel import ShardContext
+from .proposal.nuts import NUTSProposal
+from .proposal.nuts_acc_rej import NUTSProposalWithAccRej
+from .samples.samples import Samples
+
+
+class SMCSampler:
+    def __init__(self, K: int, N: int, target, step_size=None, sample_proposal=None, momentum_proposal=None,
+                 lkernel="forwardsLKernel", tempering=False, rng=None, forward_kernel=None, verbose=False,
+                 resampling="multinomial", save_history=None, history_budget_bytes=48 << 30):
+        self.K = K  # Number of iterations
+        self.N = N  # Number of particles (global)
+        self.target = target
+        self.rng = rng
+        self.lkernel = lkernel
+        self.verbose = verbose
+        self.shard = ShardContext()
+        D = target.dim
+
+        # README form: the 4th positional argument is a forward-kernel plugin, not a step size
+        if forward_kernel is None and step_size is not None and hasattr(step_size, "rvs"):
+            forward_kernel, step_size = step_size, None
+        if forward_kernel is None:
+            cls = NUTSProposalWithAccRej if lkernel == "asymptoticLKernel" else NUTSProposal  # smc_sampler.py:45-60
+            forward_kernel = cls(target=self.target, momentum_proposal=momentum_proposal, step_size=step_size, rng=rng)
+        self.forward_kernel = forward_kernel
+        seed = getattr(forward_kernel, "seed", None)
+        if seed is None:
+            seed = dev.seed_from_rng(rng)
+        self.seed = seed
+
+        if lkernel == "asymptoticLKernel":
+            self.estimator = EstimateFromTempered(self.target, self.N, self.K, seed, shard=self.shard,
+                                                  resampling=resampling)
+        else:
+            self.estimator = Estimate(self.target, shard=self.shard)
+
+        # Outputs (smc_sampler.py:66-85)
+        self.resampled = [False] * (self.K + 1)
+        self.ess = np.zeros(self.K + 1)
+        self.log_likelihood = np.zeros(self.K + 1)
+        self.phi = np.zeros(self.K + 1)
+        self.acceptance_rate = np.zeros(self.K + 1)
+        self.run_time = None
+        self.leapfrogs = np.zeros(self.K, dtype=np.int64)   # gradient evaluations per iteration (metric counter)
+        self.propose_time = np.zeros(self.K)                 # device seconds of the propose phase (CUDA events)
+
+        self.samples = Samples(self.N, D, sample_proposal, self.target, forward_kernel, lkernel, tempering, seed,
+                               resampling=resampling, shard=self.shard)
+        self.samples.initialise_samples()
+        n_local = self.samples.n_local
+
+        hist_bytes = (self.K + 1) * n_local * (D + 1) * 8
+        if save_history is None:
+            save_history = lkernel == "asymptoticLKernel" or hist_bytes <= history_budget_bytes
+        self.save_history = save_history
+        if save_history:  # device-resident history (the reference keeps it in host RAM, smc_sampler.py:73-74)
+            self._x_saved = dev.empty(self.K + 1, n_local, D)
+            self._logw_saved = dev.empty(self.K + 1, n_local)
+            self._x_saved[0].copy_(self.samples.x)
+            self._logw_saved[0].copy_(self.samples.logw)
+        else:
+            self._x_saved = self._logw_saved = None
+
+        self._mean_dev = dev.zeros(self.K + 1, D)
+        self._var_dev = dev.zeros(self.K + 1, D)
+        self._moved = dev.zeros(self.K + 1)
+        self.mean_estimate = np.zeros([self.K + 1, D])
+        self.variance_estimate = np.zeros([self.K + 1, D])
+
+    # history is exposed with the reference's names; device tensors (use .cpu().numpy() for host copies)
+    @property
+    def x_saved(self):
+        return self._x_saved
+
+    @property
+    def logw_saved(self):
+        return self._logw_saved
+
+    def update_sampler(self, k, mean_estimate, variance_estimate):
+        """smc_sampler.py:88-97; scalars are fetched once per iteration, vectors stay on the device until the end."""
+        s = self.samples
+        self.log_likelihood[k] = s.log_likelihood
+        self._mean_dev[k].copy_(mean_estimate)
+        self._var_dev[k].copy_(variance_estimate)
+        self.ess[k] = s.ess
+        if s.x_new is s.x:  # after update_samples x is x_new: the reference then records 0 (smc_sampler.py:97,148)
+            self._moved[k] = 0.0
+        else:
+            _cabi.call("smcb_count_moved", dev.ptr(s.x), dev.ptr(s.x_new), s.n_local, s.D, dev.ptr(self._moved[k:k + 1]),
+                       dev.ptr(dev.reduce_ws()), dev.stream_ptr())
+
+    def sample(self, show_progress=True):
+        """Sample from the target distribution using an SMC sampler (smc_sampler.py:101-155)."""
+        start_time = time()
+        s = self.samples
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(self.K)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(self.K)]
+        lf = dev.zeros(self.K, dtype=torch.int64)
+
+        for k in tqdm(range(self.K), desc="NUTS Sampling", disable=not show_progress):
+            self.phi[k] = s.phi_new
+            s.normalise_weights()
+            mean_estimate, variance_estimate = self.estimator.return_estimate(s.x, s.wn)
+            s.calculate_ess()
+            s.resample_if_required()
+            self.resampled[k] = s.resampled_last
+            ev0[k].record()
+            s.propose_samples()
+            ev1[k].record()
+            if getattr(s, "n_leapfrog", None) is not None:
+                lf[k] = s.n_leapfrog.sum(dtype=torch.int64)
+            s.update_temperature()
+            s.reweight()
+            self.update_sampler(k, mean_estimate, variance_estimate)
+            s.update_samples()
+            if self.save_history:
+                self._x_saved[k + 1].copy_(s.x_new)
+                self._logw_saved[k + 1].copy_(s.logw_new)
+
+        # final estimates from the last proposal step (smc_sampler.py:143-149)
+        s.normalise_weights()
+        mean_estimate, variance_estimate = self.estimator.return_estimate(s.x, s.wn)
+        s.calculate_ess()
+        self.update_sampler(self.K, mean_estimate, variance_estimate)
+        self.phi[self.K] = s.phi_new
+
+        torch.cuda.synchronize()
+        self.leapfrogs = self.shard.all_reduce_sum_(lf).cpu().numpy()
+        self.propose_time = np.array([a.elapsed_time(b) * 1e-3 for a, b in zip(ev0, ev1)])
+        self.mean_estimate = self._mean_dev.cpu().numpy()
+        self.variance_estimate = self._var_dev.cpu().numpy()
+        self.acceptance_rate = self.shard.all_reduce_sum_(self._moved.clone()).cpu().numpy() / self.N
+
+        # asymptotic L-kernel: re-estimate every iteration from the tempered history (smc_sampler.py:152-153)
+        if self.lkernel == "asymptoticLKernel":
+            self.mean_estimate, self.variance_estimate = self.estimator.estimate_from_tempered(
+                self._x_saved, self._logw_saved, self.phi)
+
+        torch.cuda.synchronize()
+        self.run_time = time() - start_time

@@ -1,0 +1,57 @@
+"""ctypes wrapper for tests/hostsim/hostsim.cpp (CPU simulation of the device lanes; test tool only)."""
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = HERE / "_hostsim.so"
+        src = HERE / "hostsim.cpp"
+        hdrs = list((HERE.parents[1] / "smc-nuts_b200" / "csrc").glob("*.cuh"))
+        if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in [src] + hdrs):
+            subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                            "-o", str(so), str(src)], check=True)
+        _LIB = ctypes.CDLL(str(so))
+    return _LIB
+
+
+def pack_model(name, np_target):
+    """Host blob -> (kind, packed data, dim, T, q) in the device layout of csrc/models.cuh."""
+    if name == "arma":
+        return 0, np.ascontiguousarray(np_target.y), 4, len(np_target.y), 0.0
+    if name == "PRMwCD":
+        t = np_target
+        rows = np.zeros((t.Nobs, 14))
+        rows[:, :11] = t.X
+        rows[:, 12] = t.y
+        rows[:, 13] = t.lgam
+        return 1, np.ascontiguousarray(rows.ravel()), 13, t.Nobs, t.q
+    return 2, np.ascontiguousarray(np_target.P.ravel()), np_target.dim, 0, 0.0
+
+
+def nuts(name, np_target, x, r, eps, phi, max_depth=10, accrej=False, seed=0, iteration=0, particle0=0, lanes=32):
+    kind, data, dim, T, q = pack_model(name, np_target)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    N = len(x)
+    o = dict(x_new=np.empty_like(x), r_new=np.empty_like(r), A_old=np.empty(N), B_old=np.empty(N), A_new=np.empty(N),
+             B_new=np.empty(N), ke_old=np.empty(N), ke_new=np.empty(N), n_leapfrog=np.empty(N, dtype=np.int32),
+             accepted=np.empty(N, dtype=np.int32), depth=np.empty(N, dtype=np.int32))
+    P = lambda a: a.ctypes.data_as(_dp)  # noqa: E731
+    I = lambda a: a.ctypes.data_as(_ip)  # noqa: E731
+    lib().hostsim_nuts(ctypes.c_int(kind), P(data), ctypes.c_int(data.size), ctypes.c_int(dim), ctypes.c_int(T),
+                       ctypes.c_double(q), P(x), P(r), ctypes.c_longlong(N), ctypes.c_double(eps), ctypes.c_double(phi),
+                       ctypes.c_int(max_depth), ctypes.c_int(int(accrej)), ctypes.c_ulonglong(seed),
+                       ctypes.c_uint(iteration), ctypes.c_ulonglong(particle0), P(o["x_new"]), P(o["r_new"]),
+                       P(o["A_old"]), P(o["B_old"]), P(o["A_new"]), P(o["B_new"]), P(o["ke_old"]), P(o["ke_new"]),
+                       I(o["n_leapfrog"]), I(o["accepted"]), I(o["depth"]), ctypes.c_int(lanes))
+    return o

@@ -1,0 +1,345 @@
+"""GPU (B200): the CUDA path, called through the plugin classes / C-ABI, against the oracle and against the
+golden fixtures produced by the unmodified reference.  Tolerances are written next to each check:
+fp64 model values 1e-10 relative (north_star), integer work (ancestors, tree sizes) bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox
+from oracle import smc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from smcnuts import _cabi, _device as dev
+    from smcnuts.estimate.estimate import Estimate
+    from smcnuts.lkernel.forward_lkernel import ForwardLKernel
+    from smcnuts.lkernel.gaussian_lkernel import GaussianApproxLKernel
+    from smcnuts.model.device_model import make_model
+    from smcnuts.parallel import ShardContext
+    from smcnuts.proposal.nuts import NUTSProposal
+    from smcnuts.proposal.nuts_acc_rej import NUTSProposalWithAccRej
+    from smcnuts.samples.samples import Resampler, normalise
+    from smcnuts.tempering.adaptive_tempering import ESSTempering
+    from smcnuts.distributions import StdNormal
+
+
+def _models(name):
+    if name.startswith("gauss"):
+        d = int(name[5:])
+        return make_model("gauss", dim=d), O.COracleTarget("gauss", dim=d)
+    return make_model(name), O.COracleTarget(name)
+
+
+# ------------------------------------------------------------------------------------------------ K1 models
+@pytest.mark.parametrize("name,gname", [("arma", "arma"), ("PRMwCD", "PRMwCD"), ("gauss8", "gauss"), ("gauss100", "gauss100")])
+def test_logp_grad_matches_golden_and_oracle(golden, name, gname):
+    g = golden("models")
+    m, t = _models(name)
+    X = g[f"{gname}_X"]
+    for phi in (0.0, 0.37, 1.0):
+        lp, gr = m.logpdf(X, phi), m.logpdfgrad(X, phi)
+        ref_lp, ref_g = g[f"{gname}_lp_{phi}"], g[f"{gname}_grad_{phi}"]
+        assert np.array_equal(np.isneginf(lp), np.isneginf(ref_lp))
+        fin = np.isfinite(ref_lp)
+        np.testing.assert_allclose(lp[fin], ref_lp[fin], rtol=1e-10)                 # north_star: 1e-10 relative
+        np.testing.assert_allclose(gr[fin], ref_g[fin], rtol=1e-10, atol=1e-9)
+        assert np.all(np.isneginf(gr[~fin]))
+    if f"{gname}_mp_lp_0.37" in g:
+        np.testing.assert_allclose(m.logpdf(X[:8], 0.37), g[f"{gname}_mp_lp_0.37"], rtol=1e-12)   # vs mpmath 50 digits
+    # 20k random points against the C oracle
+    rng = np.random.default_rng(3)
+    Xr = rng.normal(size=(20000, m.dim)) * 0.5
+    A, B = (v.cpu().numpy() for v in m.split(Xr))
+    Ao, Bo, _, _ = t.split(Xr, grads=False)
+    np.testing.assert_allclose(A, Ao, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(B, Bo, rtol=1e-11, atol=1e-9)
+    gr = m.logpdfgrad(Xr, 0.6)
+    np.testing.assert_allclose(gr, t.logpdfgrad(Xr, 0.6), rtol=1e-10, atol=1e-8)
+    assert isinstance(m.logpdf(Xr[0], 0.5), float) and m.logpdfgrad(Xr[0]).shape == (m.dim,)
+
+
+def test_philox_streams_match_oracle():
+    n = 5000
+    u = dev.empty(n)
+    for draw in (0, 1, 6):
+        _cabi.call("smcb_uniforms", 10, 3, 2, 17, n, draw, dev.ptr(u), dev.stream_ptr())
+        assert np.array_equal(u.cpu().numpy(), O.uniforms(10, 3, 2, 17, n, draw))               # bit-exact
+    for D in (4, 13):
+        z = StdNormal(D, seed=10, stream=_cabi.STREAM_MOMENTUM).rvs(n, iteration=5, particle0=3).cpu().numpy()
+        np.testing.assert_allclose(z, philox.normals(10, 5, 1, np.arange(3, 3 + n), D), rtol=1e-13, atol=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------ K2/K3 NUTS
+NUTS_CASES = ["arma", "arma_tempered", "arma_prior", "PRMwCD", "PRMwCD_tempered", "gauss8", "gauss100"]
+
+
+@pytest.mark.parametrize("case", NUTS_CASES)
+def test_nuts_transition_matches_reference_golden(golden, case):
+    """Same x0, r0 and the same Philox draws as the unmodified reference -> same transition."""
+    g = golden("nuts")
+    name = case.split("_")[0]
+    m, _ = _models(name)
+    x0, r0 = g[f"{case}_x0"], g[f"{case}_r0"]
+    eps, phi, it, seed = float(g[f"{case}_eps"]), float(g[f"{case}_phi"]), int(g[f"{case}_iteration"]), int(g[f"{case}_seed"])
+    for cls in (NUTSProposal, NUTSProposalWithAccRej):
+        k = cls(m, StdNormal(m.dim), eps, rng=seed)
+        k.iteration = it
+        xn, rn = k.rvs(x0, r0, phi)
+        nl = k.last["n_leapfrog"].cpu().numpy()
+        same = nl == g[f"{case}_n_leapfrog"]
+        # long PRMwCD trajectories amplify last-bit differences (FMA, libm); tree sizes must agree on >= 90 %
+        assert same.mean() >= (0.9 if name == "PRMwCD" else 1.0), same.mean()
+        acc = g[f"{case}_accepted"] if cls is NUTSProposalWithAccRej else np.ones(len(x0), dtype=bool)
+        acc_dev = k.last["accepted"].cpu().numpy().astype(bool)
+        ok = same & acc & acc_dev
+        assert (acc_dev[same] == acc[same]).mean() >= 0.95
+        np.testing.assert_allclose(xn[ok], g[f"{case}_x_new"][ok], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(rn[ok], g[f"{case}_r_new"][ok], rtol=1e-6, atol=1e-7)
+        rej = ~acc_dev
+        assert np.array_equal(xn[rej], x0[rej]) and np.array_equal(rn[rej], r0[rej])
+
+
+@pytest.mark.parametrize("name,eps,N", [("arma", 0.01, 20000), ("PRMwCD", 0.01, 1500), ("gauss8", 0.1, 20000),
+                                        ("gauss33", 0.15, 3000)])
+def test_nuts_batch_matches_oracle(name, eps, N):
+    """Work-queue kernel (many more particles than lanes) against the recursive C oracle."""
+    m, t = _models(name)
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(N, m.dim)) * 0.3
+    if name == "arma":
+        x += np.array([0.0, 0.9, 0.0, -1.7])
+        x[:50] = rng.normal(size=(50, 4)) * 2.0
+        x[0, 3] = 800.0
+    r = rng.normal(size=(N, m.dim))
+    for accrej, phi in ((False, 1.0), (True, 0.3)):
+        ref = t.nuts_batch(x, r, eps, phi, 10, seed=5, iteration=2, particle0=1 << 33, accrej=accrej, nthreads=8)
+        k = (NUTSProposalWithAccRej if accrej else NUTSProposal)(m, StdNormal(m.dim), eps, rng=5)
+        k.particle0 = 1 << 33
+        o = k.transition(dev.to_device(x), dev.to_device(r), phi, iteration=2)
+        o = {kk: v.cpu().numpy() for kk, v in o.items()}
+        same = o["n_leapfrog"] == ref["n_leapfrog"]
+        assert same.mean() >= (0.9 if name == "PRMwCD" else 0.995), same.mean()
+        assert np.array_equal(o["depth"][same], ref["depth"][same])
+        assert (o["accepted"][same] == ref["accepted"][same]).mean() >= 0.999
+        ok = same & (o["accepted"] == ref["accepted"])
+        fin = ok & np.all(np.isfinite(ref["x_new"]), axis=1)
+        np.testing.assert_allclose(o["x_new"][fin], ref["x_new"][fin], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(o["r_new"][fin], ref["r_new"][fin], rtol=1e-6, atol=1e-7)
+        with np.errstate(invalid="ignore"):
+            lp_new = o["A_new"] + phi * o["B_new"]
+        lp_new = np.where(np.isfinite(lp_new), lp_new, -np.inf)
+        np.testing.assert_allclose(lp_new[fin], ref["lp_new"][fin], rtol=1e-8, atol=1e-8)
+        np.testing.assert_allclose(o["ke_old"], 0.5 * np.sum(r * r, axis=1), rtol=1e-13)
+        np.testing.assert_allclose(o["ke_new"][fin], 0.5 * np.sum(o["r_new"][fin] ** 2, axis=1), rtol=1e-13)
+        # total leapfrog count (the metric's counter) agrees to well under 1 %
+        assert abs(int(o["n_leapfrog"].sum()) - int(ref["n_leapfrog"].sum())) <= 0.01 * ref["n_leapfrog"].sum()
+
+
+def test_nuts_rejects_bad_arguments():
+    m, _ = _models("arma")
+    k = NUTSProposal(m, StdNormal(4), 0.01, rng=1, max_tree_depth=11)
+    with pytest.raises(_cabi.SmcbError):
+        k.rvs(np.zeros((4, 4)), np.zeros((4, 4)))
+    with pytest.raises(TypeError):
+        NUTSProposal(object(), None, 0.1)
+
+
+# ------------------------------------------------------------------------------------------------ K5/K7 weights
+def test_normalise_ess_estimates_match_reference_golden(golden):
+    g = golden("lkernel_weights")
+    sh = ShardContext()
+    for tag, name in (("a", "arma"), ("b", "PRMwCD")):
+        logw = dev.to_device(g[f"weights_{tag}_logw"])
+        wn, stats, _ = normalise(logw, sh)
+        logZ, ess = stats.cpu().numpy()
+        np.testing.assert_allclose(wn.cpu().numpy(), g[f"weights_{tag}_wn"], rtol=1e-13, atol=0)
+        assert math.isclose(logZ, float(g[f"weights_{tag}_logZ"]), rel_tol=1e-14)
+        assert math.isclose(ess, float(g[f"weights_{tag}_ess"]), rel_tol=1e-12)
+        m, _ = _models(name)
+        mean, var = Estimate(m).return_estimate(g[f"weights_{tag}_x"], g[f"weights_{tag}_wn"])
+        np.testing.assert_allclose(mean, g[f"weights_{tag}_mean_c"], rtol=1e-12)
+        np.testing.assert_allclose(var, g[f"weights_{tag}_var_c"], rtol=1e-11)
+        mean, var = Estimate(m).return_estimate_unconstrained(g[f"weights_{tag}_x"], g[f"weights_{tag}_wn"])
+        np.testing.assert_allclose(mean, g[f"weights_{tag}_mean_u"], rtol=1e-12)
+        np.testing.assert_allclose(var, g[f"weights_{tag}_var_u"], rtol=1e-11)
+
+
+def test_normalise_edge_cases():
+    sh = ShardContext()
+    wn, stats, _ = normalise(dev.to_device(np.array([-np.inf, 0.0, -np.inf, math.log(3.0)])), sh)
+    np.testing.assert_allclose(wn.cpu().numpy(), [0, 0.25, 0, 0.75], rtol=1e-15)
+    assert math.isclose(stats[0].item(), math.log(4.0), rel_tol=1e-15) and math.isclose(stats[1].item(), 1.6, rel_tol=1e-14)
+    wn, stats, _ = normalise(dev.to_device(np.array([5.0])), sh)
+    assert wn.item() == 1.0 and stats[0].item() == 5.0 and stats[1].item() == 1.0
+    wn, stats, _ = normalise(dev.to_device(np.array([0.0, np.nan, 1.0])), sh)   # NaN poisons, as in the reference
+    assert math.isnan(stats[0].item())
+    big = np.random.default_rng(0).normal(size=3_000_001) * 5
+    wn, stats, _ = normalise(dev.to_device(big), sh)
+    wn_o, logZ_o = O.normalise_weights(big)
+    assert math.isclose(stats[0].item(), logZ_o, rel_tol=1e-13)
+    assert math.isclose(stats[1].item(), O.calculate_ess(wn_o), rel_tol=1e-11)
+    np.testing.assert_allclose(wn.cpu().numpy(), wn_o, rtol=1e-12)
+
+
+def test_reweight_kernels_match_oracle(golden):
+    rng = np.random.default_rng(4)
+    for D, n in ((4, 1000), (16, 70001), (13, 513)):
+        logw, lpx, lpn = rng.normal(size=(3, n))
+        r, rn = rng.normal(size=(2, n, D))
+        want = O.reweight_non_asymptotic(logw, lpx, lpn, O.forward_lkernel(rn), O.std_normal_logpdf(r))
+        d = [dev.to_device(a) for a in (logw, lpx, lpn, r, rn)]
+        out = dev.empty(n)
+        _cabi.call("smcb_reweight_forward", *(dev.ptr(a) for a in d), n, D, dev.ptr(out), dev.stream_ptr())
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
+        ke0, ke1 = dev.empty(n), dev.empty(n)
+        _cabi.call("smcb_row_half_sqnorm", dev.ptr(d[3]), n, D, dev.ptr(ke0), dev.stream_ptr())
+        _cabi.call("smcb_row_half_sqnorm", dev.ptr(d[4]), n, D, dev.ptr(ke1), dev.stream_ptr())
+        _cabi.call("smcb_reweight_forward_ke", dev.ptr(d[0]), dev.ptr(d[1]), dev.ptr(d[2]), dev.ptr(ke0), dev.ptr(ke1), n,
+                   dev.ptr(out), dev.stream_ptr())
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
+        A, B = rng.normal(size=(2, n))
+        B[::97] = -np.inf
+        _cabi.call("smcb_reweight_asymptotic", dev.ptr(d[0]), dev.ptr(dev.to_device(A)), dev.ptr(dev.to_device(B)), 0.7, 0.2,
+                   n, dev.ptr(out), dev.stream_ptr())
+        with np.errstate(invalid="ignore"):
+            f = lambda p: np.where(np.isfinite(A + p * B), A + p * B, -np.inf)   # noqa: E731
+            want = O.reweight_asymptotic(logw, f(0.7), f(0.2))
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-13, equal_nan=True)
+    g = golden("lkernel_weights")
+    for D in (4, 13, 100):
+        m, _ = _models(f"gauss{D}")
+        fl = ForwardLKernel(m, StdNormal(D)).calculate_L(g[f"gaussL_{D}_r_new"], None)
+        np.testing.assert_allclose(fl, g[f"fwdL_{D}"], rtol=1e-13)                       # reference ForwardLKernel
+        q = NUTSProposal(m, StdNormal(D), 0.1, rng=0).logpdf(g[f"gaussL_{D}_r_new"])
+        np.testing.assert_allclose(q, g[f"qlogpdf_{D}"], rtol=1e-13)                     # reference NUTSProposal.logpdf
+
+
+# ------------------------------------------------------------------------------------------------ K6 Gaussian L
+@pytest.mark.parametrize("D", [4, 13, 100])
+def test_gaussian_lkernel_matches_reference_golden(golden, D):
+    g = golden("lkernel_weights")
+    m, _ = _models(f"gauss{D}")
+    r_new, x_new = g[f"gaussL_{D}_r_new"], g[f"gaussL_{D}_x_new"]
+    L = GaussianApproxLKernel(m, len(r_new)).calculate_L(r_new, x_new)
+    np.testing.assert_allclose(L, g[f"gaussL_{D}_L"], rtol=1e-8 if D == 100 else 1e-9)
+
+
+def test_gaussian_lkernel_large_n_matches_oracle():
+    rng = np.random.default_rng(9)
+    D, n = 6, 200_003
+    x_new = rng.normal(size=(n, D)) @ rng.normal(size=(D, D))
+    r_new = 0.5 * rng.normal(size=(n, D)) - 0.2 * x_new
+    m, _ = _models("gauss6")
+    L = GaussianApproxLKernel(m, n).calculate_L(r_new, x_new)
+    np.testing.assert_allclose(L, O.gaussian_lkernel(r_new, x_new), rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ K8 tempering
+def test_tempering_matches_reference_golden(golden):
+    g = golden("tempering")
+    m, _ = _models("arma")
+    for j in range(4):
+        lpri, ll, old = g[f"temper_{j}_logpri"], g[f"temper_{j}_loglik"], float(g[f"temper_{j}_old_phi"])
+        # feed the split directly: A = logpri, B = loglik
+        ts = ESSTempering(len(ll), m, alpha=0.5)
+        phi = ts.calculate_phi_from_split(dev.to_device(lpri), dev.to_device(ll), old)
+        assert math.isclose(phi, float(g[f"temper_{j}_phi"]), rel_tol=1e-9), (phi, float(g[f"temper_{j}_phi"]))
+        assert ts.passes <= 12
+    # the reference entry point: calculate_phi([x_new, lp_old, old_phi]) on real model values
+    t = O.COracleTarget("arma")
+    x = np.random.default_rng(2).normal(size=(4000, 4)) * 0.3 + np.array([0.0, 0.5, 0.0, -1.0])
+    A, B, _, _ = t.split(x, grads=False)
+    want = O.calculate_phi((A + B) - A, A, A + 0.0 * B, 0.0, len(x))
+    got = ESSTempering(len(x), m).calculate_phi([x, None, 0.0])
+    assert math.isclose(got, want, rel_tol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ K9-K11 resampling
+def _cdf_dev(wn):
+    n = len(wn)
+    w = dev.to_device(wn)
+    cdf, tot = dev.empty(n), dev.empty(1)
+    ws = dev.workspace("scan", _cabi.lib().smcb_scan_workspace_bytes(n))
+    _cabi.call("smcb_cdf", dev.ptr(w), n, 0, 0, dev.ptr(cdf), dev.ptr(tot), dev.ptr(ws), dev.stream_ptr())
+    return cdf, tot
+
+
+def _ancestors(cdf_t, u):
+    idx = dev.empty(len(u), dtype=torch.int64)
+    _cabi.call("smcb_ancestors_multinomial", dev.ptr(cdf_t), cdf_t.shape[0], dev.ptr(dev.to_device(u)), len(u), dev.ptr(idx),
+               dev.stream_ptr())
+    return idx.cpu().numpy()
+
+
+def test_multinomial_ancestors_bit_exact_with_numpy_choice(golden):
+    g = golden("choice")
+    for flavour in ("RandomState", "Generator"):
+        for N in (1, 2, 7, 100, 4096):
+            wn, u, want = g[f"{flavour}_{N}_wn"], g[f"{flavour}_{N}_u"], g[f"{flavour}_{N}_idx"]
+            # (a) same cdf, same uniforms -> bit-exact ancestors
+            assert np.array_equal(_ancestors(dev.to_device(O.cdf_of(wn)), u), want)
+            # (b) device scan: indices may differ only where u is within the scan's rounding of a cdf boundary
+            cdf_t, _ = _cdf_dev(wn)
+            got = _ancestors(cdf_t, u)
+            bad = got != want
+            if bad.any():
+                c = O.cdf_of(wn)
+                assert np.all(np.abs(u[bad] - c[np.minimum(got[bad], want[bad])]) < 1e-13)
+            assert bad.mean() <= 0.001
+    # (c) dyadic weights: every partial sum exact -> device scan == np.cumsum bit for bit -> indices bit-exact
+    cdf_t, tot = _cdf_dev(g["dyadic_wn"])
+    assert np.array_equal(cdf_t.cpu().numpy(), O.cdf_of(g["dyadic_wn"])) and tot.item() == 1.0
+    assert np.array_equal(_ancestors(cdf_t, g["dyadic_u"]), g["dyadic_idx"])
+
+
+@pytest.mark.parametrize("n", [1, 5, 2048, 2049, 1_000_003])
+def test_cdf_scan_and_systematic(n):
+    rng = np.random.default_rng(n)
+    w = rng.exponential(size=n) ** 2
+    if n > 4:
+        w[rng.integers(0, n, n // 3)] = 0.0
+    wn = w / w.sum()
+    cdf_t, tot = _cdf_dev(wn)
+    cdf = cdf_t.cpu().numpy()
+    np.testing.assert_allclose(cdf, O.cdf_of(wn), rtol=1e-12, atol=1e-15)
+    assert cdf[-1] == 1.0 and np.all(np.diff(cdf) >= 0) and math.isclose(tot.item(), 1.0, rel_tol=1e-12)
+    u0 = 0.6180339887
+    idx = dev.empty(n, dtype=torch.int64)
+    _cabi.call("smcb_ancestors_systematic", dev.ptr(cdf_t), n, u0, 0, n, n, dev.ptr(idx), dev.stream_ptr())
+    idx = idx.cpu().numpy()
+    assert np.array_equal(idx, O.systematic_ancestors(None, u0, cdf=cdf))        # same cdf -> bit-exact
+    assert np.all(np.diff(idx) >= 0) and np.all(wn[idx] > 0)
+    counts = np.bincount(idx, minlength=n)
+    assert np.all(np.abs(counts - n * wn) < 1.0 + 1e-6 * n)                      # systematic: |offspring - N w| < 1
+
+
+def test_gather_rows():
+    rng = np.random.default_rng(0)
+    for D, n in ((4, 1000), (13, 777), (16, 100_000), (100, 50)):
+        x = rng.normal(size=(n, D))
+        idx = rng.integers(0, n, size=n + 7)
+        out = dev.empty(n + 7, D)
+        _cabi.call("smcb_gather_rows", dev.ptr(dev.to_device(x)), dev.ptr(dev.to_device(idx, torch.int64)), n + 7, D,
+                   dev.ptr(out), dev.stream_ptr())
+        assert np.array_equal(out.cpu().numpy(), x[idx])
+
+
+def test_resampler_end_to_end_against_oracle():
+    n, D, seed, it = 50_000, 4, 10, 7
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(n, D))
+    w = rng.exponential(size=n) ** 4
+    wn = w / w.sum()
+    for scheme in ("multinomial", "systematic"):
+        rs = Resampler(n, seed, ShardContext(), scheme=scheme)
+        got = rs.resample_rows(dev.to_device(x), dev.to_device(wn), iteration=it).cpu().numpy()
+        if scheme == "multinomial":
+            want_idx = O.multinomial_ancestors(wn, O.uniforms(seed, it, philox.STREAM_RESAMPLE, 0, n))
+        else:
+            want_idx = O.systematic_ancestors(wn, float(O.uniforms(seed, it, philox.STREAM_RESAMPLE, 0, 1)[0]))
+        idx = rs.last_idx.cpu().numpy()
+        assert (idx != want_idx).mean() <= 1e-4
+        assert np.array_equal(got, x[idx])

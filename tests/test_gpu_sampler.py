@@ -1,0 +1,111 @@
+"""GPU (B200): whole SMCSampler runs through the reference-facing API against the golden reference runs and
+the oracle loop, plus size-independent properties at BASELINE.json's N = 2^20."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import smc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from smcnuts.distributions import StdNormal
+    from smcnuts.model.bridgestan import StanModel
+    from smcnuts.model.device_model import make_model
+    from smcnuts.smc_sampler import SMCSampler
+
+RUNS = [("arma_forward", "arma", {}, "forwardsLKernel"), ("arma_gauss", "arma", {}, "GaussianApproxLKernel"),
+        ("arma_asymptotic", "arma", {}, "asymptoticLKernel"), ("arma_forward_tempered", "arma", {}, "forwardsLKernel"),
+        ("PRMwCD_asymptotic", "PRMwCD", {}, "asymptoticLKernel"), ("gauss8_gaussL", "gauss", {"dim": 8}, "GaussianApproxLKernel")]
+
+
+def _run(tname, kw, N, K, eps, lk, temp, seed=10, **extra):
+    m = make_model(tname, **kw)
+    s = SMCSampler(K=K, N=N, target=m, step_size=eps, sample_proposal=StdNormal(m.dim), momentum_proposal=StdNormal(m.dim),
+                   lkernel=lk, tempering=temp, rng=seed, **extra)
+    s.sample(show_progress=False)
+    return s
+
+
+@pytest.mark.parametrize("name,tname,kw,lk", RUNS)
+def test_small_runs_match_reference_golden(golden, name, tname, kw, lk):
+    """N ~ 100 runs with the reference's configuration (config 1 of BASELINE.json and friends), same Philox
+    streams as the golden reference runs.  Quantities that precede any long trajectory agree tightly; later
+    ones within the drift that 1-ulp libm differences produce through the (chaotic) Hamiltonian flow."""
+    g = golden("runs")
+    N, K, eps, temp = g[f"{name}_cfg"]
+    N, K = int(N), int(K)
+    s = _run(tname, kw, N, K, float(eps), lk, bool(temp))
+    np.testing.assert_allclose(s.x_saved[0].cpu().numpy(), g[f"{name}_x_first"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(s.logw_saved[0].cpu().numpy(), g[f"{name}_logw_first"], rtol=1e-9, atol=1e-9)
+    assert math.isclose(s.phi[0], g[f"{name}_phi"][0], rel_tol=1e-9)
+    assert math.isclose(s.ess[0], g[f"{name}_ess"][0], rel_tol=1e-9)
+    assert math.isclose(s.log_likelihood[0], g[f"{name}_log_likelihood"][0], rel_tol=1e-10)
+    np.testing.assert_allclose(s.mean_estimate[0], g[f"{name}_mean_estimate"][0], rtol=1e-6, atol=1e-9) if lk != "asymptoticLKernel" else None
+    lf_ref = g[f"{name}_leapfrogs"]
+    assert abs(int(s.leapfrogs[0]) - int(lf_ref[0])) <= 0.1 * lf_ref[0] + 64
+    if tname != "PRMwCD":   # short trees: the whole run tracks the reference
+        assert np.array_equal(s.leapfrogs, lf_ref) or np.abs(s.leapfrogs - lf_ref).sum() <= 0.05 * lf_ref.sum()
+        np.testing.assert_allclose(s.phi, g[f"{name}_phi"], rtol=1e-4)
+        np.testing.assert_allclose(s.ess, g[f"{name}_ess"], rtol=0.15)
+        np.testing.assert_allclose(s.mean_estimate[K], g[f"{name}_mean_estimate"][K], rtol=0.2, atol=0.05)
+    assert s.acceptance_rate[K] == 0.0 and s.resampled[K] is False and s.run_time > 0
+    assert s.mean_estimate.shape == (K + 1, s.target.dim) and s.x_saved.shape == (K + 1, N, s.target.dim)
+
+
+def test_config1_arma_forward_tracks_oracle_exactly_in_structure():
+    """BASELINE.json config 1 (arma, N=100, K=10, forward L-kernel) against the oracle loop with the same seed."""
+    o = O.OracleSMC(10, 100, "arma", 0.01, "forwardsLKernel", False, seed=10).run()
+    s = _run("arma", {}, 100, 10, 0.01, "forwardsLKernel", False)
+    assert np.abs(s.leapfrogs - o.n_leapfrog).sum() <= 0.05 * o.n_leapfrog.sum()
+    np.testing.assert_allclose(s.ess, o.ess, rtol=0.15)
+    np.testing.assert_allclose(s.log_likelihood, o.log_likelihood, rtol=0.05, atol=0.5)
+    assert list(s.resampled) == list(o.resampled)
+
+
+def test_stanmodel_constructor_and_readme_signature(tmp_path):
+    from smcnuts.model.device_model import DATA_DIR
+    from smcnuts.proposal.nuts import NUTSProposal
+    m = StanModel("arma", model_path="arma.stan", data_path=str(DATA_DIR / "arma" / "arma.json"))
+    assert m.dim == 4 and m.constrained_dim == 4 and m.param_names[-1] == "sigma"
+    fk = NUTSProposal(m, StdNormal(4), 0.01, rng=3)
+    s = SMCSampler(5, 256, m, fk, StdNormal(4), False, "forwardsLKernel", rng=3)      # README form
+    s.sample(show_progress=False)
+    assert np.all(np.isfinite(s.mean_estimate)) and s.leapfrogs.sum() > 0
+    with pytest.raises(Exception, match="Unknown L-kernel"):
+        SMCSampler(2, 64, m, 0.01, StdNormal(4), StdNormal(4), "nope")
+    with pytest.raises(NotImplementedError):
+        StanModel("eight_schools", "x.stan", None)
+
+
+@pytest.mark.parametrize("lk,temp", [("forwardsLKernel", False), ("GaussianApproxLKernel", False), ("asymptoticLKernel", True)])
+def test_arma_posterior_recovery_large_n(lk, temp):
+    """Final estimates agree with the gold-standard posterior means (stan_models/arma/arma.params) within MC error,
+    and with the oracle's small-N estimate spread."""
+    truth = np.array([0.00678443, 0.95700831, -0.03407898, 0.16660982])
+    sd = np.array([0.0113, 0.0228, 0.0594, 0.0084])
+    K = 30 if temp else 20
+    s = _run("arma", {}, 1 << 15, K, 0.01, lk, temp, seed=3)
+    err = np.abs(s.mean_estimate[K] - truth) / sd
+    assert np.all(err < 0.35), (s.mean_estimate[K], err)
+    if temp:
+        assert s.phi[K] == 1.0 and np.all(np.diff(s.phi) >= 0)
+
+
+def test_full_size_properties_n_2_20():
+    """BASELINE.json config 2 shape (arma, N = 2^20, forward L-kernel), 3 iterations: size-independent properties."""
+    N = 1 << 20
+    s = _run("arma", {}, N, 3, 0.01, "forwardsLKernel", False, seed=10, resampling="systematic")
+    assert np.all(np.isfinite(s.log_likelihood)) and np.all(s.ess > 0) and np.all(s.ess <= N)
+    assert s.leapfrogs.min() >= N                       # every particle takes at least one leapfrog
+    wn = s.samples.wn
+    assert math.isclose(wn.sum().item(), 1.0, rel_tol=1e-9)
+    idx = s.samples.resampler.last_idx
+    if idx is not None:                                  # systematic ancestors are sorted
+        assert bool((idx[1:] >= idx[:-1]).all())
+    # estimates are the importance-weighted mean of the constrained particles
+    x = s.samples.x.clone()
+    x[:, 3] = x[:, 3].exp()
+    np.testing.assert_allclose(s.mean_estimate[3], (wn[:, None] * x).sum(0).cpu().numpy(), rtol=1e-9)

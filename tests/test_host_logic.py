@@ -1,0 +1,155 @@
+"""CPU: host-side logic of the plugin layer (batched bisection, shard routing, seeds, collectives over gloo)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+from scipy.optimize import bisect as scipy_bisect
+
+from oracle import smc_oracle as O
+from smcnuts import _device as dev
+from smcnuts.parallel import ShardContext, split_counts, systematic_slot_bounds
+from smcnuts.tempering.adaptive_tempering import _merge_triples, bisect_batched
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_batched_bisect_reproduces_scipy_bit_for_bit():
+    rng = np.random.default_rng(0)
+    for _ in range(60):
+        a, s = rng.uniform(0.02, 0.98), rng.uniform(0.5, 30)
+        lo = rng.uniform(0.0, a * 0.9)
+        f = lambda p: -(np.tanh(s * (p - a)) + 0.01 * (p - a))   # noqa: E731  positive at lo, negative at 1
+        calls = []
+
+        def fb(ps):
+            calls.append(len(ps))
+            return [f(p) for p in ps]
+        got = bisect_batched(fb, lo, 1.0)
+        assert got == scipy_bisect(f, lo, 1.0) == O.bisect(f, lo, 1.0)
+        assert len(calls) <= 12 and max(calls) <= 16
+
+
+def test_batched_bisect_edge_cases():
+    assert bisect_batched(lambda ps: [1.0 for _ in ps], 0.2, 1.0) == 1.0           # f(1) >= 0 -> 1.0
+    with pytest.raises(ValueError):
+        bisect_batched(lambda ps: [-1.0 for _ in ps], 0.2, 1.0)                     # same sign
+    with pytest.raises(ValueError):
+        bisect_batched(lambda ps: [float("nan") if p < 1 else -1.0 for p in ps], 0.2, 1.0)
+
+
+def test_tempering_golden_through_batched_bisect(golden):
+    g = golden("tempering")
+    for j in range(4):
+        ll, lpri, c = g[f"temper_{j}_loglik"], g[f"temper_{j}_logpri"], g[f"temper_{j}_lp_old"]
+        N = len(ll)
+        fb = lambda ps: [O.ess_at_phi(p, ll, lpri, c) - N * 0.5 for p in ps]   # noqa: E731
+        assert bisect_batched(fb, float(g[f"temper_{j}_old_phi"]), 1.0) == float(g[f"temper_{j}_phi"])
+
+
+def test_merge_triples_matches_direct_logsumexp():
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(4, 1000)) * 30
+    x[2, :] = -np.inf
+    tri = []
+    for p in range(4):
+        fin = x[p][~np.isneginf(x[p])]
+        m = fin.max() if len(fin) else -np.inf
+        tri.append([[m, np.exp(fin - m).sum() if len(fin) else 0.0, np.exp(2 * (fin - m)).sum() if len(fin) else 0.0]])
+    m = _merge_triples(np.array(tri))[0]
+    wn, logZ = O.normalise_weights(x.ravel())
+    assert np.isclose(m[0] + np.log(m[1]), logZ, rtol=1e-14)
+    assert np.isclose(m[1] ** 2 / m[2], O.calculate_ess(wn), rtol=1e-12)
+
+
+def test_systematic_slot_bounds_match_per_slot_search():
+    rng = np.random.default_rng(2)
+    for N, P in ((64, 2), (1000, 4), (4096, 8)):
+        w = rng.exponential(size=N) ** 2
+        w[rng.integers(0, N, N // 4)] = 0
+        cdf = O.cdf_of(w / w.sum())
+        u0 = rng.uniform()
+        idx = O.systematic_ancestors(None, u0, cdf=cdf)
+        m = N // P
+        bounds = systematic_slot_bounds(np.concatenate([[0.0], cdf[m - 1::m]]), u0, N)
+        assert bounds[0] == 0 and bounds[-1] == N and np.all(np.diff(bounds) >= 0)
+        for q in range(P):   # rank q serves exactly the slots whose ancestor it owns
+            served = np.arange(bounds[q], bounds[q + 1])
+            assert np.all(idx[served] // m == q)
+            sc = split_counts(int(bounds[q]), int(bounds[q + 1]), m, P)
+            assert sum(sc) == len(served)
+            assert sc == [int(np.sum(served // m == d)) for d in range(P)]
+
+
+def test_seed_from_rng_is_reproducible():
+    assert dev.seed_from_rng(10) == 10
+    assert dev.seed_from_rng(np.random.RandomState(7)) == dev.seed_from_rng(np.random.RandomState(7))
+    assert dev.seed_from_rng(np.random.default_rng(7)) == dev.seed_from_rng(np.random.default_rng(7))
+    assert dev.seed_from_rng(None) == 0
+
+
+def test_std_normal_detection():
+    from scipy.stats import multivariate_normal
+    assert dev.is_std_normal(multivariate_normal(mean=np.zeros(4), cov=np.eye(4)), 4)
+    assert not dev.is_std_normal(multivariate_normal(mean=np.zeros(4), cov=2 * np.eye(4)), 4)
+    assert not dev.is_std_normal(multivariate_normal(mean=np.ones(4), cov=np.eye(4)), 4)
+
+
+def test_single_shard_context_is_a_noop():
+    import torch
+    s = ShardContext()
+    assert (s.world, s.rank) == (1, 0) and s.local_count(12) == 12 and s.offset(12) == 0
+    t = torch.arange(3.0)
+    assert s.all_gather_vec(t).shape == (1, 3) and s.all_reduce_sum_(t) is t
+
+
+def test_gloo_world2_collectives_and_systematic_routing(tmp_path):
+    """world_size-2 gloo run of the N>1 host path: shard partition, all_gather_vec, all_reduce, the systematic
+    slot split and the all-to-all-v row migration (rows gathered with numpy in place of the CUDA gather)."""
+    script = tmp_path / "w2.py"
+    script.write_text(f'''
+import sys, os
+sys.path.insert(0, {str(ROOT)!r}); sys.path.insert(0, {str(ROOT / "smc-nuts_b200")!r})
+import numpy as np, torch, torch.distributed as dist
+from oracle import smc_oracle as O
+from smcnuts.parallel import ShardContext, split_counts, systematic_slot_bounds
+dist.init_process_group("gloo")
+s = ShardContext()
+assert s.world == 2
+N, D = 512, 3
+rng = np.random.default_rng(4)
+w = rng.exponential(size=N) ** 3; wn = w / w.sum(); x = rng.normal(size=(N, D)); u0 = 0.37
+m = s.local_count(N); lo_p = s.offset(N)
+# global exclusive scan of rank totals, as Resampler._cdf does
+tot = torch.tensor([wn[lo_p:lo_p + m].sum()])
+totals = s.all_gather_vec(tot).view(-1).numpy()
+off = np.concatenate([[0.0], np.cumsum(totals)])
+cdf_local = (off[s.rank] + np.cumsum(wn[lo_p:lo_p + m])) / off[-1]
+lasts = s.all_gather_vec(torch.tensor([cdf_local[-1]])).view(-1).numpy()
+bounds = systematic_slot_bounds(np.concatenate([[0.0], lasts]), u0, N)
+lo, hi = int(bounds[s.rank]), int(bounds[s.rank + 1])
+pos = (np.arange(lo, hi, dtype=np.float64) + u0) / N
+idx_local = np.minimum(np.searchsorted(cdf_local, pos, side="right"), m - 1)
+send = torch.tensor(x[lo_p:lo_p + m][idx_local]).reshape(-1, D)
+send_counts = split_counts(lo, hi, m, 2)
+mylo, myhi = s.rank * m, (s.rank + 1) * m
+recv_counts = [max(0, min(myhi, int(bounds[q + 1])) - max(mylo, int(bounds[q]))) for q in range(2)]
+got = s.all_to_all_rows(send, send_counts, recv_counts).numpy()
+cdf = np.concatenate([c.numpy() for c in [torch.tensor(cdf_local)]])
+full_cdf = s.all_gather_vec(torch.tensor(cdf_local)).view(-1).numpy()
+want = x[np.minimum(np.searchsorted(full_cdf, (np.arange(N) + u0) / N, side="right"), N - 1)][mylo:myhi]
+assert got.shape == want.shape and np.array_equal(got, want), (s.rank, got.shape)
+t = torch.ones(4, dtype=torch.float64) * (s.rank + 1)
+assert torch.equal(s.all_reduce_sum_(t), torch.full((4,), 3.0, dtype=torch.float64))
+assert s.all_reduce_sum_scalar(s.rank + 1) == 3.0
+dist.destroy_process_group()
+print("rank", s.rank, "ok")
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2

@@ -1,0 +1,76 @@
+"""CPU: the DEVICE lane state machine (csrc/nuts_lane.cuh compiled with g++, tests/hostsim) against the
+oracle and the reference golden transitions.  Validates kernel logic without a GPU."""
+import numpy as np
+import pytest
+
+from oracle import smc_oracle as O
+from tests.hostsim import sim
+
+CASES = ["arma", "arma_tempered", "arma_prior", "PRMwCD", "PRMwCD_tempered", "gauss8", "gauss100"]
+
+
+def _target(case):
+    tname = case.split("_")[0]
+    kw = {}
+    if tname.startswith("gauss"):
+        kw, tname = {"dim": int(tname[5:])}, "gauss"
+    return tname, O.COracleTarget(tname, **kw)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("accrej", [False, True])
+def test_lane_matches_reference_golden(golden, case, accrej):
+    g = golden("nuts")
+    tname, t = _target(case)
+    x0, r0 = g[f"{case}_x0"], g[f"{case}_r0"]
+    eps, phi, it, seed = float(g[f"{case}_eps"]), float(g[f"{case}_phi"]), int(g[f"{case}_iteration"]), int(g[f"{case}_seed"])
+    o = sim.nuts(tname, t.np_target, x0, r0, eps, phi, 10, accrej, seed, it, 0, lanes=5)
+    assert np.array_equal(o["n_leapfrog"], g[f"{case}_n_leapfrog"])
+    acc = g[f"{case}_accepted"] if accrej else np.ones(len(x0), dtype=bool)
+    assert np.array_equal(o["accepted"].astype(bool), acc)
+    np.testing.assert_allclose(o["x_new"][acc], g[f"{case}_x_new"][acc], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(o["r_new"][acc], g[f"{case}_r_new"][acc], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(o["x_new"][~acc], x0[~acc]) and np.array_equal(o["r_new"][~acc], r0[~acc])
+
+
+@pytest.mark.parametrize("tname,kw,eps,N", [("arma", {}, 0.01, 400), ("PRMwCD", {}, 0.01, 40),
+                                            ("gauss", {"dim": 8}, 0.1, 300), ("gauss", {"dim": 33}, 0.15, 60)])
+@pytest.mark.parametrize("lanes", [1, 32])
+def test_lane_matches_c_oracle_bitwise(tname, kw, eps, N, lanes):
+    """Same compiler flags, same expression order -> the lane machine must reproduce the recursive C
+    oracle bit for bit (x', r', split log-densities, tree sizes, depths, MH outcomes)."""
+    t = O.COracleTarget(tname, **kw)
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(N, t.dim)) * 0.3
+    if tname == "arma":
+        x += np.array([0.0, 0.9, 0.0, -1.7])
+        x[:20] = rng.normal(size=(20, 4)) * 2.0   # wild starts: divergences, -inf
+        x[0, 3] = 800.0
+    r = rng.normal(size=(N, t.dim))
+    for accrej in (False, True):
+        for phi in (1.0, 0.2):
+            ref = t.nuts_batch(x, r, eps, phi, 10, seed=77, iteration=3, particle0=1000, accrej=accrej)
+            o = sim.nuts(tname, t.np_target, x, r, eps, phi, 10, accrej, 77, 3, 1000, lanes=lanes)
+            assert np.array_equal(o["n_leapfrog"], ref["n_leapfrog"])
+            assert np.array_equal(o["depth"], ref["depth"])
+            assert np.array_equal(o["accepted"], ref["accepted"])
+            assert np.array_equal(o["x_new"], ref["x_new"], equal_nan=True)
+            assert np.array_equal(o["r_new"], ref["r_new"], equal_nan=True)
+            with np.errstate(invalid="ignore"):
+                lp_old = o["A_old"] + phi * o["B_old"]
+                lp_new = o["A_new"] + phi * o["B_new"]
+            lp_old = np.where(np.isfinite(lp_old), lp_old, -np.inf)
+            lp_new = np.where(np.isfinite(lp_new), lp_new, -np.inf)
+            assert np.array_equal(lp_old, ref["lp_old"]) and np.array_equal(lp_new, ref["lp_new"])
+            np.testing.assert_allclose(o["ke_old"], 0.5 * np.sum(r * r, axis=1), rtol=1e-14)
+
+
+def test_max_depth_cap():
+    """depth > MAX_TREE_DEPTH break (nuts.py:109-110): a flat target never U-turns -> 2^(L+1)-1 leapfrogs."""
+    t = O.COracleTarget("gauss", dim=4)
+    x = np.zeros((3, 4)); r = np.ones((3, 4)) * 1e-3
+    for L in (3, 10):
+        ref = t.nuts_batch(x, r, 1e-6, 1.0, L, seed=1)
+        o = sim.nuts("gauss", t.np_target, x, r, 1e-6, 1.0, L, False, 1, 0, 0, lanes=2)
+        assert np.all(ref["n_leapfrog"] == 2 ** (L + 1) - 1) and np.array_equal(o["n_leapfrog"], ref["n_leapfrog"])
+        assert np.array_equal(o["x_new"], ref["x_new"])
