@@ -1,0 +1,273 @@
+"""bench.py -- leapfrog grad-evals/s (and SMC iters/s) of the SMC-NUTS particle hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload arma|PRMwCD|gauss]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+A "step" is one SMC iteration (normalise -> estimate -> ESS -> resample -> NUTS propose -> temper -> reweight,
+/root/reference/smcnuts/smc_sampler.py:109-140) over the whole particle set.  Default workload is
+BASELINE.json configs[1]: arma, N = 2^20 particles per GPU, forward-proposal L-kernel, fp64.  Prints ONE JSON line.
+
+`value`  : leapfrog gradient evaluations per second over the K timed steps, inputs resident in HBM,
+           timed with CUDA events between barriers, max over ranks.
+`e2e`    : the same metric through the reference-facing plugin call NUTSProposal.rvs(x_host, r_host, phi) with
+           pinned HOST buffers: H2D of x and r, the transition, D2H of x_new and r_new, every step.
+`roofline`: the NUTS kernel's algorithmic FP64 FLOPs / its CUDA-event time, against the FP64 FMA peak measured
+           live on this GPU by smcb_probe_fp64 (MEASURED_PEAKS.json carries no FP64 figure).
+`cpu_baseline`: the oracle's C port of the same NUTS transition on this box's host cores (OpenMP, all cores) on a
+           bounded sample of the SAME particle state.
+`--impl reference`: the oracle port of the whole SMC iteration (the reference is pure Python + BridgeStan, which is
+           not installable offline and cannot travel) on the host cores, bounded particle count, same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "smc-nuts_b200"))
+
+WORKLOADS = {
+    # name: (model, model kwargs, step size, lkernel, tempering, log2 particles per GPU, FLOP per fused value+grad)
+    "arma": ("arma", {}, 0.01, "forwardsLKernel", False, 20, 3900.0),
+    "PRMwCD": ("PRMwCD", {}, 0.01, "asymptoticLKernel", True, 20, 5200.0),
+    "gauss": ("gauss", {"dim": 100}, 0.1, "GaussianApproxLKernel", False, 22, 20200.0),
+}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """Reference arm: the oracle port of the SMC iteration on the host cores (all threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import smc_oracle as O
+    model, kw, eps, lk, temp, _, _ = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    n = 1 << args.ref_log2n
+    smc = O.OracleSMC(args.warmup + args.steps, n, model, eps, lk, temp, seed=10, nthreads=cores, target_kw=kw,
+                      save_history=False).init()
+    for k in range(args.warmup):
+        smc.step(k)
+    t0 = time.perf_counter()
+    for k in range(args.warmup, args.warmup + args.steps):
+        smc.step(k)
+    dt = time.perf_counter() - t0
+    lf = int(smc.n_leapfrog[args.warmup:].sum())
+    val = lf / dt
+    sample = f"{n} particles x {args.steps} SMC iterations (of the 2^20-particle workload), oracle C port of NUTS + numpy weights"
+    print(json.dumps({
+        "impl": "reference", "metric": "leapfrog_grad_evals_per_s", "value": val, "unit": "grad-evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "smc_iters_per_s": args.steps / dt,
+        "config": {"workload": f"{args.workload}: {model} N={n} (bounded sample) {lk} tempering={temp} eps={eps}", "particles": n},
+        "cpu_baseline": {"value": val, "unit": "grad-evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "grad-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = pure Python + BridgeStan (not installable offline); timed here: its C/numpy oracle port, all host cores",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="arma", choices=sorted(WORKLOADS))
+    ap.add_argument("--log2n", type=int, default=None, help="log2 particles PER GPU (default: the workload's)")
+    ap.add_argument("--ref-log2n", type=int, default=16, help="particles of the bounded CPU reference sample")
+    ap.add_argument("--cpu-log2n", type=int, default=18, help="particles of the bounded cpu_baseline sample")
+    ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "systematic"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from smcnuts import _cabi, _device as dev
+    from smcnuts.distributions import StdNormal
+    from smcnuts.model.device_model import make_model
+    from smcnuts.proposal.nuts import NUTSProposal
+    from smcnuts.smc_sampler import SMCSampler
+
+    model, kw, eps, lk, temp, log2n, flop_per_eval = WORKLOADS[args.workload]
+    log2n = args.log2n or log2n
+    n_local = 1 << log2n
+    N = n_local * world
+    W, K = args.warmup, args.steps
+    m = make_model(model, **kw)
+    D = m.dim
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- FP64 peak of this GPU (roofline denominator)
+    sink = dev.zeros(1)
+    pb, pt, pi = 148 * 8, 256, 20000
+    peak = 0.0
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); _cabi.call("smcb_probe_fp64", pb, pt, pi, dev.ptr(sink), dev.stream_ptr()); b.record()
+        torch.cuda.synchronize()
+        peak = max(peak, pb * pt * pi * 16 / (a.elapsed_time(b) * 1e-3))
+
+    # ---------------------------------------------------------------- device-resident run: W warm-up + K timed steps
+    smc = SMCSampler(K=W + K, N=N, target=m, step_size=eps, sample_proposal=StdNormal(D), momentum_proposal=StdNormal(D),
+                     lkernel=lk, tempering=temp, rng=10, resampling=args.resampling, save_history=(lk == "asymptoticLKernel"))
+    smc.begin()
+    smc.forward_kernel.record_events = True
+    for k in range(W):
+        smc.iterate(k)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _cabi.lib().smcb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(W, W + K):
+        smc.iterate(k)
+    e1.record()
+    barrier()
+    launches = _cabi.lib().smcb_launch_count() - launches0
+    dt = e0.elapsed_time(e1) * 1e-3
+    lf_local = smc._lf[W:W + K].clone()
+    nuts_dt = sum(a.elapsed_time(b) for a, b in smc.forward_kernel.events[W:W + K]) * 1e-3
+    smc.forward_kernel.record_events = False
+    t = torch.tensor([dt, nuts_dt], dtype=torch.float64, device="cuda")
+    lf_all = lf_local.sum().reshape(1).clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lf_all, op=dist.ReduceOp.SUM)
+    dt, nuts_dt = t.tolist()
+    lf_total = int(lf_all.item())
+    value = lf_total / dt
+    lf_rank = int(lf_local.sum().item())
+
+    # ---------------------------------------------------------------- e2e: plugin API with pinned host buffers
+    fk = NUTSProposal(m, StdNormal(D), eps, rng=10)
+    fk.particle0 = rank * n_local
+    x_host = smc.samples.x.cpu().pin_memory()
+    r_host = torch.empty_like(x_host).pin_memory()
+    r_host.copy_(StdNormal(D, seed=11).rvs(n_local, iteration=0, particle0=rank * n_local))
+    phi = float(smc.samples.phi_new)
+    e2e_lf = 0
+    for _ in range(3):
+        fk.rvs(x_host, r_host, phi)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    t0.record()
+    for _ in range(K):
+        xn, rn = fk.rvs(x_host, r_host, phi)
+        e2e_lf += int(fk.last["n_leapfrog"].sum().item())       # D2H read of the step's result
+    t1.record()
+    barrier()
+    e2e_dt = max(t0.elapsed_time(t1) * 1e-3, time.perf_counter() - wall0 if world == 1 else 0.0)
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+    le = torch.tensor([e2e_lf], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(le, op=dist.ReduceOp.SUM)
+    e2e_val = le.item() / te.item()
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---------------------------------------------------------------- cpu_baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import smc_oracle as O
+        cores = os.cpu_count() or 1
+        ns = min(n_local, 1 << args.cpu_log2n)
+        t_or = O.COracleTarget(model, **kw)
+        xs = x_host[:ns].numpy().copy()
+        rs = r_host[:ns].numpy().copy()
+        c0 = time.perf_counter()
+        ref = t_or.nuts_batch(xs, rs, eps, phi, 10, seed=10, iteration=0, accrej=(lk == "asymptoticLKernel"), nthreads=cores)
+        cdt = time.perf_counter() - c0
+        cpu = {"value": float(ref["n_leapfrog"].sum()) / cdt, "unit": "grad-evals/s", "cores": cores, "kind": "port",
+               "sample": f"one NUTS transition for the first {ns} of the {n_local} particles of the timed state "
+                         f"({int(ref['n_leapfrog'].sum())} leapfrogs, {cdt:.2f} s), oracle/smc_oracle.c with OpenMP"}
+
+    if rank == 0:
+        evals = lf_rank + K * n_local                      # leapfrogs + the initial evaluation of every transition
+        achieved = evals * flop_per_eval / nuts_dt
+        hist = (K + W + 1) * n_local * (D + 1) * 8 if smc.save_history else 0
+        ws_bytes = n_local * 8 * (4 * D + 12)
+        line = {
+            "metric": "leapfrog_grad_evals_per_s", "value": value, "unit": "grad-evals/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "smc_iters_per_s": K / dt,
+            "leapfrogs_per_particle_per_step": lf_total / (K * N),
+            "config": {"workload": f"{args.workload}: {model} N={n_local}/GPU (global {N}) {lk} tempering={temp} eps={eps} "
+                                   f"resampling={args.resampling}, BASELINE.json configs[{ {'arma': 1, 'PRMwCD': 2, 'gauss': 3}[args.workload] }]",
+                       "particles_per_gpu": n_local, "particles_global": N, "dim": D,
+                       "l2": f"per-step working set {ws_bytes / 1e6:.0f} MB of particle arrays (> 126 MB L2 from N=2^20, D>=4: "
+                             f"x, r, x_new, r_new + 12 per-particle scalars), inputs larger than L2; no explicit flush"},
+            "e2e": {"value": e2e_val, "unit": "grad-evals/s", "h2d_bytes_per_step": 2 * n_local * D * 8,
+                    "d2h_bytes_per_step": 2 * n_local * D * 8 + 8, "ms_per_step": te.item() / K * 1e3,
+                    "api": "smcnuts.proposal.nuts.NUTSProposal.rvs(x_host, r_host, phi) with pinned host tensors"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "kernel": "nuts_transition_kernel", "achieved": achieved / 1e12, "peak": peak / 1e12,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "measured live: smcb_probe_fp64 DFMA loop on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
+                         "flop_per_eval": flop_per_eval, "evals": evals, "kernel_s": nuts_dt,
+                         "kernel_share_of_step": nuts_dt / dt},
+            "cpu_baseline": cpu,
+            "clocks": clk,
+            "history_bytes": hist,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

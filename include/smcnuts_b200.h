@@ -144,6 +144,9 @@ int smcb_gaussL_factor(const double* gram, long long N_total, int D, double ridg
 int smcb_gaussL_logpdf(const double* r_new, const double* x_new, long long N, int D, const double* mean,
                        const double* G, const double* logdet, double* out, void* stream);
 
+/* out[0] (int64) = sum of an int32 array: the per-iteration leapfrog / grad-eval counter */
+int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, void* stream);
+
 /* ---- measurement helper: dependent-chain-free DFMA loop; out_flops[0] = FLOPs executed (device double) */
 int smcb_probe_fp64(int blocks, int threads, int iters, double* out_sink, void* stream);
 

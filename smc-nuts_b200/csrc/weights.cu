@@ -356,6 +356,37 @@ __global__ void __launch_bounds__(kRedThreads) count_moved_kernel(const double* 
     }
 }
 
+// sum of an int32 array -> int64 (the grad-eval counter of the metric)
+__global__ void __launch_bounds__(kRedThreads) sum_int32_kernel(const int* __restrict__ v, long long N, long long* out,
+                                                                 double* ws) {
+    __shared__ long long sh[kRedThreads / 32];
+    __shared__ bool is_last;
+    long long acc = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) acc += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    long long* wsl = (long long*)ws;
+    if (threadIdx.x == 0) {
+        long long s = 0;
+        for (int w = 0; w < kRedThreads / 32; ++w) s += sh[w];
+        wsl[(size_t)blockIdx.x * kRedMaxVals] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    unsigned* counter = (unsigned*)(ws + (size_t)kRedMaxBlocks * kRedMaxVals);
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        long long s = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += ((const volatile long long*)wsl)[(size_t)b * kRedMaxVals];
+        out[0] = s;
+        *counter = 0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ FP64 probe
 __global__ void probe_fp64_kernel(int iters, double* sink) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -545,6 +576,14 @@ int smcb_count_moved(const double* x, const double* x_new, long long N, int D, d
     if (reset_counter(workspace, st)) return -1;
     count_moved_kernel<<<stride_grid(N, kRedThreads, 8), kRedThreads, 0, st>>>(x, x_new, N, D, out_count, (double*)workspace);
     return check_launch("count_moved_kernel");
+}
+
+int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, void* stream) {
+    SMCB_REQUIRE(v && out && workspace && N >= 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (reset_counter(workspace, st)) return -1;
+    sum_int32_kernel<<<stride_grid(N, kRedThreads, 8), kRedThreads, 0, st>>>(v, N, out, (double*)workspace);
+    return check_launch("sum_int32_kernel");
 }
 
 int smcb_probe_fp64(int blocks, int threads, int iters, double* out_sink, void* stream) {

@@ -31,7 +31,7 @@ def is_host(a):
 def to_device(a, dtype=F64):
     """numpy / torch(any device) -> contiguous CUDA tensor (no copy if already there)."""
     if isinstance(a, torch.Tensor):
-        return a.to(device=device(), dtype=dtype).contiguous()
+        return a.to(device=device(), dtype=dtype, non_blocking=True).contiguous()
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device())
 
 
@@ -40,6 +40,17 @@ def like_input(t, ref):
     if is_host(ref):
         return t.cpu().numpy()
     return t
+
+
+def to_host_like(t, ref):
+    """Device result -> the container type of `ref`: CUDA tensor in -> CUDA tensor out; host buffers (numpy or
+    CPU torch tensors) come back through a pinned staging buffer (one async D2H + sync)."""
+    if isinstance(ref, torch.Tensor) and ref.is_cuda:
+        return t
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host if isinstance(ref, torch.Tensor) else host.numpy()
 
 
 def empty(*shape, dtype=F64):

@@ -30,6 +30,8 @@ class NUTSProposal:
         self.iteration = 0        # Philox iteration key; SMCSampler sets it, standalone calls auto-increment
         self.particle0 = 0        # global index of local particle 0 (multi-GPU shards)
         self.last = None          # per-particle by-products of the last transition (device tensors)
+        self.record_events = False  # bench.py: CUDA events tightly around the kernel launch
+        self.events = []
 
     def rvs(self, x_cond, r_cond, phi: float = 1.0):
         """Propagate particles through one NUTS transition each.  numpy in -> numpy out; CUDA tensors stay put."""
@@ -37,7 +39,7 @@ class NUTSProposal:
         r = dev.to_device(r_cond).reshape(-1, self.target.dim)
         out = self.transition(x, r, phi)
         self.iteration += 1
-        return dev.like_input(out["x_new"], x_cond), dev.like_input(out["r_new"], r_cond)
+        return dev.to_host_like(out["x_new"], x_cond), dev.to_host_like(out["r_new"], r_cond)
 
     def transition(self, x, r, phi=1.0, iteration=None):
         """Device entry point: returns dict of device tensors (x_new, r_new, A_old, B_old, A_new, B_new,
@@ -52,12 +54,18 @@ class NUTSProposal:
                  A_new=dev.empty(N), B_new=dev.empty(N), ke_old=dev.empty(N), ke_new=dev.empty(N),
                  n_leapfrog=dev.empty(N, dtype=torch.int32), accepted=dev.empty(N, dtype=torch.int32),
                  depth=dev.empty(N, dtype=torch.int32))
+        if self.record_events:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _cabi.call("smcb_nuts_transition", h, dev.ptr(x), dev.ptr(r), N, self.step_size, float(phi),
                    self.max_tree_depth, int(self.accept_reject), self.seed, it, self.particle0,
                    dev.ptr(o["x_new"]), dev.ptr(o["r_new"]), dev.ptr(o["A_old"]), dev.ptr(o["B_old"]),
                    dev.ptr(o["A_new"]), dev.ptr(o["B_new"]), dev.ptr(o["ke_old"]), dev.ptr(o["ke_new"]),
                    dev.ptr(o["n_leapfrog"]), dev.ptr(o["accepted"]), dev.ptr(o["depth"]), dev.ptr(ws), ws.numel(),
                    dev.stream_ptr())
+        if self.record_events:
+            e1.record()
+            self.events.append((e0, e1))
         self.last = o
         return o
 

@@ -107,35 +107,39 @@ class SMCSampler:
             _cabi.call("smcb_count_moved", dev.ptr(s.x), dev.ptr(s.x_new), s.n_local, s.D, dev.ptr(self._moved[k:k + 1]),
                        dev.ptr(dev.reduce_ws()), dev.stream_ptr())
 
-    def sample(self, show_progress=True):
-        """Sample from the target distribution using an SMC sampler (smc_sampler.py:101-155)."""
-        start_time = time()
+    def begin(self):
+        """Allocate the per-run counters; sample() calls this, bench.py calls it before stepping manually."""
+        self._ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(self.K)]
+        self._ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(self.K)]
+        self._lf = dev.zeros(self.K, dtype=torch.int64)
+        self._start_time = time()
+
+    def iterate(self, k):
+        """One SMC iteration, in the reference's order of operations (smc_sampler.py:109-140)."""
         s = self.samples
-        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(self.K)]
-        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(self.K)]
-        lf = dev.zeros(self.K, dtype=torch.int64)
+        self.phi[k] = s.phi_new
+        s.normalise_weights()
+        mean_estimate, variance_estimate = self.estimator.return_estimate(s.x, s.wn)
+        s.calculate_ess()
+        s.resample_if_required()
+        self.resampled[k] = s.resampled_last
+        self._ev0[k].record()
+        s.propose_samples()
+        self._ev1[k].record()
+        if getattr(s, "n_leapfrog", None) is not None:
+            _cabi.call("smcb_sum_int32", dev.ptr(s.n_leapfrog), s.n_local, dev.ptr(self._lf[k:k + 1]),
+                       dev.ptr(dev.reduce_ws()), dev.stream_ptr())
+        s.update_temperature()
+        s.reweight()
+        self.update_sampler(k, mean_estimate, variance_estimate)
+        s.update_samples()
+        if self.save_history:
+            self._x_saved[k + 1].copy_(s.x_new)
+            self._logw_saved[k + 1].copy_(s.logw_new)
 
-        for k in tqdm(range(self.K), desc="NUTS Sampling", disable=not show_progress):
-            self.phi[k] = s.phi_new
-            s.normalise_weights()
-            mean_estimate, variance_estimate = self.estimator.return_estimate(s.x, s.wn)
-            s.calculate_ess()
-            s.resample_if_required()
-            self.resampled[k] = s.resampled_last
-            ev0[k].record()
-            s.propose_samples()
-            ev1[k].record()
-            if getattr(s, "n_leapfrog", None) is not None:
-                lf[k] = s.n_leapfrog.sum(dtype=torch.int64)
-            s.update_temperature()
-            s.reweight()
-            self.update_sampler(k, mean_estimate, variance_estimate)
-            s.update_samples()
-            if self.save_history:
-                self._x_saved[k + 1].copy_(s.x_new)
-                self._logw_saved[k + 1].copy_(s.logw_new)
-
-        # final estimates from the last proposal step (smc_sampler.py:143-149)
+    def finish(self):
+        """Final estimates from the last proposal step (smc_sampler.py:143-155)."""
+        s = self.samples
         s.normalise_weights()
         mean_estimate, variance_estimate = self.estimator.return_estimate(s.x, s.wn)
         s.calculate_ess()
@@ -143,8 +147,8 @@ class SMCSampler:
         self.phi[self.K] = s.phi_new
 
         torch.cuda.synchronize()
-        self.leapfrogs = self.shard.all_reduce_sum_(lf).cpu().numpy()
-        self.propose_time = np.array([a.elapsed_time(b) * 1e-3 for a, b in zip(ev0, ev1)])
+        self.leapfrogs = self.shard.all_reduce_sum_(self._lf.clone()).cpu().numpy()
+        self.propose_time = np.array([a.elapsed_time(b) * 1e-3 for a, b in zip(self._ev0, self._ev1)])
         self.mean_estimate = self._mean_dev.cpu().numpy()
         self.variance_estimate = self._var_dev.cpu().numpy()
         self.acceptance_rate = self.shard.all_reduce_sum_(self._moved.clone()).cpu().numpy() / self.N
@@ -155,4 +159,11 @@ class SMCSampler:
                 self._x_saved, self._logw_saved, self.phi)
 
         torch.cuda.synchronize()
-        self.run_time = time() - start_time
+        self.run_time = time() - self._start_time
+
+    def sample(self, show_progress=True):
+        """Sample from the target distribution using an SMC sampler (smc_sampler.py:101-155)."""
+        self.begin()
+        for k in tqdm(range(self.K), desc="NUTS Sampling", disable=not show_progress):
+            self.iterate(k)
+        self.finish()
