@@ -105,9 +105,15 @@ static void arma_split(const Model* m, const double* x, double* A, double* B, do
     double e = y[0] - (mu + beta * mu);
     double dm = -(1.0 + beta), db = -mu, dt = 0.0;
     double S = e * e, Sm = e * dm, Sb = e * db, St = e * dt;
+    /* err[t] = y[t] - (mu + beta*y[t-1] + theta*err[t-1]) (arma.stan:26-27), associated as
+     * (y[t] - (mu + beta*y[t-1])) - theta*err[t-1] -- the same order as the device function in
+     * smc-nuts_b200/csrc/models.cuh, so the g++ build of the device lane code is bit-identical to this oracle.
+     * oracle/models.py keeps the literal Stan order; the two agree to ~1e-15 (tests/test_oracle_golden.py). */
+    const double ntheta = -theta;
     for (int t = 1; t < T; ++t) {
-        double en = y[t] - (mu + beta * y[t - 1] + theta * e);
-        double dmn = -1.0 - theta * dm, dbn = -y[t - 1] - theta * db, dtn = -e - theta * dt;
+        double c = y[t] - (mu + beta * y[t - 1]);
+        double en = ntheta * e + c;
+        double dmn = ntheta * dm - 1.0, dbn = ntheta * db - y[t - 1], dtn = ntheta * dt - e;
         e = en; dm = dmn; db = dbn; dt = dtn;
         S += e * e; Sm += e * dm; Sb += e * db; St += e * dt;
     }

@@ -52,11 +52,17 @@ struct ArmaModel {
         double e = ylag - (mu + beta * mu);
         double dm = -(1.0 + beta), db = -mu, dt = 0.0;
         double S = e * e, Sm = e * dm, Sb = e * db, St = e * dt;
-#pragma unroll 4
+        // One DFMA per loop-carried chain and step (e, d_mu, d_beta, d_theta) plus four accumulator DFMAs: the
+        // y-only part of nu[t] is formed off the critical path, so a single warp keeps the FP64 pipe busy.
+        const double ntheta = -theta;
+#pragma unroll 8
         for (int t = 1; t < T; ++t) {
             const double yt = y[t];
-            const double en = yt - (mu + beta * ylag + theta * e);
-            const double dmn = -1.0 - theta * dm, dbn = -ylag - theta * db, dtn = -e - theta * dt;
+            const double c = yt - (mu + beta * ylag);       // y[t] - (mu + beta*y[t-1]); independent of the chains
+            const double en = ntheta * e + c;                // err[t] = y[t] - nu[t]              (arma.stan:26-27)
+            const double dmn = ntheta * dm - 1.0;
+            const double dbn = ntheta * db - ylag;
+            const double dtn = ntheta * dt - e;
             e = en; dm = dmn; db = dbn; dt = dtn; ylag = yt;
             S += e * e; Sm += e * dm; Sb += e * db; St += e * dt;
         }

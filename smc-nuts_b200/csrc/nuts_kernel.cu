@@ -5,6 +5,7 @@
 // owns one particle at a time and pulls the next index from a global atomic queue (warp-aggregated)
 // when its tree ends, which absorbs the 1..2047-leapfrog raggedness of NUTS trees
 // (/root/reference/smcnuts/proposal/nuts.py:50-53 loops particles serially instead).
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,6 +29,13 @@ int device_sm_count() {
         if (n <= 0) n = 148;
     }
     return n;
+}
+
+// Tuning knob for experiments (tools/quick_time.py): cap on resident CTAs per SM of the NUTS kernel.
+static int blocks_per_sm_cap() {
+    const char* e = getenv("SMCB_NUTS_BLOCKS_PER_SM");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 1 << 20;
 }
 
 template <class M> struct LaunchCfg;
@@ -127,6 +135,7 @@ static int launch_nuts(const Model* mdl, NutsArgs a, long long ws_bytes, cudaStr
     int occ = 0;
     SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
     if (occ < 1) return fail("smcb_nuts_transition", "kernel does not fit on an SM");
+    if (occ > blocks_per_sm_cap()) occ = blocks_per_sm_cap();
     long long blocks = (long long)device_sm_count() * occ;
     const long long need = (a.N + NT - 1) / NT;
     if (blocks > need) blocks = need;

@@ -213,16 +213,23 @@ __device__ void lse_block_finish(Lse (&v)[NV], double* ws, double* out, int nv) 
     unsigned* counter = (unsigned*)(ws + (size_t)kRedMaxBlocks * kRedMaxVals);
     if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last) {
+    if (is_last) {  // all threads of the last block merge the per-block partials: strided, then warp/block tree
         __threadfence();
-        if (threadIdx.x < nv) {
-            const int j = threadIdx.x;
+        for (int j = 0; j < nv; ++j) {
             Lse r = lse_empty();
-            for (unsigned b = 0; b < gridDim.x; ++b) {
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += kRedThreads) {
                 const volatile double* p = ws + (size_t)b * kRedMaxVals + j * 3;
                 r = lse_merge(r, Lse{p[0], p[1], p[2]});
             }
-            out[j * 3] = r.m; out[j * 3 + 1] = r.s1; out[j * 3 + 2] = r.s2;
+            r = lse_warp_reduce(r);
+            __syncthreads();
+            if (lane == 0) { sh[warp * 3] = r.m; sh[warp * 3 + 1] = r.s1; sh[warp * 3 + 2] = r.s2; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                Lse t = lse_empty();
+                for (int w = 0; w < kRedThreads / 32; ++w) t = lse_merge(t, Lse{sh[w * 3], sh[w * 3 + 1], sh[w * 3 + 2]});
+                out[j * 3] = t.m; out[j * 3 + 1] = t.s1; out[j * 3 + 2] = t.s2;
+            }
         }
         if (threadIdx.x == 0) *counter = 0;
     }
@@ -311,11 +318,18 @@ __global__ void __launch_bounds__(kRedThreads) weighted_moment_kernel(const doub
     unsigned* counter = (unsigned*)(ws + (size_t)kRedMaxBlocks * kRedMaxVals);
     if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last) {
+    if (is_last) {  // thread t sums column (t % D) over blocks t/D, t/D + used/D, ...; then the same column fold
         __threadfence();
+        double a2 = 0.0;
+        if ((int)threadIdx.x < threads_used)
+            for (unsigned b = threadIdx.x / D; b < gridDim.x; b += threads_used / D)
+                a2 += ((const volatile double*)ws)[(size_t)b * kRedMaxVals + col];
+        __syncthreads();
+        sh[threadIdx.x] = a2;
+        __syncthreads();
         if ((int)threadIdx.x < D) {
             double s = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) s += ((const volatile double*)ws)[(size_t)b * kRedMaxVals + threadIdx.x];
+            for (int t = threadIdx.x; t < threads_used; t += D) s += sh[t];
             out[threadIdx.x] = s;
         }
         if (threadIdx.x == 0) *counter = 0;
@@ -347,12 +361,21 @@ __global__ void __launch_bounds__(kRedThreads) count_moved_kernel(const double* 
     unsigned* counter = (unsigned*)(ws + (size_t)kRedMaxBlocks * kRedMaxVals);
     if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last) {
         __threadfence();
         double s = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += ((const volatile double*)ws)[(size_t)b * kRedMaxVals];
-        out[0] = s;
-        *counter = 0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kRedThreads) s += ((const volatile double*)ws)[(size_t)b * kRedMaxVals];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kRedThreads / 32; ++w) t += sh[w];
+            out[0] = t;
+            *counter = 0;
+        }
     }
 }
 
@@ -378,12 +401,21 @@ __global__ void __launch_bounds__(kRedThreads) sum_int32_kernel(const int* __res
     unsigned* counter = (unsigned*)(ws + (size_t)kRedMaxBlocks * kRedMaxVals);
     if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last) {
         __threadfence();
         long long s = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += ((const volatile long long*)wsl)[(size_t)b * kRedMaxVals];
-        out[0] = s;
-        *counter = 0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kRedThreads) s += ((const volatile long long*)wsl)[(size_t)b * kRedMaxVals];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long t = 0;
+            for (int w = 0; w < kRedThreads / 32; ++w) t += sh[w];
+            out[0] = t;
+            *counter = 0;
+        }
     }
 }
 
@@ -518,7 +550,7 @@ int smcb_lse_partial(const double* logw, long long N, double* out3, void* worksp
     SMCB_REQUIRE(logw && out3 && workspace && N >= 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (reset_counter(workspace, st)) return -1;
-    lse_partial_kernel<<<stride_grid(N, kRedThreads, 8), kRedThreads, 0, st>>>(logw, N, out3, (double*)workspace);
+    lse_partial_kernel<<<stride_grid(N, kRedThreads * 4, 4), kRedThreads, 0, st>>>(logw, N, out3, (double*)workspace);
     return check_launch("lse_partial_kernel");
 }
 
@@ -549,7 +581,7 @@ int smcb_ess_multi_phi(const double* loglik, const double* logpri, const double*
     SMCB_REQUIRE(m >= 1 && m <= kMaxPhi, "1 <= m <= 16 candidate temperatures per pass");
     cudaStream_t st = (cudaStream_t)stream;
     if (reset_counter(workspace, st)) return -1;
-    const int grid = stride_grid(N, kRedThreads, 4);
+    const int grid = stride_grid(N, kRedThreads * 2, 4);
     if (m == 1) ess_multi_phi_kernel<1><<<grid, kRedThreads, 0, st>>>(loglik, logpri, c, N, phis, m, out, (double*)workspace);
     else if (m <= 4) ess_multi_phi_kernel<4><<<grid, kRedThreads, 0, st>>>(loglik, logpri, c, N, phis, m, out, (double*)workspace);
     else if (m <= 8) ess_multi_phi_kernel<8><<<grid, kRedThreads, 0, st>>>(loglik, logpri, c, N, phis, m, out, (double*)workspace);
@@ -564,7 +596,7 @@ int smcb_weighted_moment(const double* x, const double* wn, long long N, int D, 
     cudaStream_t st = (cudaStream_t)stream;
     if (reset_counter(workspace, st)) return -1;
     const int used = (kRedThreads / D) * D;
-    weighted_moment_kernel<<<stride_grid(N * D, kRedThreads, 8), kRedThreads, 0, st>>>(x, wn, N, D, constrain, center,
+    weighted_moment_kernel<<<stride_grid(N * D, kRedThreads * 4, 4), kRedThreads, 0, st>>>(x, wn, N, D, constrain, center,
                                                                                         power, out, (double*)workspace, used);
     return check_launch("weighted_moment_kernel");
 }
@@ -574,7 +606,7 @@ int smcb_count_moved(const double* x, const double* x_new, long long N, int D, d
     SMCB_REQUIRE(x && x_new && out_count && workspace && N >= 0 && D >= 1, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (reset_counter(workspace, st)) return -1;
-    count_moved_kernel<<<stride_grid(N, kRedThreads, 8), kRedThreads, 0, st>>>(x, x_new, N, D, out_count, (double*)workspace);
+    count_moved_kernel<<<stride_grid(N, kRedThreads * 2, 4), kRedThreads, 0, st>>>(x, x_new, N, D, out_count, (double*)workspace);
     return check_launch("count_moved_kernel");
 }
 
@@ -582,7 +614,7 @@ int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, v
     SMCB_REQUIRE(v && out && workspace && N >= 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (reset_counter(workspace, st)) return -1;
-    sum_int32_kernel<<<stride_grid(N, kRedThreads, 8), kRedThreads, 0, st>>>(v, N, out, (double*)workspace);
+    sum_int32_kernel<<<stride_grid(N, kRedThreads * 4, 4), kRedThreads, 0, st>>>(v, N, out, (double*)workspace);
     return check_launch("sum_int32_kernel");
 }
 

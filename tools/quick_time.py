@@ -56,17 +56,23 @@ def nuts(name, N, eps, flop_per_eval, spread, centre, iters=3):
 
 
 if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
     print(torch.cuda.get_device_name(0))
-    probe()
-    nuts("arma", 1 << 20, 0.01, 3900, 0.02, [0.0068, 0.957, -0.034, float(np.log(0.1666))])
-    nuts("PRMwCD", 1 << 16, 0.01, 5200, 0.02, [0.8925, 0.0946, 1.3969, 0.1151, -1.4883, -0.0898, 0.6766, -1.7521, -0.3014,
-                                             1.6721, -0.1868, -0.1491, float(np.log(0.3326))], iters=2)
-    nuts("gauss", 1 << 14, 0.1, 20200, 1.0, [0.0] * 100, iters=2)
-    m = make_model("arma")
-    t0 = time.time()
-    s = SMCSampler(K=10, N=1 << 20, target=m, step_size=0.01, sample_proposal=StdNormal(4), momentum_proposal=StdNormal(4),
-                   lkernel="forwardsLKernel", tempering=False, rng=10)
-    s.sample(show_progress=False)
-    print(f"SMC arma N=2^20 K=10: run_time {s.run_time:.3f}s (ctor+run {time.time() - t0:.3f}s), leapfrogs {s.leapfrogs}, "
-          f"propose ms {np.round(s.propose_time * 1e3, 2)}")
-    print("mean", s.mean_estimate[-1], "ess", s.ess)
+    if which in ("all", "probe"):
+        probe()
+    if which in ("all", "arma"):
+        nuts("arma", 1 << 20, 0.01, 3900, 0.02, [0.0068, 0.957, -0.034, float(np.log(0.1666))], iters=4)
+    if which in ("all", "prm"):
+        nuts("PRMwCD", 1 << 18, 0.01, 5200, 0.02, [0.8925, 0.0946, 1.3969, 0.1151, -1.4883, -0.0898, 0.6766, -1.7521, -0.3014,
+                                                 1.6721, -0.1868, -0.1491, float(np.log(0.3326))], iters=2)
+    if which in ("all", "gauss"):
+        nuts("gauss", 1 << 14, 0.1, 20200, 1.0, [0.0] * 100, iters=2)
+    if which in ("all", "smc"):
+        m = make_model("arma")
+        t0 = time.time()
+        s = SMCSampler(K=10, N=1 << 20, target=m, step_size=0.01, sample_proposal=StdNormal(4), momentum_proposal=StdNormal(4),
+                       lkernel="forwardsLKernel", tempering=False, rng=10)
+        s.sample(show_progress=False)
+        print(f"SMC arma N=2^20 K=10: run_time {s.run_time:.3f}s (ctor+run {time.time() - t0:.3f}s), leapfrogs {s.leapfrogs}, "
+              f"propose ms {np.round(s.propose_time * 1e3, 2)}")
+        print("mean", s.mean_estimate[-1], "ess", s.ess)
