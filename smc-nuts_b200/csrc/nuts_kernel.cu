@@ -56,8 +56,8 @@ __device__ __forceinline__ const double* stage_model(const ModelDesc& d, double*
     }
 }
 
-template <class M>
-__global__ void __launch_bounds__(LaunchCfg<M>::NT, LaunchCfg<M>::MIN_BLOCKS)
+template <class M, int MINB>
+__global__ void __launch_bounds__(LaunchCfg<M>::NT, MINB)
 nuts_transition_kernel(NutsArgs a, int staged, int rec_doubles) {
     extern __shared__ double smem[];
     M model(a.model, stage_model<M>(a.model, smem, staged));
@@ -124,13 +124,32 @@ __global__ void combine_logp_kernel(const double* __restrict__ A, const double* 
     }
 }
 
+// Experiment hook: SMCB_NUTS_MINB selects a register budget (min resident CTAs/SM in __launch_bounds__).
+static int minb_override() {
+    const char* e = getenv("SMCB_NUTS_MINB");
+    return e ? atoi(e) : 0;
+}
+template <class M>
+static auto pick_kernel() {
+    switch (minb_override()) {
+        case 1: return nuts_transition_kernel<M, 1>;
+        case 2: return nuts_transition_kernel<M, 2>;
+        case 3: return nuts_transition_kernel<M, 3>;
+        case 4: return nuts_transition_kernel<M, 4>;
+        case 5: return nuts_transition_kernel<M, 5>;
+        case 6: return nuts_transition_kernel<M, 6>;
+        case 8: return nuts_transition_kernel<M, 8>;
+        default: return nuts_transition_kernel<M, LaunchCfg<M>::MIN_BLOCKS>;
+    }
+}
+
 template <class M>
 static int launch_nuts(const Model* mdl, NutsArgs a, long long ws_bytes, cudaStream_t st) {
     const int NT = LaunchCfg<M>::NT;
     const int D = M::dim_of(mdl->desc);
     const int staged = M::staged_doubles(mdl->desc);
     const size_t smem = sizeof(double) * (size_t)staged;
-    auto kern = nuts_transition_kernel<M>;
+    auto kern = pick_kernel<M>();
     if (smem > 48 * 1024) SMCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
@@ -154,7 +173,7 @@ static long long nuts_ws_bytes(const Model* mdl, long long N, int max_depth) {
     const int NT = LaunchCfg<M>::NT;
     const int D = M::dim_of(mdl->desc);
     const size_t smem = sizeof(double) * (size_t)M::staged_doubles(mdl->desc);
-    auto kern = nuts_transition_kernel<M>;
+    auto kern = pick_kernel<M>();
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) return -1;

@@ -214,7 +214,7 @@ def test_reweight_kernels_match_oracle(golden):
         with np.errstate(invalid="ignore"):
             f = lambda p: np.where(np.isfinite(A + p * B), A + p * B, -np.inf)   # noqa: E731
             want = O.reweight_asymptotic(logw, f(0.7), f(0.2))
-        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-13, equal_nan=True)
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-13, atol=1e-14, equal_nan=True)   # FMA in A + phi*B
     g = golden("lkernel_weights")
     for D in (4, 13, 100):
         m, _ = _models(f"gauss{D}")
@@ -325,7 +325,7 @@ def test_cdf_scan_and_systematic(n):
     bad = idx != want
     pos = (np.arange(n) + u0) / n
     assert bad.mean() <= 1e-5 and np.all(np.abs(pos[bad] - cdf[np.minimum(idx[bad], want[bad])]) < 1e-15)
-    assert (np.diff(idx) < 0).mean() <= 1e-5 and np.mean(wn[idx] > 0) > 0.9999
+    assert (np.diff(idx) < 0).sum() <= 1e-5 * n and np.mean(wn[idx] > 0) > 0.9999
     counts = np.bincount(idx, minlength=n)
     assert np.all(np.abs(counts - n * wn) < 1.0 + 1e-6 * n)                      # systematic: |offspring - N w| < 1
 

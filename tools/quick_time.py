@@ -62,6 +62,18 @@ if __name__ == "__main__":
         probe()
     if which in ("all", "arma"):
         nuts("arma", 1 << 20, 0.01, 3900, 0.02, [0.0068, 0.957, -0.034, float(np.log(0.1666))], iters=4)
+    if which == "logp":
+        for name, flop, D in (("arma", 3900, 4), ("PRMwCD", 5200, 13)):
+            m = make_model(name)
+            x = torch.randn(1 << 22, D, dtype=torch.float64, device="cuda") * 0.1
+            A, B, g = dev.empty(1 << 22), dev.empty(1 << 22), dev.empty(1 << 22, D)
+            for N in (1 << 20, 1 << 22):
+                t, _ = ev_time(lambda: _cabi.call("smcb_logp_grad", m.handle, dev.ptr(x), N, 1.0, dev.ptr(A), dev.ptr(B), dev.ptr(g),
+                                                  dev.stream_ptr()))
+                print(f"logp_grad {name} N={N}: {t * 1e6:.1f} us -> {N * flop / t / 1e12:.2f} TFLOP/s")
+    if which == "armaN":
+        for lg in (18, 19, 20, 21, 22, 23):
+            nuts("arma", 1 << lg, 0.01, 3900, 0.02, [0.0068, 0.957, -0.034, float(np.log(0.1666))], iters=3)
     if which in ("all", "prm"):
         nuts("PRMwCD", 1 << 18, 0.01, 5200, 0.02, [0.8925, 0.0946, 1.3969, 0.1151, -1.4883, -0.0898, 0.6766, -1.7521, -0.3014,
                                                  1.6721, -0.1868, -0.1491, float(np.log(0.3326))], iters=2)
