@@ -105,19 +105,123 @@ def run_reference(args):
     }))
 
 
+def run_micro(args):
+    """BASELINE.json configs[4]: weight-update + ESS + systematic resampling microbench, D = 16, 2^25 particles
+    per GPU (2^28 over 8 GPUs), sharded with all-to-all-v migration.  HBM-bound: algorithmic bytes per particle are
+    SURVEY.md section 8d's: reweight 16D+32, normalise+ESS 24, scan 16, ancestors 12, gather 16D+4."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from smcnuts import _cabi, _device as dev
+    from smcnuts.parallel import ShardContext
+    from smcnuts.samples.samples import Resampler, normalise
+    D = 16
+    n = 1 << (args.log2n or 25)
+    N = n * world
+    sh = ShardContext()
+    off = rank * n
+    st = dev.stream_ptr()
+
+    def normal(shape_n, d, stream, it):
+        out = dev.empty(shape_n, d) if d else dev.empty(shape_n)
+        _cabi.call("smcb_normals", 10, it, stream, off, shape_n, d or 1, dev.ptr(out), st)
+        return out
+    x, r, r_new = normal(n, D, 4, 0), normal(n, D, 1, 0), normal(n, D, 1, 1)
+    logw0, lp_x, lp_xn = normal(n, 0, 5, 0), normal(n, 0, 5, 1), normal(n, 0, 5, 2)
+    logw = dev.empty(n)
+    _cabi.call("smcb_affine", dev.ptr(logw0), n, 2.0, 0.0, dev.ptr(logw), st)          # logw ~ N(0, 2^2)
+    out = dev.empty(n)
+    rs = Resampler(N, 10, sh, scheme="systematic")
+    rs.keep_idx = False
+    names = ["reweight_forward", "lse+normalise", "scan(cdf)", "ancestors+gather+migrate"]
+    alg_bytes = [16 * D + 32, 24, 16, 12 + 16 * D + 4]   # SURVEY 8d: 288 + 24 + 16 + (12 + 260) = 600 B at D = 16
+    W, K = max(args.warmup, 3), args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(K)]
+
+    def step(it, ev=None):
+        if ev: ev[0].record()
+        _cabi.call("smcb_reweight_forward", dev.ptr(logw), dev.ptr(lp_x), dev.ptr(lp_xn), dev.ptr(r), dev.ptr(r_new), n, D,
+                   dev.ptr(out), st)
+        if ev: ev[1].record()
+        wn, stats, _ = normalise(out, sh)
+        if ev: ev[2].record()
+        cdf = rs._cdf(wn)
+        if ev: ev[3].record()
+        rs_x = rs.resample_from_cdf(x, cdf, it)
+        if ev: ev[4].record()
+        return rs_x, stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for it in range(W):
+        step(it)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = _cabi.lib().smcb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(K):
+        xs, stats = step(W + it, evs[it])
+    e1.record()
+    barrier()
+    launches = _cabi.lib().smcb_launch_count() - l0
+    dt = e0.elapsed_time(e1) * 1e-3
+    per = np.array([[ev[i].elapsed_time(ev[i + 1]) * 1e-3 for i in range(len(names))] for ev in evs]).mean(axis=0)
+    t = torch.tensor([dt] + list(per), dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt, per = t[0].item(), t[1:].cpu().numpy()
+    clk = clocks.stop() if rank == 0 else None
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    if rank == 0:
+        ess = float(stats[1].item())
+        kern = {nm: {"ms": float(p * 1e3), "alg_bytes_per_particle": b, "achieved_gbs": b * n / p / 1e9, "frac": b * n / p / 1e9 / hbm}
+                for nm, p, b in zip(names, per, alg_bytes)}
+        total_b = sum(alg_bytes)
+        print(json.dumps({
+            "metric": "resample_chain_particles_per_s", "value": N * K / dt, "unit": "particles/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"micro: weight-update + ESS + systematic resampling, D={D}, N={n}/GPU (global {N}), "
+                                   "BASELINE.json configs[4]", "particles_per_gpu": n, "dim": D, "ess": ess,
+                       "l2": f"arrays of {n * D * 8 / 1e9:.1f} GB each, far larger than L2"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": total_b * n / (dt / K) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": total_b * n / (dt / K) / 1e9 / hbm, "traffic": None,
+                         "alg_bytes_per_particle": total_b,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "kernels": kern, "clocks": clk,
+            "migrated_rows_last_step": rs.last_migrated_rows,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="arma", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="arma", choices=sorted(WORKLOADS) + ["micro"])
     ap.add_argument("--log2n", type=int, default=None, help="log2 particles PER GPU (default: the workload's)")
     ap.add_argument("--ref-log2n", type=int, default=16, help="particles of the bounded CPU reference sample")
     ap.add_argument("--cpu-log2n", type=int, default=18, help="particles of the bounded cpu_baseline sample")
     ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "systematic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload == "micro":
+        return run_micro(args)
     if args.impl == "reference":
         return run_reference(args)
 

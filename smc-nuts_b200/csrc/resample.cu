@@ -175,6 +175,58 @@ __global__ void gather_rows_kernel(const double* __restrict__ x, const int64_t* 
     }
 }
 
+// Systematic ancestors + gather fused (no index round trip through HBM).  Positions are sorted, so the ancestors of
+// one tile of output rows lie in one contiguous cdf range [bounds[t], bounds[t+1]]:
+//   pass 1 (tile_bounds_kernel): one full binary search per TILE, all tiles in parallel (latency hidden by parallelism);
+//   pass 2 (resample_systematic_fused_kernel): warps take tiles in grid-stride order (balanced, address-local), every
+//   row searches only inside its tile's (L1-resident) range and copies its ancestor's row with 16-byte accesses.
+__global__ void tile_bounds_kernel(const double* __restrict__ cdf, long long N, double u0, long long j0,
+                                   long long M_total, long long M, int rows_per_tile, long long ntiles,
+                                   long long* __restrict__ bounds) {
+    const double den = (double)M_total;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t <= ntiles; t += (long long)gridDim.x * blockDim.x) {
+        const long long j = min(M - 1, t * rows_per_tile);   // first row of tile t (last row overall for t == ntiles)
+        bounds[t] = upper_bound(cdf, N, ((double)(j0 + j) + u0) / den);
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) resample_systematic_fused_kernel(const double* __restrict__ cdf, long long N,
+                                                                        double u0, long long j0, long long M_total,
+                                                                        long long M, const double* __restrict__ x,
+                                                                        double* __restrict__ out,
+                                                                        int64_t* __restrict__ idx,
+                                                                        const long long* __restrict__ bounds) {
+    constexpr int D = 2 * LPR, GROUPS = 32 / LPR, R = 8, ROWS = GROUPS * R;   // rows per warp tile
+    const int lane = threadIdx.x & 31, sub = lane % LPR, g = lane / LPR;
+    const double den = (double)M_total;
+    const long long ntiles = (M + ROWS - 1) / ROWS;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (long long tile = wid; tile < ntiles; tile += nwarps) {
+        const long long jlo = tile * ROWS, jhi = min(M, jlo + ROWS) - 1;
+        const long long blo = bounds[tile], bhi = bounds[tile + 1];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const long long j = jlo + g + (long long)k * GROUPS;
+            if (j <= jhi) {
+                long long lo = blo, hi = bhi;   // the ancestor lies in [blo, bhi]
+                if (lo < hi) {
+                    const double pos = ((double)(j0 + j) + u0) / den;
+                    while (lo < hi) {
+                        const long long mid = (lo + hi) >> 1;
+                        if (pos < cdf[mid]) hi = mid;
+                        else lo = mid + 1;
+                    }
+                }
+                const double2 v = *reinterpret_cast<const double2*>(x + lo * D + 2 * sub);
+                *reinterpret_cast<double2*>(out + j * D + 2 * sub) = v;
+                if (idx && sub == 0) idx[j] = lo;
+            }
+        }
+    }
+}
+
 }  // namespace smcb
 
 using namespace smcb;
@@ -217,6 +269,47 @@ int smcb_ancestors_systematic(const double* cdf, long long N, double u0, long lo
     if (M == 0) return 0;
     ancestors_systematic_kernel<<<stride_grid(M, 256, 8), 256, 0, (cudaStream_t)stream>>>(cdf, N, u0, j0, M_total, M, idx);
     return check_launch("ancestors_systematic_kernel");
+}
+
+long long smcb_resample_workspace_bytes(long long M, int D) {
+    const int lpr = D >= 2 ? D / 2 : 1;
+    const int rows = (32 / (lpr > 32 ? 32 : lpr)) * 8;
+    return ((M + rows - 1) / rows + 2) * 8;
+}
+
+int smcb_resample_systematic(const double* cdf, long long N, double u0, long long j0, long long M_total, long long M,
+                             const double* x, int D, double* out, int64_t* idx, void* workspace, void* stream) {
+    SMCB_REQUIRE(cdf && x && out && workspace && N >= 1 && M >= 0 && M_total >= 1 && D >= 1, "bad argument");
+    SMCB_REQUIRE(x != out, "resampling cannot run in place");
+    if (M == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = (((uintptr_t)x | (uintptr_t)out) % 16) == 0;
+    if (aligned && (D == 2 || D == 4 || D == 8 || D == 16 || D == 32 || D == 64)) {
+        const int lpr = D / 2;
+        const int rows = (32 / lpr) * 8;
+        const long long ntiles = (M + rows - 1) / rows;
+        long long* bounds = (long long*)workspace;
+        tile_bounds_kernel<<<stride_grid(ntiles + 1, 256, 8), 256, 0, st>>>(cdf, N, u0, j0, M_total, M, rows, ntiles, bounds);
+        if (check_launch("tile_bounds_kernel")) return -1;
+        const long long blocks = (ntiles + 7) / 8;
+        const long long cap = (long long)device_sm_count() * 8;
+        const int grid = (int)(blocks < cap ? blocks : cap);
+        switch (lpr) {
+            case 1: resample_systematic_fused_kernel<1><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
+            case 2: resample_systematic_fused_kernel<2><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
+            case 4: resample_systematic_fused_kernel<4><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
+            case 8: resample_systematic_fused_kernel<8><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
+            case 16: resample_systematic_fused_kernel<16><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
+            default: resample_systematic_fused_kernel<32><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
+        }
+        return check_launch("resample_systematic_fused_kernel");
+    }
+    // general D: separate ancestor search (needs idx scratch from the caller) and gather
+    SMCB_REQUIRE(idx, "this D needs an idx buffer (unfused path)");
+    ancestors_systematic_kernel<<<stride_grid(M, 256, 8), 256, 0, st>>>(cdf, N, u0, j0, M_total, M, idx);
+    if (check_launch("ancestors_systematic_kernel")) return -1;
+    gather_rows_kernel<1><<<stride_grid(M * D, 256, 8), 256, 0, st>>>(x, idx, M, D, out);
+    return check_launch("gather_rows_kernel");
 }
 
 int smcb_gather_rows(const double* x, const int64_t* idx, long long M, int D, double* out, void* stream) {

@@ -54,6 +54,62 @@ __device__ __forceinline__ void tile_half_sqnorm(const double* __restrict__ r, l
     __syncthreads();
 }
 
+// Cooperative variant for D = 2*LPR (LPR = lanes per row, a power of two): LPR adjacent lanes read one row as
+// 16-byte chunks, so every warp-level load covers 32/LPR whole rows = 512 contiguous bytes; the squares are folded
+// with log2(LPR) shuffles.  ROWS_PER_ITER rows per group are in flight to keep enough bytes outstanding.
+template <int LPR>
+__device__ __forceinline__ double group_half_sqnorm(const double* __restrict__ rowp, int sub) {
+    const double2 v = *reinterpret_cast<const double2*>(rowp + 2 * sub);
+    double s = v.x * v.x + v.y * v.y;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return 0.5 * s;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) reweight_forward_coop_kernel(const double* __restrict__ logw,
+                                                                    const double* __restrict__ lp_x,
+                                                                    const double* __restrict__ lp_xnew,
+                                                                    const double* __restrict__ r,
+                                                                    const double* __restrict__ r_new, long long N,
+                                                                    double* __restrict__ out) {
+    constexpr int D = 2 * LPR, U = LPR < 4 ? LPR : 4;  // lane `sub` < U of a group finishes row i0 + sub
+    const int sub = threadIdx.x % LPR;
+    const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+    const long long ngroups = (long long)gridDim.x * blockDim.x / LPR;
+    const long long nfull = (N / U) * U;
+    for (long long i0 = group * U; i0 < nfull; i0 += ngroups * U) {
+        double2 a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a[u] = *reinterpret_cast<const double2*>(r + (i0 + u) * D + 2 * sub);
+            b[u] = *reinterpret_cast<const double2*>(r_new + (i0 + u) * D + 2 * sub);
+        }
+        double k0[U], k1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { k0[u] = a[u].x * a[u].x + a[u].y * a[u].y; k1[u] = b[u].x * b[u].x + b[u].y * b[u].y; }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                k0[u] += __shfl_xor_sync(0xffffffffu, k0[u], o);
+                k1[u] += __shfl_xor_sync(0xffffffffu, k1[u], o);
+            }
+        if (sub < U) {  // lane `sub` of the group finishes row i0 + sub: coalesced 8-byte scalars
+            double kk0 = k0[0], kk1 = k1[0];
+#pragma unroll
+            for (int u = 1; u < U; ++u) if (sub == u) { kk0 = k0[u]; kk1 = k1[u]; }
+            const long long i = i0 + sub;
+            out[i] = logw[i] + lp_xnew[i] - lp_x[i] + (-0.5 * kk1) - (-0.5 * kk0);
+        }
+    }
+    // tail rows (N % U)
+    for (long long i = nfull + group; i < N; i += ngroups) {
+        const double k0 = group_half_sqnorm<LPR>(r + i * D, sub), k1 = group_half_sqnorm<LPR>(r_new + i * D, sub);
+        if (sub == 0) out[i] = logw[i] + lp_xnew[i] - lp_x[i] + (-k1) - (-k0);
+    }
+}
+
 __global__ void row_half_sqnorm_kernel(const double* __restrict__ r, long long N, int D, double* __restrict__ out) {
     extern __shared__ double sm[];
     constexpr int ROWS = kRedThreads;
@@ -512,6 +568,19 @@ int smcb_reweight_forward(const double* logw, const double* lp_x, const double* 
                           const double* r_new, long long N, int D, double* out, void* stream) {
     SMCB_REQUIRE(logw && lp_x && lp_xnew && r && r_new && out && N >= 0 && D >= 1 && D <= 110, "bad argument (D <= 110)");
     if (N == 0) return 0;
+    const bool aligned = (((uintptr_t)r | (uintptr_t)r_new) % 16) == 0;
+    if (aligned && (D == 4 || D == 8 || D == 16 || D == 32 || D == 64)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const int grid = stride_grid(N * (D / 2) / (D >= 8 ? 4 : 2), 256, 8);
+        switch (D) {
+            case 4: reweight_forward_coop_kernel<2><<<grid, 256, 0, st>>>(logw, lp_x, lp_xnew, r, r_new, N, out); break;
+            case 8: reweight_forward_coop_kernel<4><<<grid, 256, 0, st>>>(logw, lp_x, lp_xnew, r, r_new, N, out); break;
+            case 16: reweight_forward_coop_kernel<8><<<grid, 256, 0, st>>>(logw, lp_x, lp_xnew, r, r_new, N, out); break;
+            case 32: reweight_forward_coop_kernel<16><<<grid, 256, 0, st>>>(logw, lp_x, lp_xnew, r, r_new, N, out); break;
+            default: reweight_forward_coop_kernel<32><<<grid, 256, 0, st>>>(logw, lp_x, lp_xnew, r, r_new, N, out); break;
+        }
+        return check_launch("reweight_forward_coop_kernel");
+    }
     const size_t smem = tile_smem(D);
     if (smem > 48 * 1024)
         SMCB_CUDA(cudaFuncSetAttribute(reweight_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -45,6 +45,7 @@ class Resampler:
         self.N, self.seed, self.shard, self.stream, self.scheme = N, seed, shard, stream, scheme
         self.n_local = shard.local_count(N)
         self.offset = shard.offset(N)
+        self.keep_idx = True          # materialise the ancestor indices (diagnostic; bench.py turns it off)
         self.last_idx = None          # ancestors of the last resample (global indices for this rank's slots)
         self.last_migrated_rows = 0   # rows this rank received from other ranks (diagnostic)
 
@@ -67,17 +68,25 @@ class Resampler:
 
     def resample_rows(self, x, wn, iteration):
         """Returns the resampled rows for this rank's output slots."""
+        return self.resample_from_cdf(x, self._cdf(wn), iteration)
+
+    def resample_from_cdf(self, x, cdf, iteration):
         sh, st = self.shard, dev.stream_ptr()
         n, D = x.shape
-        cdf = self._cdf(wn)
         if sh.world == 1:
             idx = dev.empty(n, dtype=torch.int64)
             if self.scheme == "multinomial":
                 u = dev.empty(n)
                 _cabi.call("smcb_uniforms", self.seed, iteration, self.stream, 0, n, 0, dev.ptr(u), st)
                 _cabi.call("smcb_ancestors_multinomial", dev.ptr(cdf), n, dev.ptr(u), n, dev.ptr(idx), st)
-            else:
-                _cabi.call("smcb_ancestors_systematic", dev.ptr(cdf), n, self._u0(iteration), 0, n, n, dev.ptr(idx), st)
+            else:   # ancestors + gather in one kernel; idx is kept only as a diagnostic
+                out = dev.empty(n, D)
+                keep = idx if (self.keep_idx or D not in (2, 4, 8, 16, 32, 64)) else None
+                ws = dev.workspace("resample", _cabi.lib().smcb_resample_workspace_bytes(n, D))
+                _cabi.call("smcb_resample_systematic", dev.ptr(cdf), n, self._u0(iteration), 0, n, n, dev.ptr(x), D,
+                           dev.ptr(out), dev.ptr(keep), dev.ptr(ws), st)
+                self.last_idx = keep
+                return out
             out = dev.empty(n, D)
             _cabi.call("smcb_gather_rows", dev.ptr(x), dev.ptr(idx), n, D, dev.ptr(out), st)
             self.last_idx = idx
@@ -103,8 +112,9 @@ class Resampler:
         idx = dev.empty(max(m, 1), dtype=torch.int64)
         send = dev.empty(max(m, 1), D)
         if m:
-            _cabi.call("smcb_ancestors_systematic", dev.ptr(cdf), n, u0, lo, self.N, m, dev.ptr(idx), st)
-            _cabi.call("smcb_gather_rows", dev.ptr(x), dev.ptr(idx), m, D, dev.ptr(send), st)
+            ws = dev.workspace("resample", _cabi.lib().smcb_resample_workspace_bytes(m, D))
+            _cabi.call("smcb_resample_systematic", dev.ptr(cdf), n, u0, lo, self.N, m, dev.ptr(x), D, dev.ptr(send),
+                       dev.ptr(idx), dev.ptr(ws), st)
         send_counts = split_counts(lo, hi, self.n_local, sh.world)
         mylo, myhi = sh.rank * self.n_local, (sh.rank + 1) * self.n_local
         recv_counts = [max(0, min(myhi, int(bounds[q + 1])) - max(mylo, int(bounds[q]))) for q in range(sh.world)]
