@@ -131,10 +131,15 @@ def run_micro(args):
         out = dev.empty(shape_n, d) if d else dev.empty(shape_n)
         _cabi.call("smcb_normals", 10, it, stream, off, shape_n, d or 1, dev.ptr(out), st)
         return out
-    x, r, r_new = normal(n, D, 4, 0), normal(n, D, 1, 0), normal(n, D, 1, 1)
-    logw0, lp_x, lp_xn = normal(n, 0, 5, 0), normal(n, 0, 5, 1), normal(n, 0, 5, 2)
-    logw = dev.empty(n)
-    _cabi.call("smcb_affine", dev.ptr(logw0), n, 2.0, 0.0, dev.ptr(logw), st)          # logw ~ N(0, 2^2)
+    # synthetic inputs (generated outside the timed region): momenta before/after a short move, mild log-weights with a
+    # trend across the global index so that rank weight totals differ (ESS ~ 0.3 N; ~1/4 of the rows migrate at P = 8)
+    x, r = normal(n, D, 4, 0), normal(n, D, 1, 0)
+    r_new = r + 0.05 * normal(n, D, 1, 1)
+    lp_x = normal(n, 0, 5, 1)
+    lp_xn = lp_x + 0.1 * normal(n, 0, 5, 2)
+    gidx = (torch.arange(n, device=x.device, dtype=torch.float64) + off) / N - 0.5
+    logw = normal(n, 0, 5, 0) + 1.5 * gidx
+    del gidx
     out = dev.empty(n)
     rs = Resampler(N, 10, sh, scheme="systematic")
     rs.keep_idx = False
