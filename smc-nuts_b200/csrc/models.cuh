@@ -33,6 +33,8 @@ struct ModelDesc {
 struct ArmaModel {
     static constexpr int DMAX = 4;
     static constexpr int STATIC_D = 4;
+    static constexpr int GROUP = 1, NLOC = 4, STATIC_NL = 4;   // one lane per particle, 4 coordinates per lane
+    SMCB_HD constexpr int nloc() const { return 4; }
     const double* y;
     int T;
     SMCB_HD explicit ArmaModel(const ModelDesc& d, const double* staged) : y(staged), T(d.T) {}
@@ -82,6 +84,8 @@ struct ArmaModel {
 struct PrmModel {
     static constexpr int DMAX = 13;
     static constexpr int STATIC_D = 13;
+    static constexpr int GROUP = 1, NLOC = 13, STATIC_NL = 13;
+    SMCB_HD constexpr int nloc() const { return 13; }
     static constexpr int M = 12, C = 11, ROW = 14;
     const double* rows;
     int NO;
@@ -140,6 +144,8 @@ struct PrmModel {
 struct GaussModel {
     static constexpr int DMAX = 128;
     static constexpr int STATIC_D = 0;  // runtime dimension
+    static constexpr int GROUP = 1, NLOC = 128, STATIC_NL = 0;
+    SMCB_HD int nloc() const { return D; }
     const double* P;
     int D;
     SMCB_HD explicit GaussModel(const ModelDesc& d, const double* staged) : P(staged), D(d.dim) {}
@@ -161,5 +167,65 @@ struct GaussModel {
         B = -0.5 * qf;
     }
 };
+
+// Tensor-core variant for the NUTS kernel: 4 lanes per particle, 8 particles per warp.  Lane `sub` of a group holds
+// coordinates sub, sub+4, ... (exactly the A-fragment layout of mma.m8n8k4: row = particle, col = k), the precision
+// matrix is pre-packed on the host in B-fragment order with the columns of every 8-block permuted so that the C
+// fragment lands in the same ownership pattern (no shuffles): -P x for 8 particles costs 2*NT8^2 DMMA + as many
+// conflict-free 256-byte shared-memory loads.  NT8 = ceil(D/8) blocks of 8 coordinates (zero padded).
+template <int NT8>
+struct GaussModelG {
+    static constexpr int DMAX = 8 * NT8;
+    static constexpr int STATIC_D = 0;
+    static constexpr int GROUP = 4, NLOC = 2 * NT8, STATIC_NL = 2 * NT8, KK = 2 * NT8;
+    const double* pfrag;  // [NT8][KK][32] doubles, shared memory
+    int D;
+    SMCB_HD explicit GaussModelG(const ModelDesc& d, const double* staged) : pfrag(staged), D(d.dim) {}
+    SMCB_HD static int dim_of(const ModelDesc& d) { return d.dim; }
+    SMCB_HD int dim() const { return D; }
+    SMCB_HD constexpr int nloc() const { return NLOC; }
+    static int staged_doubles(const ModelDesc&) { return NT8 * KK * 32; }
+    static int frag_offset(const ModelDesc& d) { return d.dim * d.dim; }  // pfrag follows the plain matrix in the blob
+
+    SMCB_HD void eval(const double (&x)[NLOC], double phi, double& A, double& B, double (&g)[NLOC]) const {
+#if defined(__CUDA_ARCH__)
+        const int lane = threadIdx.x & 31;
+        double qf = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT8; ++nt) {
+            double c0 = 0.0, c1 = 0.0;
+            const double* bp = pfrag + (size_t)nt * KK * 32 + lane;
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) {
+                const double b = bp[kk * 32];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c0), "+d"(c1) : "d"(x[kk]), "d"(b));
+            }
+            g[2 * nt] = phi * (-c0);
+            g[2 * nt + 1] = phi * (-c1);
+            qf += x[2 * nt] * c0 + x[2 * nt + 1] * c1;
+        }
+        qf += __shfl_xor_sync(0xffffffffu, qf, 1);
+        qf += __shfl_xor_sync(0xffffffffu, qf, 2);
+        A = 0.0;
+        B = -0.5 * qf;
+#else
+        (void)x; (void)phi; A = B = 0.0; (void)g;
+#endif
+    }
+};
+
+// host-side packing of P into B-fragment order (see GaussModelG)
+inline void pack_gauss_fragments(const double* P, int D, int nt8, double* out) {
+    const int KK = 2 * nt8;
+    for (int nt = 0; nt < nt8; ++nt)
+        for (int kk = 0; kk < KK; ++kk)
+            for (int l = 0; l < 32; ++l) {
+                const int k = 4 * kk + (l % 4);
+                const int n = l / 4;
+                const int col = 8 * nt + 4 * (n % 2) + n / 2;
+                out[((size_t)nt * KK + kk) * 32 + l] = (k < D && col < D) ? P[(size_t)k * D + col] : 0.0;
+            }
+}
 
 }  // namespace smcb

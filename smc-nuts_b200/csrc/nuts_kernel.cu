@@ -38,17 +38,21 @@ static int blocks_per_sm_cap() {
     return v > 0 ? v : 1 << 20;
 }
 
-template <class M> struct LaunchCfg;
-template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 3; };
+template <class M> struct LaunchCfg { static constexpr int NT = 128, MIN_BLOCKS = 2; };   // GaussModelG<NT8>
+template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
 template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2; };
 template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1; };
 
-// Model data (y[200]; the 100 x 14 PRMwCD table) is staged once per CTA into shared memory, where every lane
-// reads the same address each step (broadcast, conflict-free).  The Gaussian precision matrix stays in L1/L2.
+template <class M> struct StageOffset { static int of(const ModelDesc&) { return 0; } };
+template <int NT8> struct StageOffset<GaussModelG<NT8>> { static int of(const ModelDesc& d) { return d.dim * d.dim; } };
+
+// Model data (y[200]; the 100 x 14 PRMwCD table; the Gaussian B-fragments) is staged once per CTA into shared memory,
+// where every lane reads the same address each step (broadcast / conflict-free).  The plain Gaussian precision
+// matrix of the one-lane-per-particle fallback stays in L1/L2.
 template <class M>
-__device__ __forceinline__ const double* stage_model(const ModelDesc& d, double* smem, int staged) {
-    if constexpr (M::STATIC_D != 0) {
-        for (int i = threadIdx.x; i < staged; i += blockDim.x) smem[i] = d.data[i];
+__device__ __forceinline__ const double* stage_model(const ModelDesc& d, double* smem, int staged, int offset) {
+    if constexpr (M::STATIC_NL != 0) {
+        for (int i = threadIdx.x; i < staged; i += blockDim.x) smem[i] = d.data[offset + i];
         __syncthreads();
         return smem;
     } else {
@@ -56,39 +60,41 @@ __device__ __forceinline__ const double* stage_model(const ModelDesc& d, double*
     }
 }
 
-template <class M, int MINB>
-__global__ void __launch_bounds__(LaunchCfg<M>::NT, MINB)
-nuts_transition_kernel(NutsArgs a, int staged, int rec_doubles) {
+template <class M>
+__global__ void __launch_bounds__(LaunchCfg<M>::NT, LaunchCfg<M>::MIN_BLOCKS)
+nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles) {
     extern __shared__ double smem[];
-    M model(a.model, stage_model<M>(a.model, smem, staged));
-    Lane<M> lane;
-    lane.phase = kIdle;
-    double* ws = a.ws + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * rec_doubles;
+    constexpr int G = M::GROUP;
+    M model(a.model, stage_model<M>(a.model, smem, staged, stage_offset));
     const unsigned lane_id = threadIdx.x & 31u;
+    Lane<M> lane;
+    lane.idle_init(model, (int)(lane_id % G));
+    double* ws = a.ws + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * rec_doubles;
+    constexpr unsigned kLeaders = G == 1 ? 0xffffffffu : 0x11111111u;   // first lane of every particle group
+    const unsigned group_first = lane_id & ~(unsigned)(G - 1);
     bool drained = false;
     for (;;) {
-        // ---- refill finished lanes from the particle work queue (warp-aggregated atomic)
+        // ---- refill finished particle groups from the work queue (warp-aggregated atomic)
         const bool want = (lane.phase == kIdle) && !drained;
-        const unsigned m = __ballot_sync(0xffffffffu, want);
+        const unsigned m = __ballot_sync(0xffffffffu, want) & kLeaders;
         if (m) {
             const int leader = __ffs(m) - 1;
             unsigned long long base = 0;
             if ((int)lane_id == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (want) {
-                const long long p = (long long)base + __popc(m & ((1u << lane_id) - 1u));
+                const long long p = (long long)base + __popc(m & ((1u << group_first) - 1u));
                 if (p < a.N) lane.begin(a, model, p, ws);
                 else drained = true;
             }
         }
         if (__all_sync(0xffffffffu, lane.phase == kIdle)) break;
-        // ---- one model evaluation per lane per trip: the initial point or one leapfrog
-        if (lane.phase != kIdle) {
-            lane.pre_eval(a);
-            double A, B, g[M::DMAX];
-            model.eval(lane.xa, a.phi, A, B, g);
-            lane.post_eval(a, A, B, g);
-        }
+        // ---- one model evaluation per particle per trip: the initial point or one leapfrog.  The evaluation is
+        //      executed by every lane (idle ones carry zeros) so that warp-wide tensor-core instructions stay legal.
+        if (lane.phase != kIdle) lane.pre_eval(a);
+        double A, B, g[M::NLOC];
+        model.eval(lane.xa, a.phi, A, B, g);
+        if (lane.phase != kIdle) lane.post_eval(a, A, B, g);
     }
 }
 
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(128) logp_grad_kernel(ModelDesc md, const doub
                                                         double* __restrict__ Bout, double* __restrict__ grad,
                                                         int staged) {
     extern __shared__ double smem[];
-    M model(md, stage_model<M>(md, smem, staged));
+    M model(md, stage_model<M>(md, smem, staged, 0));
     const int D = M::STATIC_D ? M::STATIC_D : model.dim();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
         double xv[M::DMAX], g[M::DMAX], A, B;
@@ -124,65 +130,53 @@ __global__ void combine_logp_kernel(const double* __restrict__ A, const double* 
     }
 }
 
-// Experiment hook: SMCB_NUTS_MINB selects a register budget (min resident CTAs/SM in __launch_bounds__).
-static int minb_override() {
-    const char* e = getenv("SMCB_NUTS_MINB");
-    return e ? atoi(e) : 0;
-}
 template <class M>
-static auto pick_kernel() {
-    switch (minb_override()) {
-        case 1: return nuts_transition_kernel<M, 1>;
-        case 2: return nuts_transition_kernel<M, 2>;
-        case 3: return nuts_transition_kernel<M, 3>;
-        case 4: return nuts_transition_kernel<M, 4>;
-        case 5: return nuts_transition_kernel<M, 5>;
-        case 6: return nuts_transition_kernel<M, 6>;
-        case 8: return nuts_transition_kernel<M, 8>;
-        default: return nuts_transition_kernel<M, LaunchCfg<M>::MIN_BLOCKS>;
-    }
+static long long nuts_blocks(const Model* mdl, long long N, size_t smem, int* occ_out) {
+    const int NT = LaunchCfg<M>::NT;
+    auto kern = nuts_transition_kernel<M>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) return -1;
+    if (occ > blocks_per_sm_cap()) occ = blocks_per_sm_cap();
+    long long blocks = (long long)device_sm_count() * occ;
+    const long long need = (N * M::GROUP + NT - 1) / NT;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    if (occ_out) *occ_out = occ;
+    (void)mdl;
+    return blocks;
+}
+
+template <class M>
+static long long nuts_ws_bytes(const Model* mdl, long long N, int max_depth) {
+    const size_t smem = sizeof(double) * (size_t)M::staged_doubles(mdl->desc);
+    const long long blocks = nuts_blocks<M>(mdl, N, smem, nullptr);
+    if (blocks < 0) return -1;
+    M probe(mdl->desc, nullptr);
+    return (long long)sizeof(double) * nuts_ws_doubles(probe.nloc(), max_depth) * blocks * LaunchCfg<M>::NT + 256;
 }
 
 template <class M>
 static int launch_nuts(const Model* mdl, NutsArgs a, long long ws_bytes, cudaStream_t st) {
     const int NT = LaunchCfg<M>::NT;
-    const int D = M::dim_of(mdl->desc);
     const int staged = M::staged_doubles(mdl->desc);
     const size_t smem = sizeof(double) * (size_t)staged;
-    auto kern = pick_kernel<M>();
-    if (smem > 48 * 1024) SMCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
-    if (occ < 1) return fail("smcb_nuts_transition", "kernel does not fit on an SM");
-    if (occ > blocks_per_sm_cap()) occ = blocks_per_sm_cap();
-    long long blocks = (long long)device_sm_count() * occ;
-    const long long need = (a.N + NT - 1) / NT;
-    if (blocks > need) blocks = need;
-    const int rec = nuts_ws_doubles(D, a.max_depth);
+    const long long blocks = nuts_blocks<M>(mdl, a.N, smem, nullptr);
+    if (blocks < 0) return fail("smcb_nuts_transition", "kernel does not fit on an SM");
+    M probe(mdl->desc, nullptr);
+    const int rec = nuts_ws_doubles(probe.nloc(), a.max_depth);
     const long long ws_need = (long long)sizeof(double) * rec * blocks * NT + 256;
     if (ws_bytes < ws_need) return fail("smcb_nuts_transition", "workspace too small (see smcb_nuts_workspace_bytes)");
     // queue head lives in the last 256 bytes of the workspace
     a.queue = (unsigned long long*)((char*)a.ws + (ws_need - 256));
     SMCB_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), st));
-    kern<<<(int)blocks, NT, smem, st>>>(a, staged, rec);
+    nuts_transition_kernel<M><<<(int)blocks, NT, smem, st>>>(a, staged, StageOffset<M>::of(mdl->desc), rec);
     return check_launch("nuts_transition_kernel");
 }
 
-template <class M>
-static long long nuts_ws_bytes(const Model* mdl, long long N, int max_depth) {
-    const int NT = LaunchCfg<M>::NT;
-    const int D = M::dim_of(mdl->desc);
-    const size_t smem = sizeof(double) * (size_t)M::staged_doubles(mdl->desc);
-    auto kern = pick_kernel<M>();
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) return -1;
-    long long blocks = (long long)device_sm_count() * occ;
-    const long long need = (N + NT - 1) / NT;
-    if (blocks > need) blocks = need;
-    if (blocks < 1) blocks = 1;
-    return (long long)sizeof(double) * nuts_ws_doubles(D, max_depth) * blocks * NT + 256;
-}
+// Gaussian: tensor-core group kernel for D <= 104, one-lane-per-particle fallback above
+#define SMCB_GAUSS_DISPATCH(D, CALL_G, CALL_PLAIN) \
+    ((D) <= 8 ? CALL_G(1) : (D) <= 16 ? CALL_G(2) : (D) <= 32 ? CALL_G(4) : (D) <= 64 ? CALL_G(8) : (D) <= 104 ? CALL_G(13) : CALL_PLAIN)
 
 template <class M>
 static int launch_logp(const Model* mdl, const double* x, long long N, double phi, double* A, double* B, double* g,
@@ -227,6 +221,11 @@ int smcb_model_create(int kind, const double* host_data, long long n, int dim, v
         SMCB_REQUIRE(dim >= 1 && dim <= GaussModel::DMAX && (long long)dim * dim == n, "gauss: need P[D*D], D <= 128");
         d.dim = dim;
         packed.assign(host_data, host_data + n);
+        if (dim <= 104) {   // B-fragment packing for the tensor-core NUTS kernel, appended to the plain matrix
+            const int nt8 = dim <= 8 ? 1 : dim <= 16 ? 2 : dim <= 32 ? 4 : dim <= 64 ? 8 : 13;
+            packed.resize((size_t)n + (size_t)nt8 * 2 * nt8 * 32);
+            pack_gauss_fragments(host_data, dim, nt8, packed.data() + n);
+        }
     } else {
         return fail("smcb_model_create", "unknown model kind");
     }
@@ -280,7 +279,12 @@ int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long lon
     switch (m->desc.kind) {
         case kArma: b = nuts_ws_bytes<ArmaModel>(m, N, max_depth); break;
         case kPRMwCD: b = nuts_ws_bytes<PrmModel>(m, N, max_depth); break;
-        default: b = nuts_ws_bytes<GaussModel>(m, N, max_depth); break;
+        default: {
+#define WS_G(K) nuts_ws_bytes<GaussModelG<K>>(m, N, max_depth)
+            b = SMCB_GAUSS_DISPATCH(m->desc.dim, WS_G, nuts_ws_bytes<GaussModel>(m, N, max_depth));
+#undef WS_G
+            break;
+        }
     }
     if (b < 0) return fail("smcb_nuts_workspace_bytes", "occupancy query failed");
     *bytes = b;
@@ -309,7 +313,11 @@ int smcb_nuts_transition(void* handle, const double* x, const double* r, long lo
     switch (m->desc.kind) {
         case kArma: return launch_nuts<ArmaModel>(m, a, workspace_bytes, st);
         case kPRMwCD: return launch_nuts<PrmModel>(m, a, workspace_bytes, st);
-        default: return launch_nuts<GaussModel>(m, a, workspace_bytes, st);
+        default: {
+#define LAUNCH_G(K) launch_nuts<GaussModelG<K>>(m, a, workspace_bytes, st)
+            return SMCB_GAUSS_DISPATCH(m->desc.dim, LAUNCH_G, launch_nuts<GaussModel>(m, a, workspace_bytes, st));
+#undef LAUNCH_G
+        }
     }
 }
 

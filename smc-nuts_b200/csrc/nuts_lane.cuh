@@ -56,26 +56,45 @@ struct NutsArgs {
     unsigned long long* queue;  // work-queue head, zeroed before launch
 };
 
-SMCB_HD int nuts_ws_doubles(int D, int L) { return 3 * D + 2 * D * L + (2 * D + 2) * (L + 1); }
+// doubles of workspace per LANE; nl = coordinates held by one lane (D for one-lane-per-particle models)
+SMCB_HD int nuts_ws_doubles(int nl, int L) { return 3 * nl + 2 * nl * L + (2 * nl + 2) * (L + 1); }
 
 enum LanePhase : int { kIdle = 0, kInit = 1, kLeaf = 2 };
 
+// A particle is owned by M::GROUP adjacent lanes (1 for arma / PRMwCD; 4 for the tensor-core Gaussian, where lane
+// `sub` of the group holds coordinates sub, sub+4, sub+8, ...).  All lanes of a group execute the same control flow
+// (same particle, same Philox stream); only dot products need the group fold `gsum`.
 template <class M>
 struct Lane {
-    static constexpr int DM = M::DMAX;
-    double xa[DM], ra[DM], ga[DM];  // active edge
+    static constexpr int G = M::GROUP;
+    static constexpr int DM = M::NLOC;
+    double xa[DM], ra[DM], ga[DM];  // active edge (this lane's coordinates)
     double logu, A0, B0, As, Bs, ke0;
     long long pid;
     double* ws;
-    int phase, dir, depth, D, L;
+    int phase, dir, depth, D, L, nl, sub;
     uint32_t leaf, n_tot, n_leapfrog, free_mask;
     uint64_t pend_n, pend_ref;
     StreamReader rng;
 
-    // ---- workspace views
-    SMCB_HD double* other() const { return ws; }                                   // x, r, g of the inactive edge
-    SMCB_HD double* ckpt(int slot) const { return ws + 3 * D + 2 * D * slot; }      // x, r
-    SMCB_HD double* cand(int slot) const { return ws + 3 * D + 2 * D * L + (2 * D + 2) * slot; }  // x, r, A, B
+#define SMCB_LOCAL(i) for (int i = 0; i < (M::STATIC_NL ? M::STATIC_NL : nl); ++i)
+
+    SMCB_HD int gd(int i) const { return G == 1 ? i : sub + G * i; }   // global coordinate of local slot i
+    SMCB_HD double gsum(double v) const {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) {
+            const unsigned mask = ((1u << G) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(mask, v, o);
+        }
+#endif
+        return v;
+    }
+
+    // ---- workspace views (per lane)
+    SMCB_HD double* other() const { return ws; }                                      // x, r, g of the inactive edge
+    SMCB_HD double* ckpt(int slot) const { return ws + 3 * nl + 2 * nl * slot; }       // x, r
+    SMCB_HD double* cand(int slot) const { return ws + 3 * nl + 2 * nl * L + (2 * nl + 2) * slot; }  // x, r, A, B
 
     // ---- packed per-level pending counts: level l occupies bits [l(l+1)/2, +l+1)
     SMCB_HD uint32_t get_n(int l) const { return (uint32_t)(pend_n >> (l * (l + 1) / 2)) & ((2u << l) - 1u); }
@@ -87,15 +106,19 @@ struct Lane {
     SMCB_HD int get_ref(int l) const { return (int)((pend_ref >> (4 * l)) & 15u); }
     SMCB_HD void set_ref(int l, int s) { pend_ref = (pend_ref & ~((uint64_t)15 << (4 * l))) | ((uint64_t)s << (4 * l)); }
 
-    SMCB_HD int dimension(const M& m) const { return M::STATIC_D ? M::STATIC_D : m.dim(); }
+    SMCB_HD void idle_init(const M& m, int sub_) {
+        phase = kIdle; sub = sub_; D = m.dim(); nl = m.nloc(); pid = -1;
+        SMCB_LOCAL(i) { xa[i] = 0.0; ra[i] = 0.0; ga[i] = 0.0; }
+    }
 
     SMCB_HD void begin(const NutsArgs& a, const M& m, long long p, double* ws_) {
-        pid = p; ws = ws_; D = dimension(m); L = a.max_depth;
+        pid = p; ws = ws_; D = m.dim(); nl = m.nloc(); L = a.max_depth;
         const int d_ = D;
 #pragma unroll
-        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
-            xa[d] = a.x[p * d_ + d];
-            ra[d] = a.r[p * d_ + d];
+        SMCB_LOCAL(i) {
+            const bool ok = gd(i) < d_;
+            xa[i] = ok ? a.x[p * d_ + gd(i)] : 0.0;
+            ra[i] = ok ? a.r[p * d_ + gd(i)] : 0.0;
         }
         rng.reset(a.seed, a.iteration, kStreamNuts, a.particle0 + (uint64_t)p);
         n_leapfrog = 0;
@@ -106,11 +129,10 @@ struct Lane {
     SMCB_HD void pre_eval(const NutsArgs& a) {
         if (phase != kLeaf) return;
         const double half = dir * a.eps / 2, full = dir * a.eps;
-        const int d_ = D;
 #pragma unroll
-        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
-            ra[d] = ra[d] + half * ga[d];
-            xa[d] = xa[d] + full * ra[d];
+        SMCB_LOCAL(i) {
+            ra[i] = ra[i] + half * ga[i];
+            xa[i] = xa[i] + full * ra[i];
         }
     }
 
@@ -118,13 +140,13 @@ struct Lane {
         const int nd = (rng.next() < 0.5) ? 1 : -1;  // nuts.py:91
         if (!first && nd != dir) {                   // bring the other edge into registers
             double* o = other();
-            const int d_ = D;
+            const int n_ = nl;
 #pragma unroll
-            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
+            SMCB_LOCAL(i) {
                 double t;
-                t = o[d]; o[d] = xa[d]; xa[d] = t;
-                t = o[d_ + d]; o[d_ + d] = ra[d]; ra[d] = t;
-                t = o[2 * d_ + d]; o[2 * d_ + d] = ga[d]; ga[d] = t;
+                t = o[i]; o[i] = xa[i]; xa[i] = t;
+                t = o[n_ + i]; o[n_ + i] = ra[i]; ra[i] = t;
+                t = o[2 * n_ + i]; o[2 * n_ + i] = ga[i]; ga[i] = t;
             }
         }
         dir = nd;
@@ -136,49 +158,49 @@ struct Lane {
     // (minus, plus) is restored through `dir`.
     SMCB_HD bool uturn(const double* xc, const double* rc) const {
         double s1 = 0.0, s2 = 0.0;
-        const int d_ = D;
 #pragma unroll
-        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
-            const double dx = xa[d] - xc[d];
-            s1 += dx * rc[d];
-            s2 += dx * ra[d];
+        SMCB_LOCAL(i) {
+            const double dx = xa[i] - xc[i];
+            s1 += dx * rc[i];
+            s2 += dx * ra[i];
         }
+        s1 = gsum(s1); s2 = gsum(s2);
         return (dir * s1 < 0) || (dir * s2 < 0);
     }
 
     SMCB_HD void write_sample_from_active(const NutsArgs& a, double A, double B) {
         const int d_ = D;
 #pragma unroll
-        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
-            a.x_new[pid * d_ + d] = xa[d];
-            a.r_new[pid * d_ + d] = ra[d];
+        SMCB_LOCAL(i) {
+            if (gd(i) < d_) {
+                a.x_new[pid * d_ + gd(i)] = xa[i];
+                a.r_new[pid * d_ + gd(i)] = ra[i];
+            }
         }
         As = A; Bs = B;
     }
 
     // Consume the model evaluation at xa.  Returns true when the transition is complete.
     SMCB_HD bool post_eval(const NutsArgs& a, double A, double B, const double (&gn)[DM]) {
-        const int d_ = D;
+        const int d_ = D, n_ = nl;
         double lp = A + a.phi * B;
         const bool bad = !is_finite(lp);  // bridgestan.py:47-49,79-80: failure -> logp = -inf, grad = -inf
         if (bad) lp = neg_inf();
 #pragma unroll
-        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) ga[d] = bad ? neg_inf() : gn[d];
+        SMCB_LOCAL(i) ga[i] = (bad && gd(i) < d_) ? neg_inf() : gn[i];
 
         if (phase == kInit) {  // nuts.py:66-87
             double rr = 0.0;
 #pragma unroll
-            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) rr += ra[d] * ra[d];
-            ke0 = 0.5 * rr;
+            SMCB_LOCAL(i) rr += ra[i] * ra[i];
+            ke0 = 0.5 * gsum(rr);
             A0 = A; B0 = B;
             const double H0 = lp - ke0;
             logu = H0 - (-log1p(-rng.next()));
             write_sample_from_active(a, A, B);
             double* o = other();
 #pragma unroll
-            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
-                o[d] = xa[d]; o[d_ + d] = ra[d]; o[2 * d_ + d] = ga[d];
-            }
+            SMCB_LOCAL(i) { o[i] = xa[i]; o[n_ + i] = ra[i]; o[2 * n_ + i] = ga[i]; }
             n_tot = 1; depth = 0;
             start_doubling(true);
             phase = kLeaf;
@@ -189,10 +211,11 @@ struct Lane {
         const double half = dir * a.eps / 2;
         double rr = 0.0;
 #pragma unroll
-        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
-            ra[d] = ra[d] + half * ga[d];
-            rr += ra[d] * ra[d];
+        SMCB_LOCAL(i) {
+            ra[i] = ra[i] + half * ga[i];
+            rr += ra[i] * ra[i];
         }
+        rr = gsum(rr);
         ++n_leapfrog;
         ++leaf;
         const double joint = lp - 0.5 * rr;
@@ -205,7 +228,7 @@ struct Lane {
             if ((i0 & 1u) == 0u) {
                 double* c = ckpt(popc32(i0));
 #pragma unroll
-                for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) { c[d] = xa[d]; c[d_ + d] = ra[d]; }
+                SMCB_LOCAL(i) { c[i] = xa[i]; c[n_ + i] = ra[i]; }
             } else {
                 const int tz = ctz32(leaf);
                 for (int l = 0; l < tz; ++l) {  // nuts.py:136-148, second child = running node
@@ -222,7 +245,7 @@ struct Lane {
                     }
                     run_n = tot;
                     const double* c = ckpt(popc32(i0 - (2u << l) + 1u));
-                    if (uturn(c, c + d_)) { ++depth; return finish(a); }
+                    if (uturn(c, c + n_)) { ++depth; return finish(a); }
                 }
             }
         }
@@ -234,16 +257,18 @@ struct Lane {
                 } else {
                     const double* c = cand(run_ref);
 #pragma unroll
-                    for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) {
-                        a.x_new[pid * d_ + d] = c[d];
-                        a.r_new[pid * d_ + d] = c[d_ + d];
+                    SMCB_LOCAL(i) {
+                        if (gd(i) < d_) {
+                            a.x_new[pid * d_ + gd(i)] = c[i];
+                            a.r_new[pid * d_ + gd(i)] = c[n_ + i];
+                        }
                     }
-                    As = c[2 * d_]; Bs = c[2 * d_ + 1];
+                    As = c[2 * n_]; Bs = c[2 * n_ + 1];
                 }
             }
             n_tot += run_n;
             const double* o = other();
-            const bool stop = uturn(o, o + d_);
+            const bool stop = uturn(o, o + n_);
             ++depth;
             if (stop || depth > L) return finish(a);
             start_doubling(false);
@@ -256,8 +281,8 @@ struct Lane {
             free_mask &= ~(1u << run_ref);
             double* c = cand(run_ref);
 #pragma unroll
-            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : d_); ++d) { c[d] = xa[d]; c[d_ + d] = ra[d]; }
-            c[2 * d_] = A; c[2 * d_ + 1] = B;
+            SMCB_LOCAL(i) { c[i] = xa[i]; c[n_ + i] = ra[i]; }
+            c[2 * n_] = A; c[2 * n_ + 1] = B;
         }
         set_n(lv, run_n);
         set_ref(lv, run_ref);
@@ -268,14 +293,16 @@ struct Lane {
     SMCB_HD bool finish(const NutsArgs& a) {
         const int d_ = D;
         double rr = 0.0;
-        bool anyinf = false;
-#pragma unroll 4
-        for (int d = 0; d < d_; ++d) {
-            const double rv = a.r_new[pid * d_ + d], xv = a.x_new[pid * d_ + d];
-            rr += rv * rv;
-            anyinf |= (xv == -neg_inf()) || (xv == neg_inf());
+        int anyinf = 0;
+        SMCB_LOCAL(i) {
+            if (gd(i) < d_) {
+                const double rv = a.r_new[pid * d_ + gd(i)], xv = a.x_new[pid * d_ + gd(i)];
+                rr += rv * rv;
+                anyinf |= (xv == -neg_inf()) || (xv == neg_inf());
+            }
         }
-        double ken = 0.5 * rr;
+        double ken = 0.5 * gsum(rr);
+        if (G > 1) anyinf = gsum((double)anyinf) > 0.0;
         int acc = 1;
         if (a.accrej) {
             double lps = As + a.phi * Bs, lp0 = A0 + a.phi * B0;
@@ -287,26 +314,30 @@ struct Lane {
             const double u = stream_uniform(a.seed, a.iteration, kStreamAccRej, a.particle0 + (uint64_t)pid, 0);
             if (u > prob || anyinf) {
                 acc = 0;
-#pragma unroll 4
-                for (int d = 0; d < d_; ++d) {
-                    a.x_new[pid * d_ + d] = a.x[pid * d_ + d];
-                    a.r_new[pid * d_ + d] = a.r[pid * d_ + d];
+                SMCB_LOCAL(i) {
+                    if (gd(i) < d_) {
+                        a.x_new[pid * d_ + gd(i)] = a.x[pid * d_ + gd(i)];
+                        a.r_new[pid * d_ + gd(i)] = a.r[pid * d_ + gd(i)];
+                    }
                 }
                 As = A0; Bs = B0; ken = ke0;
             }
         }
-        if (a.A_old) a.A_old[pid] = A0;
-        if (a.B_old) a.B_old[pid] = B0;
-        if (a.A_new) a.A_new[pid] = As;
-        if (a.B_new) a.B_new[pid] = Bs;
-        if (a.ke_old) a.ke_old[pid] = ke0;
-        if (a.ke_new) a.ke_new[pid] = ken;
-        if (a.n_leapfrog) a.n_leapfrog[pid] = (int)n_leapfrog;
-        if (a.accepted) a.accepted[pid] = acc;
-        if (a.depth) a.depth[pid] = depth;
+        if (sub == 0) {
+            if (a.A_old) a.A_old[pid] = A0;
+            if (a.B_old) a.B_old[pid] = B0;
+            if (a.A_new) a.A_new[pid] = As;
+            if (a.B_new) a.B_new[pid] = Bs;
+            if (a.ke_old) a.ke_old[pid] = ke0;
+            if (a.ke_new) a.ke_new[pid] = ken;
+            if (a.n_leapfrog) a.n_leapfrog[pid] = (int)n_leapfrog;
+            if (a.accepted) a.accepted[pid] = acc;
+            if (a.depth) a.depth[pid] = depth;
+        }
         phase = kIdle;
         return true;
     }
+#undef SMCB_LOCAL
 };
 
 }  // namespace smcb

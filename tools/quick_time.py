@@ -78,7 +78,7 @@ if __name__ == "__main__":
         nuts("PRMwCD", 1 << 18, 0.01, 5200, 0.02, [0.8925, 0.0946, 1.3969, 0.1151, -1.4883, -0.0898, 0.6766, -1.7521, -0.3014,
                                                  1.6721, -0.1868, -0.1491, float(np.log(0.3326))], iters=2)
     if which in ("all", "gauss"):
-        nuts("gauss", 1 << 14, 0.1, 20200, 1.0, [0.0] * 100, iters=2)
+        nuts("gauss", 1 << 18, 0.1, 20200, 1.0, [0.0] * 100, iters=3)
     if which in ("all", "smc"):
         m = make_model("arma")
         t0 = time.time()
