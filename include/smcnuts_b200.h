@@ -154,6 +154,8 @@ int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, v
 
 /* ---- measurement helper: dependent-chain-free DFMA loop; out_flops[0] = FLOPs executed (device double) */
 int smcb_probe_fp64(int blocks, int threads, int iters, double* out_sink, void* stream);
+/* same for the FP64 tensor-core path: 8 independent mma.m8n8k4 chains per warp, 8*512 FLOPs per warp per iteration */
+int smcb_probe_dmma(int blocks, int threads, int iters, double* out_sink, void* stream);
 
 #ifdef __cplusplus
 }

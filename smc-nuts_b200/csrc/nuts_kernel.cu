@@ -94,7 +94,8 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
         if (lane.phase != kIdle) lane.pre_eval(a);
         double A, B, g[M::NLOC];
         model.eval(lane.xa, a.phi, A, B, g);
-        if (lane.phase != kIdle) lane.post_eval(a, A, B, g);
+        lane.take_grad(g);
+        if (lane.phase != kIdle) lane.post_eval(a, A, B);
     }
 }
 
@@ -211,11 +212,14 @@ int smcb_model_create(int kind, const double* host_data, long long n, int dim, v
         const int NO = (int)((n - 1) / 13);
         d.dim = 13; d.T = NO; d.q = host_data[0];
         const double *y = host_data + 1, *lg = y + NO, *X = lg + NO;
-        packed.assign((size_t)NO * PrmModel::ROW, 0.0);
+        packed.assign((size_t)PrmModel::HDR + (size_t)NO * PrmModel::ROW, 0.0);
         for (int i = 0; i < NO; ++i) {
-            for (int j = 0; j < 11; ++j) packed[(size_t)i * PrmModel::ROW + j] = X[i * 11 + j];
-            packed[(size_t)i * PrmModel::ROW + 12] = y[i];
-            packed[(size_t)i * PrmModel::ROW + 13] = lg[i];
+            double* row = packed.data() + PrmModel::HDR + (size_t)i * PrmModel::ROW;
+            for (int j = 0; j < 11; ++j) row[j] = X[i * 11 + j];
+            row[11] = y[i];
+            packed[0] += y[i];
+            for (int j = 0; j < 11; ++j) packed[1 + j] += y[i] * X[i * 11 + j];
+            packed[12] += lg[i];
         }
     } else if (kind == SMCB_MODEL_GAUSS) {
         SMCB_REQUIRE(dim >= 1 && dim <= GaussModel::DMAX && (long long)dim * dim == n, "gauss: need P[D*D], D <= 128");

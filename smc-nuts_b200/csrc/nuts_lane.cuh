@@ -125,9 +125,27 @@ struct Lane {
         phase = kInit;
     }
 
+    SMCB_HD void prefetch_lines(const double* p, int ndoubles) const {
+#if defined(__CUDA_ARCH__)
+        for (int b = 0; b < ndoubles * 8; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p + b));
+#else
+        (void)p; (void)ndoubles;
+#endif
+    }
+
     // first half of the leapfrog (nuts.py:169-170); nothing to do before the initial evaluation
     SMCB_HD void pre_eval(const NutsArgs& a) {
         if (phase != kLeaf) return;
+        // the tree bookkeeping that follows this leaf reads U-turn checkpoints (and the other edge when the leaf
+        // closes a doubling): start those loads now so they land while the model evaluation runs
+        {
+            const uint32_t i0 = leaf;  // 0-based index of the leaf about to be built
+            if (i0 & 1u) {
+                const int tz = ctz32(i0 + 1u);
+                for (int l = 0; l < tz; ++l) prefetch_lines(ckpt(popc32(i0 - (2u << l) + 1u)), 2 * nl);
+            }
+            if (i0 + 1u == (1u << depth)) prefetch_lines(other(), 2 * nl);
+        }
         const double half = dir * a.eps / 2, full = dir * a.eps;
 #pragma unroll
         SMCB_LOCAL(i) {
@@ -180,14 +198,23 @@ struct Lane {
         As = A; Bs = B;
     }
 
-    // Consume the model evaluation at xa.  Returns true when the transition is complete.
-    SMCB_HD bool post_eval(const NutsArgs& a, double A, double B, const double (&gn)[DM]) {
+    // Unconditional hand-over of the fresh gradient (also on idle lanes, so that `ga` is dead across the model
+    // evaluation and its registers can hold the accumulators).
+    SMCB_HD void take_grad(const double (&gn)[DM]) {
+#pragma unroll
+        SMCB_LOCAL(i) ga[i] = gn[i];
+    }
+
+    // Consume the model evaluation at xa (gradient already in `ga`).  Returns true when the transition is complete.
+    SMCB_HD bool post_eval(const NutsArgs& a, double A, double B) {
         const int d_ = D, n_ = nl;
         double lp = A + a.phi * B;
         const bool bad = !is_finite(lp);  // bridgestan.py:47-49,79-80: failure -> logp = -inf, grad = -inf
-        if (bad) lp = neg_inf();
+        if (bad) {
+            lp = neg_inf();
 #pragma unroll
-        SMCB_LOCAL(i) ga[i] = (bad && gd(i) < d_) ? neg_inf() : gn[i];
+            SMCB_LOCAL(i) if (gd(i) < d_) ga[i] = neg_inf();
+        }
 
         if (phase == kInit) {  // nuts.py:66-87
             double rr = 0.0;

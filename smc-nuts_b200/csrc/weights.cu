@@ -487,6 +487,24 @@ __global__ void probe_fp64_kernel(int iters, double* sink) {
     if (s == 12345.678) sink[0] = s;  // never true; keeps the loop alive
 }
 
+// FP64 tensor-core probe: 8 independent mma.m8n8k4 accumulator chains per warp
+__global__ void probe_dmma_kernel(int iters, double* sink) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-9 + i;
+    const double a = 1.0000001, b = 0.9999999;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[2 * j]), "+d"(c[2 * j + 1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 12345.678) sink[0] = s;
+}
+
 static int reset_counter(void* ws, cudaStream_t st) {
     SMCB_CUDA(cudaMemsetAsync((char*)ws + (size_t)kRedMaxBlocks * kRedMaxVals * 8, 0, 8, st));
     return 0;
@@ -685,6 +703,12 @@ int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, v
     if (reset_counter(workspace, st)) return -1;
     sum_int32_kernel<<<stride_grid(N, kRedThreads * 4, 4), kRedThreads, 0, st>>>(v, N, out, (double*)workspace);
     return check_launch("sum_int32_kernel");
+}
+
+int smcb_probe_dmma(int blocks, int threads, int iters, double* out_sink, void* stream) {
+    SMCB_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && threads % 32 == 0 && iters > 0 && out_sink, "bad argument");
+    probe_dmma_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, out_sink);
+    return check_launch("probe_dmma_kernel");
 }
 
 int smcb_probe_fp64(int blocks, int threads, int iters, double* out_sink, void* stream) {

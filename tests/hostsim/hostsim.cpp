@@ -12,12 +12,11 @@ using namespace smcb;
 
 template <class M>
 static void run(NutsArgs a, int lanes) {
-    const int D = M::dim_of(a.model);
-    const int rec = nuts_ws_doubles(D, a.max_depth);
+    const int rec = nuts_ws_doubles(M(a.model, a.model.data).nloc(), a.max_depth);
     std::vector<double> ws((size_t)lanes * rec, 0.0);
     std::vector<Lane<M>> L(lanes);
     M model(a.model, a.model.data);
-    for (auto& l : L) l.phase = kIdle;
+    for (auto& l : L) l.idle_init(model, 0);
     long long head = 0;
     for (;;) {
         bool any = false;
@@ -27,9 +26,10 @@ static void run(NutsArgs a, int lanes) {
             if (l.phase == kIdle) continue;
             any = true;
             l.pre_eval(a);
-            double A, B, g[M::DMAX];
+            double A, B, g[M::NLOC];
             model.eval(l.xa, a.phi, A, B, g);
-            l.post_eval(a, A, B, g);
+            l.take_grad(g);
+            l.post_eval(a, A, B);
         }
         if (!any) break;
     }

@@ -30,11 +30,15 @@ def pack_model(name, np_target):
         return 0, np.ascontiguousarray(np_target.y), 4, len(np_target.y), 0.0
     if name == "PRMwCD":
         t = np_target
-        rows = np.zeros((t.Nobs, 14))
+        rows = np.zeros((t.Nobs, 12))
         rows[:, :11] = t.X
-        rows[:, 12] = t.y
-        rows[:, 13] = t.lgam
-        return 1, np.ascontiguousarray(rows.ravel()), 13, t.Nobs, t.q
+        rows[:, 11] = t.y
+        hdr = np.zeros(16)
+        for i in range(t.Nobs):          # same accumulation order as smcb_model_create
+            hdr[0] += t.y[i]
+            hdr[1:12] += t.y[i] * t.X[i]
+            hdr[12] += t.lgam[i]
+        return 1, np.ascontiguousarray(np.concatenate([hdr, rows.ravel()])), 13, t.Nobs, t.q
     return 2, np.ascontiguousarray(np_target.P.ravel()), np_target.dim, 0, 0.0
 
 

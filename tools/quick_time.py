@@ -33,6 +33,10 @@ def probe():
     t, _ = ev_time(lambda: _cabi.call("smcb_probe_fp64", blocks, threads, iters, dev.ptr(sink), dev.stream_ptr()))
     fl = blocks * threads * iters * 8 * 2
     print(f"FP64 DFMA probe: {fl / t / 1e12:.2f} TFLOP/s ({t * 1e3:.2f} ms)")
+    for warps in (1, 2, 4, 8):
+        t2, _ = ev_time(lambda: _cabi.call("smcb_probe_dmma", 148 * 4, 32 * warps, iters, dev.ptr(sink), dev.stream_ptr()))
+        fl2 = 148 * 4 * warps * iters * 8 * 512
+        print(f"FP64 DMMA probe ({warps} warps/CTA x 4 CTA/SM): {fl2 / t2 / 1e12:.2f} TFLOP/s ({t2 * 1e3:.2f} ms)")
     return fl / t
 
 
