@@ -152,6 +152,9 @@ int smcb_gaussL_logpdf(const double* r_new, const double* x_new, long long N, in
 /* out[0] (int64) = sum of an int32 array: the per-iteration leapfrog / grad-eval counter */
 int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, void* stream);
 
+/* out[i] = exp(x[i]) with the library's in-kernel exp (test hook: accuracy of the hot-loop exp, <= 1.5 ulp) */
+int smcb_fast_exp(const double* x, long long N, double* out, void* stream);
+
 /* ---- measurement helper: dependent-chain-free DFMA loop; out_flops[0] = FLOPs executed (device double) */
 int smcb_probe_fp64(int blocks, int threads, int iters, double* out_sink, void* stream);
 /* same for the FP64 tensor-core path: 8 independent mma.m8n8k4 chains per warp, 8*512 FLOPs per warp per iteration */

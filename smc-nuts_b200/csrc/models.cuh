@@ -119,7 +119,7 @@ struct PrmModel {
             }
             const double eta = e0 + e1;
             min_eta = eta < min_eta ? eta : min_eta;
-            const double lam = exp(eta);
+            const double lam = fast_exp(eta);
             slam += lam;
             gl[0] += lam;
 #pragma unroll

@@ -209,12 +209,12 @@ __device__ __forceinline__ Lse lse_empty() { return Lse{neg_inf(), 0.0, 0.0}; }
 __device__ __forceinline__ void lse_push(Lse& a, double x) {
     if (x == neg_inf()) return;  // samples.py:96 / adaptive_tempering.py:46: -inf entries are dropped
     if (x > a.m) {
-        const double f = exp(a.m - x);  // exp(-inf) = 0 on the first element
+        const double f = fast_exp(a.m - x);  // exp(-inf) = 0 on the first element
         a.s1 = a.s1 * f + 1.0;
         a.s2 = a.s2 * f * f + 1.0;
         a.m = x;
     } else {
-        const double e = exp(x - a.m);  // NaN input poisons the sums, as in scipy.logsumexp
+        const double e = fast_exp(x - a.m);  // NaN input poisons the sums, as in scipy.logsumexp
         a.s1 += e;
         a.s2 += e * e;
     }
@@ -313,7 +313,7 @@ __global__ void normalise_kernel(const double* __restrict__ logw, long long N, c
     const double z = *logZ;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
         const double x = logw[i];
-        wn[i] = (x == neg_inf()) ? 0.0 : exp(x - z);
+        wn[i] = (x == neg_inf()) ? 0.0 : fast_exp(x - z);
     }
 }
 
@@ -485,6 +485,11 @@ __global__ void probe_fp64_kernel(int iters, double* sink) {
     }
     const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 12345.678) sink[0] = s;  // never true; keeps the loop alive
+}
+
+__global__ void fast_exp_kernel(const double* __restrict__ x, long long N, double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        out[i] = fast_exp(x[i]);
 }
 
 // FP64 tensor-core probe: 8 independent mma.m8n8k4 accumulator chains per warp
@@ -703,6 +708,13 @@ int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, v
     if (reset_counter(workspace, st)) return -1;
     sum_int32_kernel<<<stride_grid(N, kRedThreads * 4, 4), kRedThreads, 0, st>>>(v, N, out, (double*)workspace);
     return check_launch("sum_int32_kernel");
+}
+
+int smcb_fast_exp(const double* x, long long N, double* out, void* stream) {
+    SMCB_REQUIRE(x && out && N >= 0, "bad argument");
+    if (N == 0) return 0;
+    fast_exp_kernel<<<stride_grid(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, N, out);
+    return check_launch("fast_exp_kernel");
 }
 
 int smcb_probe_dmma(int blocks, int threads, int iters, double* out_sink, void* stream) {

@@ -42,15 +42,33 @@ def like_input(t, ref):
     return t
 
 
-def to_host_like(t, ref):
-    """Device result -> the container type of `ref`: CUDA tensor in -> CUDA tensor out; host buffers (numpy or
-    CPU torch tensors) come back through a pinned staging buffer (one async D2H + sync)."""
+_PINNED = {}
+
+
+def pinned_buffer(tag, shape, dtype):
+    """Reusable page-locked staging buffer (cudaHostAlloc costs milliseconds; never allocate one per call)."""
+    key = (tag, tuple(shape), dtype)
+    buf = _PINNED.get(key)
+    if buf is None:
+        buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+        _PINNED[key] = buf
+    return buf
+
+
+def to_host_like(t, ref, tag="out"):
+    """Device result -> the container type of `ref`.
+
+    CUDA tensor in -> CUDA tensor out.  numpy in -> a fresh numpy array (copied out of a reusable pinned staging
+    buffer).  Pinned CPU torch tensor in -> the pinned staging buffer itself is returned (zero extra copy; it is
+    overwritten by the next call with the same tag and shape -- the fast path bench.py's e2e leg uses)."""
     if isinstance(ref, torch.Tensor) and ref.is_cuda:
         return t
-    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host = pinned_buffer(tag, t.shape, t.dtype)
     host.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return host if isinstance(ref, torch.Tensor) else host.numpy()
+    if isinstance(ref, torch.Tensor):
+        return host if ref.is_pinned() else host.clone()
+    return host.numpy().copy()
 
 
 def empty(*shape, dtype=F64):

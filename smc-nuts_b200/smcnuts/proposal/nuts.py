@@ -39,7 +39,7 @@ class NUTSProposal:
         r = dev.to_device(r_cond).reshape(-1, self.target.dim)
         out = self.transition(x, r, phi)
         self.iteration += 1
-        return dev.to_host_like(out["x_new"], x_cond), dev.to_host_like(out["r_new"], r_cond)
+        return dev.to_host_like(out["x_new"], x_cond, "x_new"), dev.to_host_like(out["r_new"], r_cond, "r_new")
 
     def transition(self, x, r, phi=1.0, iteration=None):
         """Device entry point: returns dict of device tensors (x_new, r_new, A_old, B_old, A_new, B_new,
