@@ -145,9 +145,10 @@ int smcb_gaussL_gram(const double* r_new, const double* x_new, long long N, int 
  * out_logdet[0] = log det S.  scratch: 6*D*D doubles. */
 int smcb_gaussL_factor(const double* gram, long long N_total, int D, double ridge, double* G, double* out_logdet,
                        double* scratch, void* stream);
-/* out_i = -0.5*(D log 2pi + logdet + |G (X_i - mean)|^2) */
+/* out_i = -0.5*(D log 2pi + logdet + |G (X_i - mean)|^2).  scratch (nullable): 2*D*(D+8) doubles; when given and
+ * D <= 104 the GEMM runs on the FP64 tensor cores (mma.m8n8k4). */
 int smcb_gaussL_logpdf(const double* r_new, const double* x_new, long long N, int D, const double* mean,
-                       const double* G, const double* logdet, double* out, void* stream);
+                       const double* G, const double* logdet, double* out, double* scratch, void* stream);
 
 /* out[0] (int64) = sum of an int32 array: the per-iteration leapfrog / grad-eval counter */
 int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, void* stream);

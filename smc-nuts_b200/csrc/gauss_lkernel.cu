@@ -92,6 +92,124 @@ __global__ void __launch_bounds__(256) gaussL_gram_kernel(const double* __restri
         }
 }
 
+// ------------------------------------------------------------------------------------------ FP64 tensor-core path
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Centred Gram with mma.m8n8k4 (k = particles): a CTA stages 32 centred rows x C8*8 columns in shared memory; each of
+// its 8 warps owns one 32 x 32 output block (pair of 4-tile column groups, upper triangle only) and accumulates it in
+// 16 tile accumulators over the whole row slab; one atomicAdd per output element per CTA at the end.
+constexpr int kGramRows = 32;
+__global__ void __launch_bounds__(256) gaussL_gram_dmma_kernel(const double* __restrict__ r, const double* __restrict__ x,
+                                                               long long N, int D, const double* __restrict__ mean,
+                                                               double* gram, int C8, int nblk, int npairs,
+                                                               long long rows_per_block) {
+    extern __shared__ double sm[];  // [kGramRows][ld]
+    const int D2 = 2 * D, W = C8 * 8, ld = W + 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.y * 8 + warp;
+    // decode pair -> (bi <= bj) over nblk column blocks of 32
+    int bi = 0, bj = 0;
+    {
+        int t = pair, row = 0;
+        while (row < nblk && t >= nblk - row) { t -= nblk - row; ++row; }
+        bi = row; bj = row + t;
+    }
+    const bool active = pair < npairs;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const long long row_begin = (long long)blockIdx.x * rows_per_block;
+    const long long row_end = min(N, row_begin + rows_per_block);
+    for (long long row0 = row_begin; row0 < row_end; row0 += kGramRows) {
+        for (int e = threadIdx.x; e < kGramRows * W; e += 256) {
+            const int k = e / W, c = e - k * W;
+            const long long i = row0 + k;
+            sm[k * ld + c] = (i < row_end && c < D2) ? xval(r, x, i, c, D) - mean[c] : 0.0;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int kk = 0; kk < kGramRows / 4; ++kk) {
+                const double* rowp = sm + (4 * kk + (lane & 3)) * ld + (lane >> 2);
+                double av[4], bv[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int ca = bi * 32 + 8 * t, cb = bj * 32 + 8 * t;
+                    av[t] = ca < W ? rowp[ca] : 0.0;
+                    bv[t] = cb < W ? rowp[cb] : 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], av[a], bv[b]);
+            }
+        }
+        __syncthreads();
+    }
+    if (active) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int gi = bi * 32 + 8 * a + (lane >> 2), gj = bj * 32 + 8 * b + 2 * (lane & 3) + e;
+                    if (gi < D2 && gj < D2 && gi <= gj) atomicAdd(&gram[(size_t)gi * D2 + gj], acc[a][b][e]);
+                }
+    }
+}
+
+// B-fragment packing of G' for the logpdf GEMM: frag[(nt*KK + kk)*32 + l] = G[8nt + l/4][4kk + l%4] (0 outside)
+__global__ void gaussL_pack_G_kernel(const double* __restrict__ G, int D, int NT8, int KK, double* __restrict__ frag) {
+    const int total = NT8 * KK * 32;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int l = t & 31, kk = (t >> 5) % KK, nt = (t >> 5) / KK;
+        const int n = 8 * nt + (l >> 2), k = 4 * kk + (l & 3);
+        frag[t] = (n < D && k < 2 * D) ? G[(size_t)n * 2 * D + k] : 0.0;
+    }
+}
+
+// z = G (X_i - mean) for 8 particles per warp (4 lanes per particle), |z|^2 folded in the group.
+template <int NT8>
+__global__ void __launch_bounds__(256) gaussL_logpdf_dmma_kernel(const double* __restrict__ r, const double* __restrict__ x,
+                                                                 long long N, int D, const double* __restrict__ mean,
+                                                                 const double* __restrict__ frag, int KK,
+                                                                 const double* __restrict__ logdet,
+                                                                 double* __restrict__ out) {
+    extern __shared__ double sm[];  // frag [NT8][KK][32]
+    for (int t = threadIdx.x; t < NT8 * KK * 32; t += blockDim.x) sm[t] = frag[t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sub = lane & 3, D2 = 2 * D;
+    const double c0 = D * kLog2Pi + logdet[0];
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (long long p0 = wid * 8; p0 < N; p0 += nwarps * 8) {
+        const long long i = p0 + (lane >> 2);
+        const bool ok = i < N;
+        double c[2 * NT8];
+#pragma unroll
+        for (int j = 0; j < 2 * NT8; ++j) c[j] = 0.0;
+        for (int kk = 0; kk < KK; ++kk) {
+            const int k = 4 * kk + sub;
+            const double av = (ok && k < D2) ? xval(r, x, i, k, D) - mean[k] : 0.0;
+            const double* bp = sm + (size_t)kk * 32 + lane;
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt) dmma884(c[2 * nt], c[2 * nt + 1], av, bp[(size_t)nt * KK * 32]);
+        }
+        double maha = 0.0;
+#pragma unroll
+        for (int j = 0; j < 2 * NT8; ++j) maha += c[j] * c[j];
+        maha += __shfl_xor_sync(0xffffffffu, maha, 1);
+        maha += __shfl_xor_sync(0xffffffffu, maha, 2);
+        if (ok && sub == 0) out[i] = -0.5 * (c0 + maha);
+    }
+}
+
 // In-place lower Cholesky of the n x n row-major matrix a (only the lower triangle is read).  One CTA.
 __device__ void chol_inplace(double* a, int n) {
     for (int j = 0; j < n; ++j) {
@@ -226,6 +344,21 @@ int smcb_gaussL_sums(const double* r_new, const double* x_new, long long N, int 
 int smcb_gaussL_gram(const double* r_new, const double* x_new, long long N, int D, const double* mean, double* gram,
                      void* stream) {
     SMCB_REQUIRE(r_new && x_new && mean && gram && N >= 1 && D >= 1 && D <= kGDmax, "bad argument (D <= 128)");
+    if (D <= 104) {   // FP64 tensor-core path
+        const int C8 = (2 * D + 7) / 8, W = C8 * 8, nblk = (W + 31) / 32, npairs = nblk * (nblk + 1) / 2;
+        const int gy = (npairs + 7) / 8;
+        long long slabs = (long long)device_sm_count() * 2 / gy;
+        if (slabs < 1) slabs = 1;
+        long long rpb = (N + slabs - 1) / slabs;
+        rpb = ((rpb + kGramRows - 1) / kGramRows) * kGramRows;
+        slabs = (N + rpb - 1) / rpb;
+        const size_t smem = sizeof(double) * (size_t)kGramRows * (W + 4);
+        if (smem > 48 * 1024)
+            SMCB_CUDA(cudaFuncSetAttribute(gaussL_gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)slabs, (unsigned)gy);
+        gaussL_gram_dmma_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(r_new, x_new, N, D, mean, gram, C8, nblk, npairs, rpb);
+        return check_launch("gaussL_gram_dmma_kernel");
+    }
     const int tiles = (2 * D + kTB - 1) / kTB;
     const int active_tiles = tiles * (tiles + 1) / 2;
     long long slabs = (long long)device_sm_count() * 4 / active_tiles;
@@ -246,9 +379,34 @@ int smcb_gaussL_factor(const double* gram, long long N_total, int D, double ridg
 }
 
 int smcb_gaussL_logpdf(const double* r_new, const double* x_new, long long N, int D, const double* mean,
-                       const double* G, const double* logdet, double* out, void* stream) {
+                       const double* G, const double* logdet, double* out, double* scratch, void* stream) {
     SMCB_REQUIRE(r_new && x_new && mean && G && logdet && out && N >= 0 && D >= 1 && D <= kGDmax, "bad argument (D <= 128)");
     if (N == 0) return 0;
+    if (D <= 104 && scratch) {   // FP64 tensor-core path; scratch holds the packed fragments of G'
+        cudaStream_t st = (cudaStream_t)stream;
+        const int NT8 = D <= 8 ? 1 : D <= 16 ? 2 : D <= 32 ? 4 : D <= 64 ? 8 : 13;
+        const int KK = (2 * D + 3) / 4;
+        const int nfrag = NT8 * KK * 32;
+        gaussL_pack_G_kernel<<<(nfrag + 255) / 256, 256, 0, st>>>(G, D, NT8, KK, scratch);
+        if (check_launch("gaussL_pack_G_kernel")) return -1;
+        const size_t smem = sizeof(double) * (size_t)nfrag;
+        const int grid = stride_grid((N + 7) / 8 * 32, 256, smem > 100 * 1024 ? 1 : 2);
+#define LAUNCH_LP(K)                                                                                                          \
+    do {                                                                                                                      \
+        if (smem > 48 * 1024)                                                                                                 \
+            SMCB_CUDA(cudaFuncSetAttribute(gaussL_logpdf_dmma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gaussL_logpdf_dmma_kernel<K><<<grid, 256, smem, st>>>(r_new, x_new, N, D, mean, scratch, KK, logdet, out);              \
+    } while (0)
+        switch (NT8) {
+            case 1: LAUNCH_LP(1); break;
+            case 2: LAUNCH_LP(2); break;
+            case 4: LAUNCH_LP(4); break;
+            case 8: LAUNCH_LP(8); break;
+            default: LAUNCH_LP(13); break;
+        }
+#undef LAUNCH_LP
+        return check_launch("gaussL_logpdf_dmma_kernel");
+    }
     const size_t smem = sizeof(double) * (size_t)D * 2 * D;
     const int in_smem = smem <= 200 * 1024;
     if (in_smem && smem > 48 * 1024)

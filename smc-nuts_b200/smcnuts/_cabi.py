@@ -50,7 +50,7 @@ _SIGS = {
     "smcb_gaussL_sums": [_vp, _vp, _ll, _i, _vp, _vp],
     "smcb_gaussL_gram": [_vp, _vp, _ll, _i, _vp, _vp, _vp],
     "smcb_gaussL_factor": [_vp, _ll, _i, _d, _vp, _vp, _vp, _vp],
-    "smcb_gaussL_logpdf": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp],
+    "smcb_gaussL_logpdf": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "smcb_sum_int32": [_vp, _ll, _vp, _vp, _vp],
     "smcb_fast_exp": [_vp, _ll, _vp, _vp],
     "smcb_probe_fp64": [_i, _i, _i, _vp, _vp],

@@ -35,6 +35,7 @@ class GaussianApproxLKernel:
         _cabi.call("smcb_gaussL_factor", dev.ptr(gram), n_total, D, self.RIDGE, dev.ptr(G), dev.ptr(logdet),
                    dev.ptr(scratch), st)
         out = dev.empty(n)
+        frag = dev.empty(2 * D * (D + 8) + 4096)
         _cabi.call("smcb_gaussL_logpdf", dev.ptr(r), dev.ptr(x), n, D, dev.ptr(mean), dev.ptr(G), dev.ptr(logdet),
-                   dev.ptr(out), st)
+                   dev.ptr(out), dev.ptr(frag), st)
         return dev.like_input(out, x_new)
