@@ -105,25 +105,51 @@ struct PrmModel {
         double gl[M];   // sum_i lambda_i * (1, X_i.)
 #pragma unroll
         for (int j = 0; j < M; ++j) gl[j] = 0.0;
-#pragma unroll 2
-        for (int i = 0; i < NO; ++i) {
-            const double* row = rows + i * ROW;
-            double xr[C];
+        // observations two at a time with their dependency chains interleaved (eta: 4 chains; exp: 2 x 2 chains)
+        int i = 0;
+#pragma unroll 1
+        for (; i + 1 < NO; i += 2) {
+            const double* rowa = rows + i * ROW;
+            const double* rowb = rowa + ROW;
+            double xa_[C], xb_[C];
 #pragma unroll
-            for (int j = 0; j < C; ++j) xr[j] = row[j];
-            double e0 = x[0], e1 = 0.0;   // two interleaved partial sums of eta_i = Beta_1 + sum_j Beta_{j+1} X_ij
+            for (int j = 0; j < C; ++j) { xa_[j] = rowa[j]; xb_[j] = rowb[j]; }
+            double a0 = x[0], a1 = 0.0, b0 = x[0], b1 = 0.0;
 #pragma unroll
             for (int j = 0; j < C; j += 2) {
-                e0 += x[j + 1] * xr[j];
-                if (j + 1 < C) e1 += x[j + 2] * xr[j + 1];
+                a0 += x[j + 1] * xa_[j];
+                b0 += x[j + 1] * xb_[j];
+                if (j + 1 < C) {
+                    a1 += x[j + 2] * xa_[j + 1];
+                    b1 += x[j + 2] * xb_[j + 1];
+                }
+            }
+            const double etaa = a0 + a1, etab = b0 + b1;
+            min_eta = etaa < min_eta ? etaa : min_eta;
+            min_eta = etab < min_eta ? etab : min_eta;
+            double lama, lamb;
+            fast_exp_pair(etaa, etab, lama, lamb);
+            slam += lama; gl[0] += lama;
+#pragma unroll
+            for (int j = 0; j < C; ++j) gl[j + 1] += lama * xa_[j];
+            slam += lamb; gl[0] += lamb;
+#pragma unroll
+            for (int j = 0; j < C; ++j) gl[j + 1] += lamb * xb_[j];
+        }
+        for (; i < NO; ++i) {   // odd tail
+            const double* row = rows + i * ROW;
+            double e0 = x[0], e1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < C; j += 2) {
+                e0 += x[j + 1] * row[j];
+                if (j + 1 < C) e1 += x[j + 2] * row[j + 1];
             }
             const double eta = e0 + e1;
             min_eta = eta < min_eta ? eta : min_eta;
             const double lam = fast_exp(eta);
-            slam += lam;
-            gl[0] += lam;
+            slam += lam; gl[0] += lam;
 #pragma unroll
-            for (int j = 0; j < C; ++j) gl[j + 1] += lam * xr[j];
+            for (int j = 0; j < C; ++j) gl[j + 1] += lam * row[j];
         }
         // sum_i y_i eta_i = Beta_1 sum y + sum_j Beta_{j+1} (X'y)_j
         double ydot = x[0] * hdr[0];
