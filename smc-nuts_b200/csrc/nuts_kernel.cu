@@ -38,10 +38,25 @@ static int blocks_per_sm_cap() {
     return v > 0 ? v : 1 << 20;
 }
 
-template <class M> struct LaunchCfg { static constexpr int NT = 128, MIN_BLOCKS = 2; };   // GaussModelG<NT8>
-template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
-template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2; };
-template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1; };
+// NT threads per CTA, MIN_BLOCKS resident CTAs/SM (register budget), HC / HK = U-turn checkpoint / candidate slots of
+// the per-lane tree workspace that live in shared memory.  MEASURED (round 1, profiles/README.md): keeping the low
+// slots in shared memory (arma HC=3, HK=1: 44 KB/CTA) made the kernel 37 % SLOWER -- the carve-out leaves almost no L1,
+// and the L1 was already serving the workspace and particle-row traffic (long_scoreboard 1.2 -> 5.7 per issue).  The
+// hot path is therefore disabled; the global per-lane records stay L1/L2 resident.
+template <class M> struct LaunchCfg { static constexpr int NT = 128, MIN_BLOCKS = 2, HC = 0, HK = 0; static constexpr bool HOT = false; };
+template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4, HC = 3, HK = 1; static constexpr bool HOT = false; };
+template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2, HC = 2, HK = 0; static constexpr bool HOT = false; };
+template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1, HC = 0, HK = 0; static constexpr bool HOT = false; };
+
+template <class M>
+static size_t nuts_smem_bytes(const ModelDesc& d) {
+    size_t doubles = (size_t)((M::staged_doubles(d) + 1) & ~1);
+    if (LaunchCfg<M>::HOT) {
+        M probe(d, nullptr);
+        doubles += (size_t)LaunchCfg<M>::NT * Lane<M>::hot_doubles(probe.nloc(), LaunchCfg<M>::HC, LaunchCfg<M>::HK);
+    }
+    return doubles * sizeof(double);
+}
 
 template <class M> struct StageOffset { static int of(const ModelDesc&) { return 0; } };
 template <int NT8> struct StageOffset<GaussModelG<NT8>> { static int of(const ModelDesc& d) { return d.dim * d.dim; } };
@@ -68,7 +83,11 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
     M model(a.model, stage_model<M>(a.model, smem, staged, stage_offset));
     const unsigned lane_id = threadIdx.x & 31u;
     Lane<M> lane;
-    lane.idle_init(model, (int)(lane_id % G));
+    if constexpr (LaunchCfg<M>::HOT)
+        lane.idle_init(model, (int)(lane_id % G), smem + ((staged + 1) & ~1) + threadIdx.x, (int)blockDim.x, LaunchCfg<M>::HC,
+                       LaunchCfg<M>::HK);
+    else
+        lane.idle_init(model, (int)(lane_id % G));
     double* ws = a.ws + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * rec_doubles;
     constexpr unsigned kLeaders = G == 1 ? 0xffffffffu : 0x11111111u;   // first lane of every particle group
     const unsigned group_first = lane_id & ~(unsigned)(G - 1);
@@ -150,7 +169,7 @@ static long long nuts_blocks(const Model* mdl, long long N, size_t smem, int* oc
 
 template <class M>
 static long long nuts_ws_bytes(const Model* mdl, long long N, int max_depth) {
-    const size_t smem = sizeof(double) * (size_t)M::staged_doubles(mdl->desc);
+    const size_t smem = nuts_smem_bytes<M>(mdl->desc);
     const long long blocks = nuts_blocks<M>(mdl, N, smem, nullptr);
     if (blocks < 0) return -1;
     M probe(mdl->desc, nullptr);
@@ -161,7 +180,7 @@ template <class M>
 static int launch_nuts(const Model* mdl, NutsArgs a, long long ws_bytes, cudaStream_t st) {
     const int NT = LaunchCfg<M>::NT;
     const int staged = M::staged_doubles(mdl->desc);
-    const size_t smem = sizeof(double) * (size_t)staged;
+    const size_t smem = nuts_smem_bytes<M>(mdl->desc);
     const long long blocks = nuts_blocks<M>(mdl, a.N, smem, nullptr);
     if (blocks < 0) return fail("smcb_nuts_transition", "kernel does not fit on an SM");
     M probe(mdl->desc, nullptr);

@@ -71,7 +71,9 @@ struct Lane {
     double xa[DM], ra[DM], ga[DM];  // active edge (this lane's coordinates)
     double logu, A0, B0, As, Bs, ke0;
     long long pid;
-    double* ws;
+    double* ws;    // cold per-lane record in global memory
+    double* hot;   // hot per-lane record in shared memory, element e at hot[e * hs]  (nullptr: none)
+    int hs, hc, hk;  // shared-memory stride; number of U-turn checkpoint / candidate slots that live in shared memory
     int phase, dir, depth, D, L, nl, sub;
     uint32_t leaf, n_tot, n_leapfrog, free_mask;
     uint64_t pend_n, pend_ref;
@@ -91,10 +93,20 @@ struct Lane {
         return v;
     }
 
-    // ---- workspace views (per lane)
-    SMCB_HD double* other() const { return ws; }                                      // x, r, g of the inactive edge
-    SMCB_HD double* ckpt(int slot) const { return ws + 3 * nl + 2 * nl * slot; }       // x, r
-    SMCB_HD double* cand(int slot) const { return ws + 3 * nl + 2 * nl * L + (2 * nl + 2) * slot; }  // x, r, A, B
+    // ---- workspace views (per lane).  A view is (pointer, element stride): the low, hot slots live in shared memory
+    //      interleaved across the CTA's lanes (stride hs, conflict-free), everything else in the global record.
+    struct View { double* p; int st; SMCB_HD double& operator[](int i) const { return p[(size_t)i * st]; } };
+    // hot layout (elements): other x, other r (2 nl) | hc checkpoints (2 nl each) | hk candidates (2 nl + 2 each)
+    SMCB_HD View other_xr() const { return hot ? View{hot, hs} : View{ws, 1}; }          // x at [i], r at [nl + i]
+    SMCB_HD double* other_g() const { return ws + 2 * nl; }
+    SMCB_HD View ckpt(int slot) const {                                                    // x at [i], r at [nl + i]
+        return slot < hc ? View{hot + (size_t)(2 * nl + 2 * nl * slot) * hs, hs} : View{ws + 3 * nl + 2 * nl * slot, 1};
+    }
+    SMCB_HD View cand(int slot) const {                                                    // x, r, A, B
+        return slot < hk ? View{hot + (size_t)(2 * nl + 2 * nl * hc + (2 * nl + 2) * slot) * hs, hs}
+                         : View{ws + 3 * nl + 2 * nl * L + (2 * nl + 2) * slot, 1};
+    }
+    SMCB_HD static int hot_doubles(int nl_, int hc_, int hk_) { return 2 * nl_ + 2 * nl_ * hc_ + (2 * nl_ + 2) * hk_; }
 
     // ---- packed per-level pending counts: level l occupies bits [l(l+1)/2, +l+1)
     SMCB_HD uint32_t get_n(int l) const { return (uint32_t)(pend_n >> (l * (l + 1) / 2)) & ((2u << l) - 1u); }
@@ -106,8 +118,9 @@ struct Lane {
     SMCB_HD int get_ref(int l) const { return (int)((pend_ref >> (4 * l)) & 15u); }
     SMCB_HD void set_ref(int l, int s) { pend_ref = (pend_ref & ~((uint64_t)15 << (4 * l))) | ((uint64_t)s << (4 * l)); }
 
-    SMCB_HD void idle_init(const M& m, int sub_) {
+    SMCB_HD void idle_init(const M& m, int sub_, double* hot_ = nullptr, int hs_ = 0, int hc_ = 0, int hk_ = 0) {
         phase = kIdle; sub = sub_; D = m.dim(); nl = m.nloc(); pid = -1;
+        hot = hot_; hs = hs_; hc = hot_ ? hc_ : 0; hk = hot_ ? hk_ : 0;
         SMCB_LOCAL(i) { xa[i] = 0.0; ra[i] = 0.0; ga[i] = 0.0; }
     }
 
@@ -142,9 +155,12 @@ struct Lane {
             const uint32_t i0 = leaf;  // 0-based index of the leaf about to be built
             if (i0 & 1u) {
                 const int tz = ctz32(i0 + 1u);
-                for (int l = 0; l < tz; ++l) prefetch_lines(ckpt(popc32(i0 - (2u << l) + 1u)), 2 * nl);
+                for (int l = 0; l < tz; ++l) {
+                    const int slot = popc32(i0 - (2u << l) + 1u);
+                    if (slot >= hc) prefetch_lines(ckpt(slot).p, 2 * nl);
+                }
             }
-            if (i0 + 1u == (1u << depth)) prefetch_lines(other(), 2 * nl);
+            if (!hot && i0 + 1u == (1u << depth)) prefetch_lines(ws, 2 * nl);
         }
         const double half = dir * a.eps / 2, full = dir * a.eps;
 #pragma unroll
@@ -157,14 +173,15 @@ struct Lane {
     SMCB_HD void start_doubling(bool first) {
         const int nd = (rng.next() < 0.5) ? 1 : -1;  // nuts.py:91
         if (!first && nd != dir) {                   // bring the other edge into registers
-            double* o = other();
+            const View o = other_xr();
+            double* og = other_g();
             const int n_ = nl;
 #pragma unroll
             SMCB_LOCAL(i) {
                 double t;
                 t = o[i]; o[i] = xa[i]; xa[i] = t;
                 t = o[n_ + i]; o[n_ + i] = ra[i]; ra[i] = t;
-                t = o[2 * n_ + i]; o[2 * n_ + i] = ga[i]; ga[i] = t;
+                t = og[i]; og[i] = ga[i]; ga[i] = t;
             }
         }
         dir = nd;
@@ -174,12 +191,13 @@ struct Lane {
 
     // U-turn test between a stored edge (xc, rc) and the active edge (nuts.py:152-160); the edge order
     // (minus, plus) is restored through `dir`.
-    SMCB_HD bool uturn(const double* xc, const double* rc) const {
+    SMCB_HD bool uturn(const View& c) const {      // c: x at [i], r at [nl + i]
         double s1 = 0.0, s2 = 0.0;
+        const int n_ = nl;
 #pragma unroll
         SMCB_LOCAL(i) {
-            const double dx = xa[i] - xc[i];
-            s1 += dx * rc[i];
+            const double dx = xa[i] - c[i];
+            s1 += dx * c[n_ + i];
             s2 += dx * ra[i];
         }
         s1 = gsum(s1); s2 = gsum(s2);
@@ -225,9 +243,10 @@ struct Lane {
             const double H0 = lp - ke0;
             logu = H0 - (-log1p(-rng.next()));
             write_sample_from_active(a, A, B);
-            double* o = other();
+            const View o = other_xr();
+            double* og = other_g();
 #pragma unroll
-            SMCB_LOCAL(i) { o[i] = xa[i]; o[n_ + i] = ra[i]; o[2 * n_ + i] = ga[i]; }
+            SMCB_LOCAL(i) { o[i] = xa[i]; o[n_ + i] = ra[i]; og[i] = ga[i]; }
             n_tot = 1; depth = 0;
             start_doubling(true);
             phase = kLeaf;
@@ -253,7 +272,7 @@ struct Lane {
         if (nleaves > 1u) {
             const uint32_t i0 = leaf - 1u;
             if ((i0 & 1u) == 0u) {
-                double* c = ckpt(popc32(i0));
+                const View c = ckpt(popc32(i0));
 #pragma unroll
                 SMCB_LOCAL(i) { c[i] = xa[i]; c[n_ + i] = ra[i]; }
             } else {
@@ -271,8 +290,7 @@ struct Lane {
                         run_ref = ref1;
                     }
                     run_n = tot;
-                    const double* c = ckpt(popc32(i0 - (2u << l) + 1u));
-                    if (uturn(c, c + n_)) { ++depth; return finish(a); }
+                    if (uturn(ckpt(popc32(i0 - (2u << l) + 1u)))) { ++depth; return finish(a); }
                 }
             }
         }
@@ -282,7 +300,7 @@ struct Lane {
                 if (run_ref < 0) {
                     write_sample_from_active(a, A, B);
                 } else {
-                    const double* c = cand(run_ref);
+                    const View c = cand(run_ref);
 #pragma unroll
                     SMCB_LOCAL(i) {
                         if (gd(i) < d_) {
@@ -294,8 +312,7 @@ struct Lane {
                 }
             }
             n_tot += run_n;
-            const double* o = other();
-            const bool stop = uturn(o, o + n_);
+            const bool stop = uturn(other_xr());
             ++depth;
             if (stop || depth > L) return finish(a);
             start_doubling(false);
@@ -306,7 +323,7 @@ struct Lane {
         if (run_ref < 0) {
             run_ref = ctz32(free_mask);
             free_mask &= ~(1u << run_ref);
-            double* c = cand(run_ref);
+            const View c = cand(run_ref);
 #pragma unroll
             SMCB_LOCAL(i) { c[i] = xa[i]; c[n_ + i] = ra[i]; }
             c[2 * n_] = A; c[2 * n_ + 1] = B;
