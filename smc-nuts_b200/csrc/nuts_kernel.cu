@@ -43,7 +43,7 @@ static int blocks_per_sm_cap() {
 // slots in shared memory (arma HC=3, HK=1: 44 KB/CTA) made the kernel 37 % SLOWER -- the carve-out leaves almost no L1,
 // and the L1 was already serving the workspace and particle-row traffic (long_scoreboard 1.2 -> 5.7 per issue).  The
 // hot path is therefore disabled; the global per-lane records stay L1/L2 resident.
-template <class M> struct LaunchCfg { static constexpr int NT = 128, MIN_BLOCKS = 2, HC = 0, HK = 0; static constexpr bool HOT = false; };
+template <class M> struct LaunchCfg { static constexpr int NT = 256, MIN_BLOCKS = 1, HC = 0, HK = 0; static constexpr bool HOT = false; };   // GaussModelG: one CTA/SM, one copy of the B fragments, more L1
 template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4, HC = 3, HK = 1; static constexpr bool HOT = false; };
 template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2, HC = 2, HK = 0; static constexpr bool HOT = false; };
 template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1, HC = 0, HK = 0; static constexpr bool HOT = false; };
