@@ -57,7 +57,9 @@ struct NutsArgs {
 };
 
 // doubles of workspace per LANE; nl = coordinates held by one lane (D for one-lane-per-particle models)
-SMCB_HD int nuts_ws_doubles(int nl, int L) { return 3 * nl + 2 * nl * L + (2 * nl + 2) * (L + 1); }
+// record: other edge (3 nl) | slot 0: checkpoint (2 nl), candidate (2 nl + 2) | slot 1: ... -- checkpoint s and
+// candidate s are neighbours so that the hot low slots of a lane share cache lines (the L1 serves this traffic)
+SMCB_HD int nuts_ws_doubles(int nl, int L) { return ((3 * nl + (4 * nl + 2) * (L + 1)) + 15) & ~15; }
 
 enum LanePhase : int { kIdle = 0, kInit = 1, kLeaf = 2 };
 
@@ -100,11 +102,11 @@ struct Lane {
     SMCB_HD View other_xr() const { return hot ? View{hot, hs} : View{ws, 1}; }          // x at [i], r at [nl + i]
     SMCB_HD double* other_g() const { return ws + 2 * nl; }
     SMCB_HD View ckpt(int slot) const {                                                    // x at [i], r at [nl + i]
-        return slot < hc ? View{hot + (size_t)(2 * nl + 2 * nl * slot) * hs, hs} : View{ws + 3 * nl + 2 * nl * slot, 1};
+        return slot < hc ? View{hot + (size_t)(2 * nl + 2 * nl * slot) * hs, hs} : View{ws + 3 * nl + (4 * nl + 2) * slot, 1};
     }
     SMCB_HD View cand(int slot) const {                                                    // x, r, A, B
         return slot < hk ? View{hot + (size_t)(2 * nl + 2 * nl * hc + (2 * nl + 2) * slot) * hs, hs}
-                         : View{ws + 3 * nl + 2 * nl * L + (2 * nl + 2) * slot, 1};
+                         : View{ws + 3 * nl + (4 * nl + 2) * slot + 2 * nl, 1};
     }
     SMCB_HD static int hot_doubles(int nl_, int hc_, int hk_) { return 2 * nl_ + 2 * nl_ * hc_ + (2 * nl_ + 2) * hk_; }
 
