@@ -122,8 +122,10 @@ int smcb_ancestors_systematic(const double* cdf, long long N, double u0, long lo
 /* systematic ancestors + gather fused: out[j, :] = x[a_j, :], a_j = ancestor of position (j0 + j + u0)/M_total;
  * idx (nullable for D in {2,4,8,16,32,64}) receives a_j.  Replaces samples.py:139-140 in one pass. */
 long long smcb_resample_workspace_bytes(long long M, int D);
-int smcb_resample_systematic(const double* cdf, long long N, double u0, long long j0, long long M_total, long long M,
-                             const double* x, int D, double* out, int64_t* idx, void* workspace, void* stream);
+/* u0_dev (nullable, device): when given, u0 is read from device memory instead (no host round trip) */
+int smcb_resample_systematic(const double* cdf, long long N, double u0, const double* u0_dev, long long j0,
+                             long long M_total, long long M, const double* x, int D, double* out, int64_t* idx,
+                             void* workspace, void* stream);
 /* out[j, :] = x[idx[j], :]  (samples.py:140) */
 int smcb_gather_rows(const double* x, const int64_t* idx, long long M, int D, double* out, void* stream);
 

@@ -180,9 +180,10 @@ __global__ void gather_rows_kernel(const double* __restrict__ x, const int64_t* 
 //   pass 1 (tile_bounds_kernel): one full binary search per TILE, all tiles in parallel (latency hidden by parallelism);
 //   pass 2 (resample_systematic_fused_kernel): warps take tiles in grid-stride order (balanced, address-local), every
 //   row searches only inside its tile's (L1-resident) range and copies its ancestor's row with 16-byte accesses.
-__global__ void tile_bounds_kernel(const double* __restrict__ cdf, long long N, double u0, long long j0,
-                                   long long M_total, long long M, int rows_per_tile, long long ntiles,
-                                   long long* __restrict__ bounds) {
+__global__ void tile_bounds_kernel(const double* __restrict__ cdf, long long N, double u0,
+                                   const double* __restrict__ u0_dev, long long j0, long long M_total, long long M,
+                                   int rows_per_tile, long long ntiles, long long* __restrict__ bounds) {
+    if (u0_dev) u0 = *u0_dev;
     const double den = (double)M_total;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t <= ntiles; t += (long long)gridDim.x * blockDim.x) {
         const long long j = min(M - 1, t * rows_per_tile);   // first row of tile t (last row overall for t == ntiles)
@@ -192,36 +193,60 @@ __global__ void tile_bounds_kernel(const double* __restrict__ cdf, long long N, 
 
 template <int LPR>
 __global__ void __launch_bounds__(256) resample_systematic_fused_kernel(const double* __restrict__ cdf, long long N,
-                                                                        double u0, long long j0, long long M_total,
+                                                                        double u0, const double* __restrict__ u0_dev,
+                                                                        long long j0, long long M_total,
                                                                         long long M, const double* __restrict__ x,
                                                                         double* __restrict__ out,
                                                                         int64_t* __restrict__ idx,
                                                                         const long long* __restrict__ bounds) {
-    constexpr int D = 2 * LPR, GROUPS = 32 / LPR, R = 8, ROWS = GROUPS * R;   // rows per warp tile
+    constexpr int D = 2 * LPR, GROUPS = 32 / LPR, ROWS = 32;   // 32 rows per warp tile: lane l owns the search of row l
     const int lane = threadIdx.x & 31, sub = lane % LPR, g = lane / LPR;
+    if (u0_dev) u0 = *u0_dev;
     const double den = (double)M_total;
     const long long ntiles = (M + ROWS - 1) / ROWS;
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     for (long long tile = wid; tile < ntiles; tile += nwarps) {
-        const long long jlo = tile * ROWS, jhi = min(M, jlo + ROWS) - 1;
-        const long long blo = bounds[tile], bhi = bounds[tile + 1];
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const long long j = jlo + g + (long long)k * GROUPS;
-            if (j <= jhi) {
-                long long lo = blo, hi = bhi;   // the ancestor lies in [blo, bhi]
-                if (lo < hi) {
-                    const double pos = ((double)(j0 + j) + u0) / den;
-                    while (lo < hi) {
-                        const long long mid = (lo + hi) >> 1;
-                        if (pos < cdf[mid]) hi = mid;
-                        else lo = mid + 1;
-                    }
+        const long long jlo = tile * ROWS;
+        const long long blo = bounds[tile], bhi = bounds[tile + 1];   // every ancestor of the tile lies in [blo, bhi]
+        const long long jmine = jlo + lane;
+        const double pos = ((double)(j0 + jmine) + u0) / den;
+        long long anc = blo;
+        const long long range = bhi - blo;   // entries blo .. bhi-1 may be <= pos
+        if (range <= 2048) {
+            // warp-cooperative rank: ancestor(row) = blo + #{i in [blo, bhi) : cdf[i] <= pos(row)}.  The cdf chunk is
+            // loaded once, coalesced; ranks come from ballots -- no dependent chain of loads per row.
+            int cnt = 0;
+            for (long long c0 = 0; c0 < range; c0 += 32) {
+                const long long i = blo + c0 + lane;
+                const double cv = (i < bhi) ? cdf[i] : 1e300;
+#pragma unroll 8
+                for (int rrow = 0; rrow < 32; ++rrow) {
+                    const double pr = __shfl_sync(0xffffffffu, pos, rrow);
+                    const unsigned b = __ballot_sync(0xffffffffu, !(pr < cv));
+                    if (lane == rrow) cnt += __popc(b);
                 }
-                const double2 v = *reinterpret_cast<const double2*>(x + lo * D + 2 * sub);
+            }
+            anc = blo + cnt;
+        } else if (jmine < M) {
+            long long lo = blo, hi = bhi;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if (pos < cdf[mid]) hi = mid;
+                else lo = mid + 1;
+            }
+            anc = lo;
+        }
+        if (anc > N - 1) anc = N - 1;
+        if (idx && jmine < M) idx[jmine] = anc;
+#pragma unroll
+        for (int k = 0; k < 32 / GROUPS; ++k) {
+            const int rrow = g + k * GROUPS;
+            const long long a = __shfl_sync(0xffffffffu, anc, rrow);
+            const long long j = jlo + rrow;
+            if (j < M) {
+                const double2 v = *reinterpret_cast<const double2*>(x + a * D + 2 * sub);
                 *reinterpret_cast<double2*>(out + j * D + 2 * sub) = v;
-                if (idx && sub == 0) idx[j] = lo;
             }
         }
     }
@@ -272,13 +297,13 @@ int smcb_ancestors_systematic(const double* cdf, long long N, double u0, long lo
 }
 
 long long smcb_resample_workspace_bytes(long long M, int D) {
-    const int lpr = D >= 2 ? D / 2 : 1;
-    const int rows = (32 / (lpr > 32 ? 32 : lpr)) * 8;
-    return ((M + rows - 1) / rows + 2) * 8;
+    (void)D;
+    return ((M + 31) / 32 + 2) * 8;
 }
 
-int smcb_resample_systematic(const double* cdf, long long N, double u0, long long j0, long long M_total, long long M,
-                             const double* x, int D, double* out, int64_t* idx, void* workspace, void* stream) {
+int smcb_resample_systematic(const double* cdf, long long N, double u0, const double* u0_dev, long long j0,
+                             long long M_total, long long M, const double* x, int D, double* out, int64_t* idx,
+                             void* workspace, void* stream) {
     SMCB_REQUIRE(cdf && x && out && workspace && N >= 1 && M >= 0 && M_total >= 1 && D >= 1, "bad argument");
     SMCB_REQUIRE(x != out, "resampling cannot run in place");
     if (M == 0) return 0;
@@ -286,26 +311,30 @@ int smcb_resample_systematic(const double* cdf, long long N, double u0, long lon
     const bool aligned = (((uintptr_t)x | (uintptr_t)out) % 16) == 0;
     if (aligned && (D == 2 || D == 4 || D == 8 || D == 16 || D == 32 || D == 64)) {
         const int lpr = D / 2;
-        const int rows = (32 / lpr) * 8;
+        const int rows = 32;
         const long long ntiles = (M + rows - 1) / rows;
         long long* bounds = (long long*)workspace;
-        tile_bounds_kernel<<<stride_grid(ntiles + 1, 256, 8), 256, 0, st>>>(cdf, N, u0, j0, M_total, M, rows, ntiles, bounds);
+        tile_bounds_kernel<<<stride_grid(ntiles + 1, 256, 8), 256, 0, st>>>(cdf, N, u0, u0_dev, j0, M_total, M, rows, ntiles,
+                                                                            bounds);
         if (check_launch("tile_bounds_kernel")) return -1;
         const long long blocks = (ntiles + 7) / 8;
         const long long cap = (long long)device_sm_count() * 8;
         const int grid = (int)(blocks < cap ? blocks : cap);
+#define SMCB_RS(L) resample_systematic_fused_kernel<L><<<grid, 256, 0, st>>>(cdf, N, u0, u0_dev, j0, M_total, M, x, out, idx, bounds)
         switch (lpr) {
-            case 1: resample_systematic_fused_kernel<1><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
-            case 2: resample_systematic_fused_kernel<2><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
-            case 4: resample_systematic_fused_kernel<4><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
-            case 8: resample_systematic_fused_kernel<8><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
-            case 16: resample_systematic_fused_kernel<16><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
-            default: resample_systematic_fused_kernel<32><<<grid, 256, 0, st>>>(cdf, N, u0, j0, M_total, M, x, out, idx, bounds); break;
+            case 1: SMCB_RS(1); break;
+            case 2: SMCB_RS(2); break;
+            case 4: SMCB_RS(4); break;
+            case 8: SMCB_RS(8); break;
+            case 16: SMCB_RS(16); break;
+            default: SMCB_RS(32); break;
         }
+#undef SMCB_RS
         return check_launch("resample_systematic_fused_kernel");
     }
     // general D: separate ancestor search (needs idx scratch from the caller) and gather
     SMCB_REQUIRE(idx, "this D needs an idx buffer (unfused path)");
+    SMCB_REQUIRE(!u0_dev, "the unfused path takes u0 by value");
     ancestors_systematic_kernel<<<stride_grid(M, 256, 8), 256, 0, st>>>(cdf, N, u0, j0, M_total, M, idx);
     if (check_launch("ancestors_systematic_kernel")) return -1;
     gather_rows_kernel<1><<<stride_grid(M * D, 256, 8), 256, 0, st>>>(x, idx, M, D, out);

@@ -42,7 +42,7 @@ _SIGS = {
     "smcb_cdf": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp],
     "smcb_ancestors_multinomial": [_vp, _ll, _vp, _ll, _vp, _vp],
     "smcb_ancestors_systematic": [_vp, _ll, _d, _ll, _ll, _ll, _vp, _vp],
-    "smcb_resample_systematic": [_vp, _ll, _d, _ll, _ll, _ll, _vp, _i, _vp, _vp, _vp, _vp],
+    "smcb_resample_systematic": [_vp, _ll, _d, _vp, _ll, _ll, _ll, _vp, _i, _vp, _vp, _vp, _vp],
     "smcb_resample_workspace_bytes": [_ll, _i],
     "smcb_gather_rows": [_vp, _vp, _ll, _i, _vp, _vp],
     "smcb_weighted_moment": [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _vp, _vp],

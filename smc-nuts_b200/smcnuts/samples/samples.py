@@ -83,8 +83,10 @@ class Resampler:
                 out = dev.empty(n, D)
                 keep = idx if (self.keep_idx or D not in (2, 4, 8, 16, 32, 64)) else None
                 ws = dev.workspace("resample", _cabi.lib().smcb_resample_workspace_bytes(n, D))
-                _cabi.call("smcb_resample_systematic", dev.ptr(cdf), n, self._u0(iteration), 0, n, n, dev.ptr(x), D,
-                           dev.ptr(out), dev.ptr(keep), dev.ptr(ws), st)
+                fused = D in (2, 4, 8, 16, 32, 64)
+                u0_dev = self._u0_dev(iteration) if fused else None       # stays on the device: no host round trip
+                _cabi.call("smcb_resample_systematic", dev.ptr(cdf), n, 0.0 if fused else self._u0(iteration),
+                           dev.ptr(u0_dev), 0, n, n, dev.ptr(x), D, dev.ptr(out), dev.ptr(keep), dev.ptr(ws), st)
                 self.last_idx = keep
                 return out
             out = dev.empty(n, D)
@@ -94,6 +96,11 @@ class Resampler:
         if self.scheme == "systematic":
             return self._systematic_sharded(x, cdf, iteration)
         return self._multinomial_sharded(x, cdf, iteration)
+
+    def _u0_dev(self, iteration):
+        u = dev.empty(1)
+        _cabi.call("smcb_uniforms", self.seed, iteration, self.stream, 0, 1, 0, dev.ptr(u), dev.stream_ptr())
+        return u
 
     def _u0(self, iteration):
         u = dev.empty(1)
@@ -113,7 +120,7 @@ class Resampler:
         send = dev.empty(max(m, 1), D)
         if m:
             ws = dev.workspace("resample", _cabi.lib().smcb_resample_workspace_bytes(m, D))
-            _cabi.call("smcb_resample_systematic", dev.ptr(cdf), n, u0, lo, self.N, m, dev.ptr(x), D, dev.ptr(send),
+            _cabi.call("smcb_resample_systematic", dev.ptr(cdf), n, u0, 0, lo, self.N, m, dev.ptr(x), D, dev.ptr(send),
                        dev.ptr(idx), dev.ptr(ws), st)
         send_counts = split_counts(lo, hi, self.n_local, sh.world)
         mylo, myhi = sh.rank * self.n_local, (sh.rank + 1) * self.n_local
