@@ -145,6 +145,7 @@ def run_micro(args):
     out = dev.empty(n)
     rs = Resampler(N, 10, sh, scheme="systematic")
     rs.keep_idx = False
+    rs.use_peer_push = not args.no_peer_push
     names = ["reweight_forward", "lse+normalise", "scan(cdf)", "ancestors+gather+migrate"]
     alg_bytes = [16 * D + 32, 24, 16, 12 + 16 * D + 4]   # 288 + 24 + 16 + (12 + 260) = 600 B at D = 16
     W, K = max(args.warmup, 3), args.steps
@@ -209,6 +210,8 @@ def run_micro(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "kernels": kern, "clocks": clk,
             "migrated_rows_last_step": rs.last_migrated_rows,
+            "migration": "single GPU" if world == 1 else ("NCCL all-to-all-v" if args.no_peer_push else
+                                                          "fused: peer stores over NVLink inside the gather kernel"),
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -226,6 +229,7 @@ def main():
     ap.add_argument("--cpu-log2n", type=int, default=18, help="particles of the bounded cpu_baseline sample")
     ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "systematic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer-push", action="store_true", help="micro: migrate with NCCL all-to-all-v instead of the fused peer stores")
     args = ap.parse_args()
     if args.workload == "micro":
         return run_micro(args)

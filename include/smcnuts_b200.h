@@ -126,6 +126,17 @@ long long smcb_resample_workspace_bytes(long long M, int D);
 int smcb_resample_systematic(const double* cdf, long long N, double u0, const double* u0_dev, long long j0,
                              long long M_total, long long M, const double* x, int D, double* out, int64_t* idx,
                              void* workspace, void* stream);
+/* Sharded variant with the particle migration FUSED into the gather: this rank serves the global output slots
+ * [j0, j0+M); row j0+j is written straight into the destination rank's buffer, peer_out[(j0+j)/rows_per_rank]
+ * (device array of P peer-mapped base pointers, see smcb_peer_*), over NVLink -- no send buffer, no all-to-all-v. */
+int smcb_resample_systematic_push(const double* cdf, long long N, double u0, long long j0, long long M_total,
+                                  long long M, const double* x, int D, double* const* peer_out, long long rows_per_rank,
+                                  int64_t* idx, void* workspace, void* stream);
+/* peer-visible device buffers (CUDA IPC): alloc on the owner (64-byte handle out), open on the other ranks */
+int smcb_peer_alloc(long long bytes, void** ptr, void* handle64);
+int smcb_peer_open(const void* handle64, void** ptr);
+int smcb_peer_close(void* ptr);
+int smcb_peer_free(void* ptr);
 /* out[j, :] = x[idx[j], :]  (samples.py:140) */
 int smcb_gather_rows(const double* x, const int64_t* idx, long long M, int D, double* out, void* stream);
 

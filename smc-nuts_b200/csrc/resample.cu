@@ -6,6 +6,8 @@
 // searchsorted(cdf, uniforms, side='right') -- verified bit-identical in tests/golden/make_golden.py --
 // so given the same cdf and the same uniforms the ancestor indices here are bit-exact.
 // The scan is reduce-then-scan over 2048-element tiles with a fixed summation tree (deterministic).
+#include <cstring>
+
 #include "capi.cuh"
 
 namespace smcb {
@@ -198,7 +200,9 @@ __global__ void __launch_bounds__(256) resample_systematic_fused_kernel(const do
                                                                         long long M, const double* __restrict__ x,
                                                                         double* __restrict__ out,
                                                                         int64_t* __restrict__ idx,
-                                                                        const long long* __restrict__ bounds) {
+                                                                        const long long* __restrict__ bounds,
+                                                                        double* const* __restrict__ peer_out,
+                                                                        long long rows_per_rank) {
     constexpr int D = 2 * LPR, GROUPS = 32 / LPR, ROWS = 32;   // 32 rows per warp tile: lane l owns the search of row l
     const int lane = threadIdx.x & 31, sub = lane % LPR, g = lane / LPR;
     if (u0_dev) u0 = *u0_dev;
@@ -246,7 +250,15 @@ __global__ void __launch_bounds__(256) resample_systematic_fused_kernel(const do
             const long long j = jlo + rrow;
             if (j < M) {
                 const double2 v = *reinterpret_cast<const double2*>(x + a * D + 2 * sub);
-                *reinterpret_cast<double2*>(out + j * D + 2 * sub) = v;
+                if (peer_out) {
+                    // fused migration: the row goes straight into the destination rank's buffer over NVLink (peer
+                    // store); slot j0 + j of the global output belongs to rank (j0 + j) / rows_per_rank
+                    const long long gj = j0 + j;
+                    const long long dst = gj / rows_per_rank;
+                    *reinterpret_cast<double2*>(peer_out[dst] + (gj - dst * rows_per_rank) * D + 2 * sub) = v;
+                } else {
+                    *reinterpret_cast<double2*>(out + j * D + 2 * sub) = v;
+                }
             }
         }
     }
@@ -320,7 +332,8 @@ int smcb_resample_systematic(const double* cdf, long long N, double u0, const do
         const long long blocks = (ntiles + 7) / 8;
         const long long cap = (long long)device_sm_count() * 8;
         const int grid = (int)(blocks < cap ? blocks : cap);
-#define SMCB_RS(L) resample_systematic_fused_kernel<L><<<grid, 256, 0, st>>>(cdf, N, u0, u0_dev, j0, M_total, M, x, out, idx, bounds)
+#define SMCB_RS(L) \
+    resample_systematic_fused_kernel<L><<<grid, 256, 0, st>>>(cdf, N, u0, u0_dev, j0, M_total, M, x, out, idx, bounds, nullptr, 1)
         switch (lpr) {
             case 1: SMCB_RS(1); break;
             case 2: SMCB_RS(2); break;
@@ -339,6 +352,62 @@ int smcb_resample_systematic(const double* cdf, long long N, double u0, const do
     if (check_launch("ancestors_systematic_kernel")) return -1;
     gather_rows_kernel<1><<<stride_grid(M * D, 256, 8), 256, 0, st>>>(x, idx, M, D, out);
     return check_launch("gather_rows_kernel");
+}
+
+int smcb_resample_systematic_push(const double* cdf, long long N, double u0, long long j0, long long M_total,
+                                  long long M, const double* x, int D, double* const* peer_out, long long rows_per_rank,
+                                  int64_t* idx, void* workspace, void* stream) {
+    SMCB_REQUIRE(cdf && x && peer_out && workspace && N >= 1 && M >= 0 && M_total >= 1 && rows_per_rank >= 1, "bad argument");
+    SMCB_REQUIRE(D == 2 || D == 4 || D == 8 || D == 16 || D == 32 || D == 64, "push path needs D in {2,4,8,16,32,64}");
+    if (M == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int lpr = D / 2;
+    const long long ntiles = (M + 31) / 32;
+    long long* bounds = (long long*)workspace;
+    tile_bounds_kernel<<<stride_grid(ntiles + 1, 256, 8), 256, 0, st>>>(cdf, N, u0, nullptr, j0, M_total, M, 32, ntiles, bounds);
+    if (check_launch("tile_bounds_kernel")) return -1;
+    const long long blocks = (ntiles + 7) / 8;
+    const long long cap = (long long)device_sm_count() * 8;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+#define SMCB_RSP(L)                                                                                                      \
+    resample_systematic_fused_kernel<L><<<grid, 256, 0, st>>>(cdf, N, u0, nullptr, j0, M_total, M, x, nullptr, idx, bounds, \
+                                                              peer_out, rows_per_rank)
+    switch (lpr) {
+        case 1: SMCB_RSP(1); break;
+        case 2: SMCB_RSP(2); break;
+        case 4: SMCB_RSP(4); break;
+        case 8: SMCB_RSP(8); break;
+        case 16: SMCB_RSP(16); break;
+        default: SMCB_RSP(32); break;
+    }
+#undef SMCB_RSP
+    return check_launch("resample_systematic_fused_kernel(push)");
+}
+
+// ---- peer-visible buffers (CUDA IPC): the destinations of the fused migration
+int smcb_peer_alloc(long long bytes, void** ptr, void* handle64) {
+    SMCB_REQUIRE(ptr && handle64 && bytes > 0, "bad argument");
+    SMCB_CUDA(cudaMalloc(ptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    SMCB_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int smcb_peer_open(const void* handle64, void** ptr) {
+    SMCB_REQUIRE(ptr && handle64, "bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SMCB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int smcb_peer_close(void* ptr) {
+    if (ptr) SMCB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+int smcb_peer_free(void* ptr) {
+    if (ptr) SMCB_CUDA(cudaFree(ptr));
+    return 0;
 }
 
 int smcb_gather_rows(const double* x, const int64_t* idx, long long M, int D, double* out, void* stream) {

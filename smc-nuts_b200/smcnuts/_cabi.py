@@ -44,6 +44,11 @@ _SIGS = {
     "smcb_ancestors_systematic": [_vp, _ll, _d, _ll, _ll, _ll, _vp, _vp],
     "smcb_resample_systematic": [_vp, _ll, _d, _vp, _ll, _ll, _ll, _vp, _i, _vp, _vp, _vp, _vp],
     "smcb_resample_workspace_bytes": [_ll, _i],
+    "smcb_resample_systematic_push": [_vp, _ll, _d, _ll, _ll, _ll, _vp, _i, _vp, _ll, _vp, _vp, _vp],
+    "smcb_peer_alloc": [_ll, ctypes.POINTER(_vp), _vp],
+    "smcb_peer_open": [_vp, ctypes.POINTER(_vp)],
+    "smcb_peer_close": [_vp],
+    "smcb_peer_free": [_vp],
     "smcb_gather_rows": [_vp, _vp, _ll, _i, _vp, _vp],
     "smcb_weighted_moment": [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _vp, _vp],
     "smcb_count_moved": [_vp, _vp, _ll, _i, _vp, _vp, _vp],

@@ -68,6 +68,70 @@ class ShardContext:
         return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
 
 
+class _RawDeviceArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view memory the C library allocated."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class PeerBuffers:
+    """Double-buffered, peer-visible destination buffers for the fused particle migration.
+
+    Every rank allocates `nbuf` buffers of [rows, D] doubles through the C-ABI (cudaMalloc + CUDA IPC handle), the
+    handles are all-gathered, and every rank maps the other ranks' buffers (NVLink peer access).  The resampling
+    kernel then stores migrating rows directly into the destination's buffer (smcb_resample_systematic_push)."""
+
+    def __init__(self, shard, rows, D, nbuf=2):
+        import ctypes
+        from . import _cabi
+        self.shard, self.rows, self.D, self.nbuf, self.cur = shard, rows, D, nbuf, 0
+        dev_ = torch.device("cuda", torch.cuda.current_device())
+        nbytes = rows * D * 8
+        self.local, handles = [], torch.empty(nbuf * 64, dtype=torch.uint8)
+        for b in range(nbuf):
+            ptr, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+            _cabi.call("smcb_peer_alloc", nbytes, ctypes.byref(ptr), ctypes.cast(h, ctypes.c_void_p))
+            self.local.append(ptr.value)
+            handles[b * 64:(b + 1) * 64] = torch.frombuffer(bytearray(h), dtype=torch.uint8)
+        allh = torch.empty(shard.world * nbuf * 64, dtype=torch.uint8, device=dev_)
+        dist.all_gather_into_tensor(allh, handles.to(dev_), group=shard.group)
+        allh = allh.cpu().numpy().reshape(shard.world, nbuf, 64)
+        self.opened, tables = [], []
+        for b in range(nbuf):
+            ptrs = []
+            for q in range(shard.world):
+                if q == shard.rank:
+                    ptrs.append(self.local[b])
+                else:
+                    p = ctypes.c_void_p()
+                    hb = (ctypes.c_ubyte * 64).from_buffer_copy(allh[q, b].tobytes())
+                    _cabi.call("smcb_peer_open", ctypes.cast(hb, ctypes.c_void_p), ctypes.byref(p))
+                    self.opened.append(p.value)
+                    ptrs.append(p.value)
+            tables.append(torch.tensor(ptrs, dtype=torch.int64).to(dev_))
+        self.tables = tables
+        self.views = [torch.as_tensor(_RawDeviceArray(p, (rows, D)), device=dev_) for p in self.local]
+        self._token = torch.zeros(1, dtype=torch.float64, device=dev_)
+
+    def next(self):
+        self.cur = (self.cur + 1) % self.nbuf
+        return self.cur
+
+    def fence(self):
+        """Stream-ordered completion barrier: every rank's push kernel precedes its contribution."""
+        dist.all_reduce(self._token, group=self.shard.group)
+
+    def close(self):
+        from . import _cabi
+        for p in self.opened:
+            _cabi.lib().smcb_peer_close(p)
+        for p in self.local:
+            _cabi.lib().smcb_peer_free(p)
+        self.opened, self.local = [], []
+
+
 def systematic_slot_bounds(boundaries, u0, n_total):
     """For cdf boundaries B_0 = 0 <= B_1 <= ... <= B_P (B_{q+1} = last cdf value held by rank q), return
     c[q] = number of systematic positions pos_j = (j + u0)/n_total, j = 0..n_total-1, with pos_j < B_q.

@@ -45,6 +45,8 @@ class Resampler:
         self.N, self.seed, self.shard, self.stream, self.scheme = N, seed, shard, stream, scheme
         self.n_local = shard.local_count(N)
         self.offset = shard.offset(N)
+        self.peers = None             # PeerBuffers for the fused NVLink migration (sharded systematic resampling)
+        self.use_peer_push = True
         self.keep_idx = True          # materialise the ancestor indices (diagnostic; bench.py turns it off)
         self.last_idx = None          # ancestors of the last resample (global indices for this rank's slots)
         self.last_migrated_rows = 0   # rows this rank received from other ranks (diagnostic)
@@ -116,6 +118,23 @@ class Resampler:
         bounds = systematic_slot_bounds(np.concatenate([[0.0], lasts]), u0, self.N)
         lo, hi = int(bounds[sh.rank]), int(bounds[sh.rank + 1])
         m = hi - lo
+        mylo, myhi = sh.rank * self.n_local, (sh.rank + 1) * self.n_local
+        recv_counts = [max(0, min(myhi, int(bounds[q + 1])) - max(mylo, int(bounds[q]))) for q in range(sh.world)]
+        self.last_migrated_rows = sum(c for q, c in enumerate(recv_counts) if q != sh.rank)
+        if self.use_peer_push and D in (2, 4, 8, 16, 32, 64):
+            # fused path: gather + migration in one kernel, rows stored straight into the destination GPU over NVLink
+            if self.peers is None or self.peers.D != D:
+                from ..parallel import PeerBuffers
+                self.peers = PeerBuffers(sh, self.n_local, D)
+            b = self.peers.next()
+            keep = dev.empty(max(m, 1), dtype=torch.int64) if self.keep_idx else None
+            if m:
+                ws = dev.workspace("resample", _cabi.lib().smcb_resample_workspace_bytes(m, D))
+                _cabi.call("smcb_resample_systematic_push", dev.ptr(cdf), n, u0, lo, self.N, m, dev.ptr(x), D,
+                           dev.ptr(self.peers.tables[b]), self.n_local, dev.ptr(keep), dev.ptr(ws), st)
+            self.peers.fence()
+            self.last_idx = keep[:m] + self.offset if keep is not None else None
+            return self.peers.views[b]
         idx = dev.empty(max(m, 1), dtype=torch.int64)
         send = dev.empty(max(m, 1), D)
         if m:
@@ -123,9 +142,6 @@ class Resampler:
             _cabi.call("smcb_resample_systematic", dev.ptr(cdf), n, u0, 0, lo, self.N, m, dev.ptr(x), D, dev.ptr(send),
                        dev.ptr(idx), dev.ptr(ws), st)
         send_counts = split_counts(lo, hi, self.n_local, sh.world)
-        mylo, myhi = sh.rank * self.n_local, (sh.rank + 1) * self.n_local
-        recv_counts = [max(0, min(myhi, int(bounds[q + 1])) - max(mylo, int(bounds[q]))) for q in range(sh.world)]
-        self.last_migrated_rows = sum(c for q, c in enumerate(recv_counts) if q != sh.rank)
         self.last_idx = idx[:m] + self.offset
         return sh.all_to_all_rows(send[:m], send_counts, recv_counts)
 
