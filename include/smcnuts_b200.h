@@ -58,8 +58,12 @@ int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long lon
 int smcb_nuts_transition(void* handle, const double* x, const double* r, long long N, double eps, double phi,
                          int max_depth, int accrej, uint64_t seed, uint32_t iteration, uint64_t particle0,
                          double* x_new, double* r_new, double* A_old, double* B_old, double* A_new, double* B_new,
-                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth, void* workspace,
+                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth,
+                         const double* A_in, const double* B_in, const double* g_in, double* g_new, void* workspace,
                          long long workspace_bytes, void* stream);
+/* A_in/B_in/g_in (all or none, accrej == 0): the split log density and gradient at x handed back from the previous
+ * transition's A_new/B_new/g_new at the same phi -- the initial evaluation (nuts.py:66,72) is then skipped.
+ * g_new (nullable): gradient of A + phi*B at the returned x_new. */
 
 /* ---- Philox streams (momentum_proposal.rvs samples.py:155; sample_proposal.rvs samples.py:77) */
 int smcb_normals(uint64_t seed, uint32_t iteration, uint32_t stream_id, uint64_t particle0, long long N, int D,

@@ -184,7 +184,7 @@ static int launch_nuts(const Model* mdl, NutsArgs a, long long ws_bytes, cudaStr
     const long long blocks = nuts_blocks<M>(mdl, a.N, smem, nullptr);
     if (blocks < 0) return fail("smcb_nuts_transition", "kernel does not fit on an SM");
     M probe(mdl->desc, nullptr);
-    const int rec = nuts_ws_doubles(probe.nloc(), a.max_depth);
+    const int rec = nuts_ws_doubles(probe.nloc(), a.max_depth, a.g_new != nullptr);
     const long long ws_need = (long long)sizeof(double) * rec * blocks * NT + 256;
     if (ws_bytes < ws_need) return fail("smcb_nuts_transition", "workspace too small (see smcb_nuts_workspace_bytes)");
     // queue head lives in the last 256 bytes of the workspace
@@ -317,9 +317,13 @@ int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long lon
 int smcb_nuts_transition(void* handle, const double* x, const double* r, long long N, double eps, double phi,
                          int max_depth, int accrej, uint64_t seed, uint32_t iteration, uint64_t particle0,
                          double* x_new, double* r_new, double* A_old, double* B_old, double* A_new, double* B_new,
-                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth, void* workspace,
+                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth,
+                         const double* A_in, const double* B_in, const double* g_in, double* g_new, void* workspace,
                          long long workspace_bytes, void* stream) {
     SMCB_REQUIRE(handle && x && r && x_new && r_new && workspace, "null argument");
+    SMCB_REQUIRE((A_in && B_in && g_in) || (!A_in && !B_in && !g_in), "A_in, B_in, g_in: all three or none");
+    SMCB_REQUIRE(!(accrej && (g_in || g_new)), "gradient carry-over is not available with the accept-reject epilogue");
+    SMCB_REQUIRE(g_new != x_new && (!g_in || (g_in != g_new)), "g_new must not alias its inputs");
     SMCB_REQUIRE(x != x_new && r != r_new, "x_new/r_new must not alias x/r");
     SMCB_REQUIRE(max_depth >= 1 && max_depth <= 10, "max_depth must be in [1, 10] (reference: MAX_TREE_DEPTH = 10)");
     SMCB_REQUIRE(iteration < (1u << 24), "iteration must be < 2^24");
@@ -331,6 +335,7 @@ int smcb_nuts_transition(void* handle, const double* x, const double* r, long lo
     a.seed = seed; a.iteration = iteration; a.particle0 = particle0;
     a.x_new = x_new; a.r_new = r_new; a.A_old = A_old; a.B_old = B_old; a.A_new = A_new; a.B_new = B_new;
     a.ke_old = ke_old; a.ke_new = ke_new; a.n_leapfrog = n_leapfrog; a.accepted = accepted; a.depth = depth;
+    a.A_in = A_in; a.B_in = B_in; a.g_in = g_in; a.g_new = g_new;
     a.ws = (double*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     switch (m->desc.kind) {

@@ -52,6 +52,13 @@ struct NutsArgs {
     int* n_leapfrog;      // [N] leapfrog steps = gradient evaluations excluding the initial one (nullable)
     int* accepted;        // [N] MH outcome (1 when accrej == 0)     (nullable)
     int* depth;           // [N] number of doublings                 (nullable)
+    // gradient carry-over (optional, accrej == 0 only): when the caller hands back the split log density and the
+    // gradient of the current positions (outputs A_new, B_new, g_new of the previous transition at the same phi), the
+    // initial evaluation of every transition (nuts.py:66,72) is skipped -- same numbers, one model evaluation less.
+    const double* A_in;   // [N]      (nullable; all three or none)
+    const double* B_in;   // [N]
+    const double* g_in;   // [N, D]   gradient of A + phi*B at x
+    double* g_new;        // [N, D]   gradient at the returned x_new (nullable)
     double* ws;           // workspace: lanes * ws_doubles(D, max_depth)
     unsigned long long* queue;  // work-queue head, zeroed before launch
 };
@@ -59,7 +66,10 @@ struct NutsArgs {
 // doubles of workspace per LANE; nl = coordinates held by one lane (D for one-lane-per-particle models)
 // record: other edge (3 nl) | slot 0: checkpoint (2 nl), candidate (2 nl + 2) | slot 1: ... -- checkpoint s and
 // candidate s are neighbours so that the hot low slots of a lane share cache lines (the L1 serves this traffic)
-SMCB_HD int nuts_ws_doubles(int nl, int L) { return ((3 * nl + (4 * nl + 2) * (L + 1)) + 15) & ~15; }
+// (candidates carry their gradient as well, nl more doubles per slot, when the caller asked for g_new)
+SMCB_HD int nuts_ws_doubles(int nl, int L, bool carry = true) {
+    return ((3 * nl + (4 * nl + 2 + (carry ? nl : 0)) * (L + 1)) + 15) & ~15;
+}
 
 enum LanePhase : int { kIdle = 0, kInit = 1, kLeaf = 2 };
 
@@ -76,6 +86,7 @@ struct Lane {
     double* ws;    // cold per-lane record in global memory
     double* hot;   // hot per-lane record in shared memory, element e at hot[e * hs]  (nullptr: none)
     int hs, hc, hk;  // shared-memory stride; number of U-turn checkpoint / candidate slots that live in shared memory
+    int slot_stride;  // doubles per (checkpoint, candidate) slot pair in the global record
     int phase, dir, depth, D, L, nl, sub;
     uint32_t leaf, n_tot, n_leapfrog, free_mask;
     uint64_t pend_n, pend_ref;
@@ -102,11 +113,11 @@ struct Lane {
     SMCB_HD View other_xr() const { return hot ? View{hot, hs} : View{ws, 1}; }          // x at [i], r at [nl + i]
     SMCB_HD double* other_g() const { return ws + 2 * nl; }
     SMCB_HD View ckpt(int slot) const {                                                    // x at [i], r at [nl + i]
-        return slot < hc ? View{hot + (size_t)(2 * nl + 2 * nl * slot) * hs, hs} : View{ws + 3 * nl + (4 * nl + 2) * slot, 1};
+        return slot < hc ? View{hot + (size_t)(2 * nl + 2 * nl * slot) * hs, hs} : View{ws + 3 * nl + slot_stride * slot, 1};
     }
     SMCB_HD View cand(int slot) const {                                                    // x, r, A, B
         return slot < hk ? View{hot + (size_t)(2 * nl + 2 * nl * hc + (2 * nl + 2) * slot) * hs, hs}
-                         : View{ws + 3 * nl + (4 * nl + 2) * slot + 2 * nl, 1};
+                         : View{ws + 3 * nl + slot_stride * slot + 2 * nl, 1};   // x, r, A, B [, g]
     }
     SMCB_HD static int hot_doubles(int nl_, int hc_, int hk_) { return 2 * nl_ + 2 * nl_ * hc_ + (2 * nl_ + 2) * hk_; }
 
@@ -137,7 +148,13 @@ struct Lane {
         }
         rng.reset(a.seed, a.iteration, kStreamNuts, a.particle0 + (uint64_t)p);
         n_leapfrog = 0;
+        slot_stride = 4 * nl + 2 + (a.g_new ? nl : 0);
         phase = kInit;
+        if (a.g_in) {   // carried-over evaluation: initialise the tree right away, the first trip is already a leapfrog
+#pragma unroll
+            SMCB_LOCAL(i) ga[i] = gd(i) < d_ ? a.g_in[p * d_ + gd(i)] : 0.0;
+            init_tree(a, a.A_in[p], a.B_in[p]);
+        }
     }
 
     SMCB_HD void prefetch_lines(const double* p, int ndoubles) const {
@@ -213,9 +230,32 @@ struct Lane {
             if (gd(i) < d_) {
                 a.x_new[pid * d_ + gd(i)] = xa[i];
                 a.r_new[pid * d_ + gd(i)] = ra[i];
+                if (a.g_new) a.g_new[pid * d_ + gd(i)] = ga[i];
             }
         }
         As = A; Bs = B;
+    }
+
+    // nuts.py:66-87 given logp = A + phi*B and its gradient (already in `ga`) at the start point
+    SMCB_HD void init_tree(const NutsArgs& a, double A, double B) {
+        const int n_ = nl;
+        double lp = A + a.phi * B;
+        if (!is_finite(lp)) lp = neg_inf();
+        double rr = 0.0;
+#pragma unroll
+        SMCB_LOCAL(i) rr += ra[i] * ra[i];
+        ke0 = 0.5 * gsum(rr);
+        A0 = A; B0 = B;
+        const double H0 = lp - ke0;
+        logu = H0 - (-log1p(-rng.next()));
+        write_sample_from_active(a, A, B);
+        const View o = other_xr();
+        double* og = other_g();
+#pragma unroll
+        SMCB_LOCAL(i) { o[i] = xa[i]; o[n_ + i] = ra[i]; og[i] = ga[i]; }
+        n_tot = 1; depth = 0;
+        start_doubling(true);
+        phase = kLeaf;
     }
 
     // Unconditional hand-over of the fresh gradient (also on idle lanes, so that `ga` is dead across the model
@@ -236,22 +276,8 @@ struct Lane {
             SMCB_LOCAL(i) if (gd(i) < d_) ga[i] = neg_inf();
         }
 
-        if (phase == kInit) {  // nuts.py:66-87
-            double rr = 0.0;
-#pragma unroll
-            SMCB_LOCAL(i) rr += ra[i] * ra[i];
-            ke0 = 0.5 * gsum(rr);
-            A0 = A; B0 = B;
-            const double H0 = lp - ke0;
-            logu = H0 - (-log1p(-rng.next()));
-            write_sample_from_active(a, A, B);
-            const View o = other_xr();
-            double* og = other_g();
-#pragma unroll
-            SMCB_LOCAL(i) { o[i] = xa[i]; o[n_ + i] = ra[i]; og[i] = ga[i]; }
-            n_tot = 1; depth = 0;
-            start_doubling(true);
-            phase = kLeaf;
+        if (phase == kInit) {
+            init_tree(a, A, B);
             return false;
         }
 
@@ -308,6 +334,7 @@ struct Lane {
                         if (gd(i) < d_) {
                             a.x_new[pid * d_ + gd(i)] = c[i];
                             a.r_new[pid * d_ + gd(i)] = c[n_ + i];
+                            if (a.g_new) a.g_new[pid * d_ + gd(i)] = c[2 * n_ + 2 + i];
                         }
                     }
                     As = c[2 * n_]; Bs = c[2 * n_ + 1];
@@ -329,6 +356,10 @@ struct Lane {
 #pragma unroll
             SMCB_LOCAL(i) { c[i] = xa[i]; c[n_ + i] = ra[i]; }
             c[2 * n_] = A; c[2 * n_ + 1] = B;
+            if (a.g_new) {
+#pragma unroll
+                SMCB_LOCAL(i) c[2 * n_ + 2 + i] = ga[i];
+            }
         }
         set_n(lv, run_n);
         set_ref(lv, run_ref);

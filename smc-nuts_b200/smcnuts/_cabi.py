@@ -22,7 +22,7 @@ _SIGS = {
     "smcb_logp_grad": [_vp, _vp, _ll, _d, _vp, _vp, _vp, _vp],
     "smcb_combine_logp": [_vp, _vp, _d, _ll, _vp, _vp],
     "smcb_nuts_workspace_bytes": [_vp, _ll, _i, ctypes.POINTER(_ll)],
-    "smcb_nuts_transition": [_vp, _vp, _vp, _ll, _d, _d, _i, _i, _u64, _u32, _u64] + [_vp] * 11 + [_vp, _ll, _vp],
+    "smcb_nuts_transition": [_vp, _vp, _vp, _ll, _d, _d, _i, _i, _u64, _u32, _u64] + [_vp] * 15 + [_vp, _ll, _vp],
     "smcb_normals": [_u64, _u32, _u32, _u64, _ll, _i, _vp, _vp],
     "smcb_uniforms": [_u64, _u32, _u32, _u64, _ll, _u32, _vp, _vp],
     "smcb_row_half_sqnorm": [_vp, _ll, _i, _vp, _vp],

@@ -41,9 +41,12 @@ class NUTSProposal:
         self.iteration += 1
         return dev.to_host_like(out["x_new"], x_cond, "x_new"), dev.to_host_like(out["r_new"], r_cond, "r_new")
 
-    def transition(self, x, r, phi=1.0, iteration=None):
+    def transition(self, x, r, phi=1.0, iteration=None, carry=None, want_grad=False):
         """Device entry point: returns dict of device tensors (x_new, r_new, A_old, B_old, A_new, B_new,
-        ke_old, ke_new, n_leapfrog, accepted, depth)."""
+        ke_old, ke_new, n_leapfrog, accepted, depth[, g_new]).
+
+        carry = (A, B, g) at `x` (the previous transition's A_new, B_new, g_new at the same phi) skips the initial
+        model evaluation of every transition; want_grad=True also returns g_new for the next call."""
         N, D = x.shape
         it = self.iteration if iteration is None else iteration
         h = self.target.handle
@@ -54,6 +57,11 @@ class NUTSProposal:
                  A_new=dev.empty(N), B_new=dev.empty(N), ke_old=dev.empty(N), ke_new=dev.empty(N),
                  n_leapfrog=dev.empty(N, dtype=torch.int32), accepted=dev.empty(N, dtype=torch.int32),
                  depth=dev.empty(N, dtype=torch.int32))
+        if self.accept_reject:
+            carry, want_grad = None, False
+        if want_grad:
+            o["g_new"] = dev.empty(N, D)
+        cA, cB, cg = carry if carry is not None else (None, None, None)
         if self.record_events:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -61,8 +69,8 @@ class NUTSProposal:
                    self.max_tree_depth, int(self.accept_reject), self.seed, it, self.particle0,
                    dev.ptr(o["x_new"]), dev.ptr(o["r_new"]), dev.ptr(o["A_old"]), dev.ptr(o["B_old"]),
                    dev.ptr(o["A_new"]), dev.ptr(o["B_new"]), dev.ptr(o["ke_old"]), dev.ptr(o["ke_new"]),
-                   dev.ptr(o["n_leapfrog"]), dev.ptr(o["accepted"]), dev.ptr(o["depth"]), dev.ptr(ws), ws.numel(),
-                   dev.stream_ptr())
+                   dev.ptr(o["n_leapfrog"]), dev.ptr(o["accepted"]), dev.ptr(o["depth"]), dev.ptr(cA), dev.ptr(cB),
+                   dev.ptr(cg), dev.ptr(o.get("g_new")), dev.ptr(ws), ws.numel(), dev.stream_ptr())
         if self.record_events:
             e1.record()
             self.events.append((e0, e1))

@@ -227,6 +227,7 @@ class Samples:
             self.phi_old = 1.0
             self.phi_new = 1.0
         self._stats = None
+        self._carry = None       # (A, B, grad) at the current x, handed back to the NUTS kernel (skips its initial evaluation)
         self._split_new = None   # (A, B) at x_new from the last transition
         self._split_x = None     # (A, B) at x (pre-move), from the last transition
         self._ke = None
@@ -298,6 +299,7 @@ class Samples:
     def _resample(self, x, wn, log_likelihood):
         """samples.py:125-146."""
         self.x = self.resampler.resample_rows(x, wn, self.iteration)
+        self._carry = None   # the carried evaluation belongs to the pre-resampling rows
         self.logw = dev.empty(self.n_local)
         _cabi.call("smcb_uniform_logw", dev.ptr(self._stats), self.N, self.n_local, dev.ptr(self.logw), dev.stream_ptr())
 
@@ -307,7 +309,11 @@ class Samples:
         self.r = self._draw_std_normal(fk.momentum_proposal, _cabi.STREAM_MOMENTUM, self.iteration)
         if hasattr(fk, "transition"):
             fk.particle0 = self.offset
-            o = fk.transition(self.x, self.r, self.phi_new, iteration=self.iteration)
+            # constant temperature and no MH epilogue: the evaluation at x_new is the next iteration's evaluation at x
+            can_carry = self.TemperingScheme is None and not getattr(fk, "accept_reject", False)
+            o = fk.transition(self.x, self.r, self.phi_new, iteration=self.iteration,
+                              carry=self._carry if can_carry else None, want_grad=can_carry)
+            self._carry = (o["A_new"], o["B_new"], o["g_new"]) if can_carry else None
             self.x_new, self.r_new = o["x_new"], o["r_new"]
             self._split_x, self._split_new = (o["A_old"], o["B_old"]), (o["A_new"], o["B_new"])
             self._ke = (o["ke_old"], o["ke_new"])

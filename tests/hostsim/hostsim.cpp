@@ -12,7 +12,7 @@ using namespace smcb;
 
 template <class M>
 static void run(NutsArgs a, int lanes) {
-    const int rec = nuts_ws_doubles(M(a.model, a.model.data).nloc(), a.max_depth);
+    const int rec = nuts_ws_doubles(M(a.model, a.model.data).nloc(), a.max_depth, a.g_new != nullptr);
     std::vector<double> ws((size_t)lanes * rec, 0.0);
     std::vector<Lane<M>> L(lanes);
     M model(a.model, a.model.data);
@@ -39,7 +39,8 @@ extern "C" int hostsim_nuts(int kind, const double* data, int n_data, int dim, i
                             const double* r, long long N, double eps, double phi, int max_depth, int accrej,
                             unsigned long long seed, unsigned iteration, unsigned long long particle0, double* x_new,
                             double* r_new, double* A_old, double* B_old, double* A_new, double* B_new, double* ke_old,
-                            double* ke_new, int* n_leapfrog, int* accepted, int* depth, int lanes) {
+                            double* ke_new, int* n_leapfrog, int* accepted, int* depth, const double* A_in,
+                            const double* B_in, const double* g_in, double* g_new, int lanes) {
     NutsArgs a;
     std::memset(&a, 0, sizeof a);
     a.model = ModelDesc{kind, dim, n_data, T, q, data};
@@ -47,6 +48,7 @@ extern "C" int hostsim_nuts(int kind, const double* data, int n_data, int dim, i
     a.seed = seed; a.iteration = iteration; a.particle0 = particle0;
     a.x_new = x_new; a.r_new = r_new; a.A_old = A_old; a.B_old = B_old; a.A_new = A_new; a.B_new = B_new;
     a.ke_old = ke_old; a.ke_new = ke_new; a.n_leapfrog = n_leapfrog; a.accepted = accepted; a.depth = depth;
+    a.A_in = A_in; a.B_in = B_in; a.g_in = g_in; a.g_new = g_new;
     if (kind == kArma) run<ArmaModel>(a, lanes);
     else if (kind == kPRMwCD) run<PrmModel>(a, lanes);
     else run<GaussModel>(a, lanes);

@@ -42,7 +42,8 @@ def pack_model(name, np_target):
     return 2, np.ascontiguousarray(np_target.P.ravel()), np_target.dim, 0, 0.0
 
 
-def nuts(name, np_target, x, r, eps, phi, max_depth=10, accrej=False, seed=0, iteration=0, particle0=0, lanes=32):
+def nuts(name, np_target, x, r, eps, phi, max_depth=10, accrej=False, seed=0, iteration=0, particle0=0, lanes=32,
+         carry=None, want_grad=False):
     kind, data, dim, T, q = pack_model(name, np_target)
     x = np.ascontiguousarray(x, dtype=np.float64)
     r = np.ascontiguousarray(r, dtype=np.float64)
@@ -50,12 +51,16 @@ def nuts(name, np_target, x, r, eps, phi, max_depth=10, accrej=False, seed=0, it
     o = dict(x_new=np.empty_like(x), r_new=np.empty_like(r), A_old=np.empty(N), B_old=np.empty(N), A_new=np.empty(N),
              B_new=np.empty(N), ke_old=np.empty(N), ke_new=np.empty(N), n_leapfrog=np.empty(N, dtype=np.int32),
              accepted=np.empty(N, dtype=np.int32), depth=np.empty(N, dtype=np.int32))
-    P = lambda a: a.ctypes.data_as(_dp)  # noqa: E731
+    if want_grad:
+        o["g_new"] = np.empty_like(x)
+    cA, cB, cg = (np.ascontiguousarray(c, dtype=np.float64) for c in carry) if carry is not None else (None, None, None)
+    P = lambda a: a.ctypes.data_as(_dp) if a is not None else None  # noqa: E731
     I = lambda a: a.ctypes.data_as(_ip)  # noqa: E731
     lib().hostsim_nuts(ctypes.c_int(kind), P(data), ctypes.c_int(data.size), ctypes.c_int(dim), ctypes.c_int(T),
                        ctypes.c_double(q), P(x), P(r), ctypes.c_longlong(N), ctypes.c_double(eps), ctypes.c_double(phi),
                        ctypes.c_int(max_depth), ctypes.c_int(int(accrej)), ctypes.c_ulonglong(seed),
                        ctypes.c_uint(iteration), ctypes.c_ulonglong(particle0), P(o["x_new"]), P(o["r_new"]),
                        P(o["A_old"]), P(o["B_old"]), P(o["A_new"]), P(o["B_new"]), P(o["ke_old"]), P(o["ke_new"]),
-                       I(o["n_leapfrog"]), I(o["accepted"]), I(o["depth"]), ctypes.c_int(lanes))
+                       I(o["n_leapfrog"]), I(o["accepted"]), I(o["depth"]), P(cA), P(cB), P(cg), P(o.get("g_new")),
+                       ctypes.c_int(lanes))
     return o

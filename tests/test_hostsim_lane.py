@@ -74,3 +74,21 @@ def test_max_depth_cap():
         o = sim.nuts("gauss", t.np_target, x, r, 1e-6, 1.0, L, False, 1, 0, 0, lanes=2)
         assert np.all(ref["n_leapfrog"] == 2 ** (L + 1) - 1) and np.array_equal(o["n_leapfrog"], ref["n_leapfrog"])
         assert np.array_equal(o["x_new"], ref["x_new"])
+
+
+@pytest.mark.parametrize("tname,kw,eps", [("arma", {}, 0.01), ("gauss", {"dim": 8}, 0.1)])
+def test_gradient_carry_over_skips_the_initial_evaluation_without_changing_anything(tname, kw, eps):
+    """Two consecutive transitions: handing (A_new, B_new, g_new) of the first to the second must give bit-identical
+    results to re-evaluating the model at the start point (nuts.py:66,72)."""
+    t = O.COracleTarget(tname, **kw)
+    rng = np.random.default_rng(9)
+    N = 200
+    x = rng.normal(size=(N, t.dim)) * 0.2 + (np.array([0.0, 0.9, 0.0, -1.7]) if tname == "arma" else 0.0)
+    r1, r2 = rng.normal(size=(2, N, t.dim))
+    a = sim.nuts(tname, t.np_target, x, r1, eps, 1.0, 10, False, 5, 0, 0, lanes=7, want_grad=True)
+    np.testing.assert_allclose(a["g_new"], t.logpdfgrad(a["x_new"], 1.0), rtol=1e-12, atol=1e-12)
+    plain = sim.nuts(tname, t.np_target, a["x_new"], r2, eps, 1.0, 10, False, 5, 1, 0, lanes=7, want_grad=True)
+    carried = sim.nuts(tname, t.np_target, a["x_new"], r2, eps, 1.0, 10, False, 5, 1, 0, lanes=7,
+                       carry=(a["A_new"], a["B_new"], a["g_new"]), want_grad=True)
+    for k in ("x_new", "r_new", "A_old", "B_old", "A_new", "B_new", "n_leapfrog", "depth", "g_new", "ke_old", "ke_new"):
+        assert np.array_equal(plain[k], carried[k]), k
