@@ -50,12 +50,7 @@ template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BL
 
 template <class M>
 static size_t nuts_smem_bytes(const ModelDesc& d) {
-    size_t doubles = (size_t)((M::staged_doubles(d) + 1) & ~1);
-    if (LaunchCfg<M>::HOT) {
-        M probe(d, nullptr);
-        doubles += (size_t)LaunchCfg<M>::NT * Lane<M>::hot_doubles(probe.nloc(), LaunchCfg<M>::HC, LaunchCfg<M>::HK);
-    }
-    return doubles * sizeof(double);
+    return sizeof(double) * (size_t)M::staged_doubles(d);
 }
 
 template <class M> struct StageOffset { static int of(const ModelDesc&) { return 0; } };
@@ -83,11 +78,7 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
     M model(a.model, stage_model<M>(a.model, smem, staged, stage_offset));
     const unsigned lane_id = threadIdx.x & 31u;
     Lane<M> lane;
-    if constexpr (LaunchCfg<M>::HOT)
-        lane.idle_init(model, (int)(lane_id % G), smem + ((staged + 1) & ~1) + threadIdx.x, (int)blockDim.x, LaunchCfg<M>::HC,
-                       LaunchCfg<M>::HK);
-    else
-        lane.idle_init(model, (int)(lane_id % G));
+    lane.idle_init(model, (int)(lane_id % G));
     double* ws = a.ws + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * rec_doubles;
     constexpr unsigned kLeaders = G == 1 ? 0xffffffffu : 0x11111111u;   // first lane of every particle group
     const unsigned group_first = lane_id & ~(unsigned)(G - 1);

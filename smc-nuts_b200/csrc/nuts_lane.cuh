@@ -63,12 +63,20 @@ struct NutsArgs {
     unsigned long long* queue;  // work-queue head, zeroed before launch
 };
 
-// doubles of workspace per LANE; nl = coordinates held by one lane (D for one-lane-per-particle models)
-// record: other edge (3 nl) | slot 0: checkpoint (2 nl), candidate (2 nl + 2) | slot 1: ... -- checkpoint s and
-// candidate s are neighbours so that the hot low slots of a lane share cache lines (the L1 serves this traffic)
-// (candidates carry their gradient as well, nl more doubles per slot, when the caller asked for g_new)
+// 16-byte pair, the unit of every access to the per-lane workspace record (LDG.128 / STG.128)
+struct alignas(16) D2 {
+    double x, y;
+};
+
+// Workspace record of one LANE (global memory, 128-byte aligned; nlp = nl rounded up to even so that every vector is
+// 16-byte aligned):
+//   other edge: x[nlp] r[nlp] g[nlp] | slot 0: checkpoint x[nlp] r[nlp], candidate x[nlp] r[nlp] A B [g[nlp]] | slot 1 ...
+// Checkpoint s and candidate s are neighbours so that the hot low slots share cache lines (the L1 serves this
+// traffic); candidates carry their gradient only when the caller asked for g_new.
+SMCB_HD int nuts_nlp(int nl) { return (nl + 1) & ~1; }
+SMCB_HD int nuts_slot_stride(int nl, bool carry) { return 4 * nuts_nlp(nl) + 2 + (carry ? nuts_nlp(nl) : 0); }
 SMCB_HD int nuts_ws_doubles(int nl, int L, bool carry = true) {
-    return ((3 * nl + (4 * nl + 2 + (carry ? nl : 0)) * (L + 1)) + 15) & ~15;
+    return ((3 * nuts_nlp(nl) + nuts_slot_stride(nl, carry) * (L + 1)) + 15) & ~15;
 }
 
 enum LanePhase : int { kIdle = 0, kInit = 1, kLeaf = 2 };
@@ -83,16 +91,15 @@ struct Lane {
     double xa[DM], ra[DM], ga[DM];  // active edge (this lane's coordinates)
     double logu, A0, B0, As, Bs, ke0;
     long long pid;
-    double* ws;    // cold per-lane record in global memory
-    double* hot;   // hot per-lane record in shared memory, element e at hot[e * hs]  (nullptr: none)
-    int hs, hc, hk;  // shared-memory stride; number of U-turn checkpoint / candidate slots that live in shared memory
-    int slot_stride;  // doubles per (checkpoint, candidate) slot pair in the global record
+    double* ws;       // per-lane record in global memory
+    int nlp, slot_stride;
     int phase, dir, depth, D, L, nl, sub;
     uint32_t leaf, n_tot, n_leapfrog, free_mask;
     uint64_t pend_n, pend_ref;
     StreamReader rng;
 
 #define SMCB_LOCAL(i) for (int i = 0; i < (M::STATIC_NL ? M::STATIC_NL : nl); ++i)
+#define SMCB_PAIRS(i) for (int i = 0; i < (M::STATIC_NL ? M::STATIC_NL : nl); i += 2)
 
     SMCB_HD int gd(int i) const { return G == 1 ? i : sub + G * i; }   // global coordinate of local slot i
     SMCB_HD double gsum(double v) const {
@@ -106,20 +113,33 @@ struct Lane {
         return v;
     }
 
-    // ---- workspace views (per lane).  A view is (pointer, element stride): the low, hot slots live in shared memory
-    //      interleaved across the CTA's lanes (stride hs, conflict-free), everything else in the global record.
-    struct View { double* p; int st; SMCB_HD double& operator[](int i) const { return p[(size_t)i * st]; } };
-    // hot layout (elements): other x, other r (2 nl) | hc checkpoints (2 nl each) | hk candidates (2 nl + 2 each)
-    SMCB_HD View other_xr() const { return hot ? View{hot, hs} : View{ws, 1}; }          // x at [i], r at [nl + i]
-    SMCB_HD double* other_g() const { return ws + 2 * nl; }
-    SMCB_HD View ckpt(int slot) const {                                                    // x at [i], r at [nl + i]
-        return slot < hc ? View{hot + (size_t)(2 * nl + 2 * nl * slot) * hs, hs} : View{ws + 3 * nl + slot_stride * slot, 1};
+    // ---- vector <-> record, two doubles (16 bytes) per access
+    SMCB_HD void stv(double* p, const double (&v)[DM]) const {
+        const int n_ = (M::STATIC_NL ? M::STATIC_NL : nl);
+#pragma unroll
+        SMCB_PAIRS(i) {
+            D2 t;
+            t.x = v[i];
+            t.y = (i + 1 < n_) ? v[i + 1 < DM ? i + 1 : i] : 0.0;
+            *reinterpret_cast<D2*>(p + i) = t;
+        }
     }
-    SMCB_HD View cand(int slot) const {                                                    // x, r, A, B
-        return slot < hk ? View{hot + (size_t)(2 * nl + 2 * nl * hc + (2 * nl + 2) * slot) * hs, hs}
-                         : View{ws + 3 * nl + slot_stride * slot + 2 * nl, 1};   // x, r, A, B [, g]
+    SMCB_HD void ldv(const double* p, double (&v)[DM]) const {
+        const int n_ = (M::STATIC_NL ? M::STATIC_NL : nl);
+#pragma unroll
+        SMCB_PAIRS(i) {
+            const D2 t = *reinterpret_cast<const D2*>(p + i);
+            v[i] = t.x;
+            if (i + 1 < n_) v[i + 1 < DM ? i + 1 : i] = t.y;
+        }
     }
-    SMCB_HD static int hot_doubles(int nl_, int hc_, int hk_) { return 2 * nl_ + 2 * nl_ * hc_ + (2 * nl_ + 2) * hk_; }
+
+    // ---- record views
+    SMCB_HD double* other_x() const { return ws; }
+    SMCB_HD double* other_r() const { return ws + nlp; }
+    SMCB_HD double* other_g() const { return ws + 2 * nlp; }
+    SMCB_HD double* ckpt(int slot) const { return ws + 3 * nlp + slot_stride * slot; }             // x[nlp] r[nlp]
+    SMCB_HD double* cand(int slot) const { return ws + 3 * nlp + slot_stride * slot + 2 * nlp; }   // x r A B [g]
 
     // ---- packed per-level pending counts: level l occupies bits [l(l+1)/2, +l+1)
     SMCB_HD uint32_t get_n(int l) const { return (uint32_t)(pend_n >> (l * (l + 1) / 2)) & ((2u << l) - 1u); }
@@ -131,14 +151,13 @@ struct Lane {
     SMCB_HD int get_ref(int l) const { return (int)((pend_ref >> (4 * l)) & 15u); }
     SMCB_HD void set_ref(int l, int s) { pend_ref = (pend_ref & ~((uint64_t)15 << (4 * l))) | ((uint64_t)s << (4 * l)); }
 
-    SMCB_HD void idle_init(const M& m, int sub_, double* hot_ = nullptr, int hs_ = 0, int hc_ = 0, int hk_ = 0) {
-        phase = kIdle; sub = sub_; D = m.dim(); nl = m.nloc(); pid = -1;
-        hot = hot_; hs = hs_; hc = hot_ ? hc_ : 0; hk = hot_ ? hk_ : 0;
+    SMCB_HD void idle_init(const M& m, int sub_) {
+        phase = kIdle; sub = sub_; D = m.dim(); nl = m.nloc(); nlp = nuts_nlp(nl); pid = -1;
         SMCB_LOCAL(i) { xa[i] = 0.0; ra[i] = 0.0; ga[i] = 0.0; }
     }
 
     SMCB_HD void begin(const NutsArgs& a, const M& m, long long p, double* ws_) {
-        pid = p; ws = ws_; D = m.dim(); nl = m.nloc(); L = a.max_depth;
+        pid = p; ws = ws_; D = m.dim(); nl = m.nloc(); nlp = nuts_nlp(nl); L = a.max_depth;
         const int d_ = D;
 #pragma unroll
         SMCB_LOCAL(i) {
@@ -148,7 +167,7 @@ struct Lane {
         }
         rng.reset(a.seed, a.iteration, kStreamNuts, a.particle0 + (uint64_t)p);
         n_leapfrog = 0;
-        slot_stride = 4 * nl + 2 + (a.g_new ? nl : 0);
+        slot_stride = nuts_slot_stride(nl, a.g_new != nullptr);
         phase = kInit;
         if (a.g_in) {   // carried-over evaluation: initialise the tree right away, the first trip is already a leapfrog
 #pragma unroll
@@ -157,30 +176,9 @@ struct Lane {
         }
     }
 
-    SMCB_HD void prefetch_lines(const double* p, int ndoubles) const {
-#if defined(__CUDA_ARCH__)
-        for (int b = 0; b < ndoubles * 8; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p + b));
-#else
-        (void)p; (void)ndoubles;
-#endif
-    }
-
     // first half of the leapfrog (nuts.py:169-170); nothing to do before the initial evaluation
     SMCB_HD void pre_eval(const NutsArgs& a) {
         if (phase != kLeaf) return;
-        // the tree bookkeeping that follows this leaf reads U-turn checkpoints (and the other edge when the leaf
-        // closes a doubling): start those loads now so they land while the model evaluation runs
-        {
-            const uint32_t i0 = leaf;  // 0-based index of the leaf about to be built
-            if (i0 & 1u) {
-                const int tz = ctz32(i0 + 1u);
-                for (int l = 0; l < tz; ++l) {
-                    const int slot = popc32(i0 - (2u << l) + 1u);
-                    if (slot >= hc) prefetch_lines(ckpt(slot).p, 2 * nl);
-                }
-            }
-            if (!hot && i0 + 1u == (1u << depth)) prefetch_lines(ws, 2 * nl);
-        }
         const double half = dir * a.eps / 2, full = dir * a.eps;
 #pragma unroll
         SMCB_LOCAL(i) {
@@ -192,53 +190,53 @@ struct Lane {
     SMCB_HD void start_doubling(bool first) {
         const int nd = (rng.next() < 0.5) ? 1 : -1;  // nuts.py:91
         if (!first && nd != dir) {                   // bring the other edge into registers
-            const View o = other_xr();
-            double* og = other_g();
-            const int n_ = nl;
+            double tx[DM], tr[DM], tg[DM];
+            ldv(other_x(), tx); ldv(other_r(), tr); ldv(other_g(), tg);
+            stv(other_x(), xa); stv(other_r(), ra); stv(other_g(), ga);
 #pragma unroll
-            SMCB_LOCAL(i) {
-                double t;
-                t = o[i]; o[i] = xa[i]; xa[i] = t;
-                t = o[n_ + i]; o[n_ + i] = ra[i]; ra[i] = t;
-                t = og[i]; og[i] = ga[i]; ga[i] = t;
-            }
+            SMCB_LOCAL(i) { xa[i] = tx[i]; ra[i] = tr[i]; ga[i] = tg[i]; }
         }
         dir = nd;
         leaf = 0; pend_n = 0; pend_ref = 0;
         free_mask = (2u << L) - 1u;
     }
 
-    // U-turn test between a stored edge (xc, rc) and the active edge (nuts.py:152-160); the edge order
+    // U-turn test between a stored edge (x at c, r at c + nlp) and the active edge (nuts.py:152-160); the edge order
     // (minus, plus) is restored through `dir`.
-    SMCB_HD bool uturn(const View& c) const {      // c: x at [i], r at [nl + i]
+    SMCB_HD bool uturn(const double* c) const {
+        double xc[DM], rc[DM];
+        ldv(c, xc); ldv(c + nlp, rc);
         double s1 = 0.0, s2 = 0.0;
-        const int n_ = nl;
 #pragma unroll
         SMCB_LOCAL(i) {
-            const double dx = xa[i] - c[i];
-            s1 += dx * c[n_ + i];
+            const double dx = xa[i] - xc[i];
+            s1 += dx * rc[i];
             s2 += dx * ra[i];
         }
         s1 = gsum(s1); s2 = gsum(s2);
         return (dir * s1 < 0) || (dir * s2 < 0);
     }
 
-    SMCB_HD void write_sample_from_active(const NutsArgs& a, double A, double B) {
+    // rows of the caller's [N, D] arrays: 16-byte accesses when the row layout allows it
+    SMCB_HD void write_row(double* base, const double (&v)[DM]) const {
         const int d_ = D;
+        if (G == 1 && (d_ & 1) == 0) {
+            stv(base + pid * d_, v);   // rows of an even number of doubles are 16-byte aligned (torch allocations are)
+        } else {
 #pragma unroll
-        SMCB_LOCAL(i) {
-            if (gd(i) < d_) {
-                a.x_new[pid * d_ + gd(i)] = xa[i];
-                a.r_new[pid * d_ + gd(i)] = ra[i];
-                if (a.g_new) a.g_new[pid * d_ + gd(i)] = ga[i];
-            }
+            SMCB_LOCAL(i) if (gd(i) < d_) base[pid * d_ + gd(i)] = v[i];
         }
+    }
+
+    SMCB_HD void write_sample_from_active(const NutsArgs& a, double A, double B) {
+        write_row(a.x_new, xa);
+        write_row(a.r_new, ra);
+        if (a.g_new) write_row(a.g_new, ga);
         As = A; Bs = B;
     }
 
     // nuts.py:66-87 given logp = A + phi*B and its gradient (already in `ga`) at the start point
     SMCB_HD void init_tree(const NutsArgs& a, double A, double B) {
-        const int n_ = nl;
         double lp = A + a.phi * B;
         if (!is_finite(lp)) lp = neg_inf();
         double rr = 0.0;
@@ -249,10 +247,7 @@ struct Lane {
         const double H0 = lp - ke0;
         logu = H0 - (-log1p(-rng.next()));
         write_sample_from_active(a, A, B);
-        const View o = other_xr();
-        double* og = other_g();
-#pragma unroll
-        SMCB_LOCAL(i) { o[i] = xa[i]; o[n_ + i] = ra[i]; og[i] = ga[i]; }
+        stv(other_x(), xa); stv(other_r(), ra); stv(other_g(), ga);
         n_tot = 1; depth = 0;
         start_doubling(true);
         phase = kLeaf;
@@ -267,7 +262,7 @@ struct Lane {
 
     // Consume the model evaluation at xa (gradient already in `ga`).  Returns true when the transition is complete.
     SMCB_HD bool post_eval(const NutsArgs& a, double A, double B) {
-        const int d_ = D, n_ = nl;
+        const int d_ = D;
         double lp = A + a.phi * B;
         const bool bad = !is_finite(lp);  // bridgestan.py:47-49,79-80: failure -> logp = -inf, grad = -inf
         if (bad) {
@@ -275,7 +270,6 @@ struct Lane {
 #pragma unroll
             SMCB_LOCAL(i) if (gd(i) < d_) ga[i] = neg_inf();
         }
-
         if (phase == kInit) {
             init_tree(a, A, B);
             return false;
@@ -300,9 +294,8 @@ struct Lane {
         if (nleaves > 1u) {
             const uint32_t i0 = leaf - 1u;
             if ((i0 & 1u) == 0u) {
-                const View c = ckpt(popc32(i0));
-#pragma unroll
-                SMCB_LOCAL(i) { c[i] = xa[i]; c[n_ + i] = ra[i]; }
+                double* c = ckpt(popc32(i0));
+                stv(c, xa); stv(c + nlp, ra);
             } else {
                 const int tz = ctz32(leaf);
                 for (int l = 0; l < tz; ++l) {  // nuts.py:136-148, second child = running node
@@ -328,20 +321,17 @@ struct Lane {
                 if (run_ref < 0) {
                     write_sample_from_active(a, A, B);
                 } else {
-                    const View c = cand(run_ref);
-#pragma unroll
-                    SMCB_LOCAL(i) {
-                        if (gd(i) < d_) {
-                            a.x_new[pid * d_ + gd(i)] = c[i];
-                            a.r_new[pid * d_ + gd(i)] = c[n_ + i];
-                            if (a.g_new) a.g_new[pid * d_ + gd(i)] = c[2 * n_ + 2 + i];
-                        }
-                    }
-                    As = c[2 * n_]; Bs = c[2 * n_ + 1];
+                    const double* c = cand(run_ref);
+                    double t[DM];
+                    ldv(c, t); write_row(a.x_new, t);
+                    ldv(c + nlp, t); write_row(a.r_new, t);
+                    const D2 ab = *reinterpret_cast<const D2*>(c + 2 * nlp);
+                    As = ab.x; Bs = ab.y;
+                    if (a.g_new) { ldv(c + 2 * nlp + 2, t); write_row(a.g_new, t); }
                 }
             }
             n_tot += run_n;
-            const bool stop = uturn(other_xr());
+            const bool stop = uturn(other_x());
             ++depth;
             if (stop || depth > L) return finish(a);
             start_doubling(false);
@@ -352,14 +342,11 @@ struct Lane {
         if (run_ref < 0) {
             run_ref = ctz32(free_mask);
             free_mask &= ~(1u << run_ref);
-            const View c = cand(run_ref);
-#pragma unroll
-            SMCB_LOCAL(i) { c[i] = xa[i]; c[n_ + i] = ra[i]; }
-            c[2 * n_] = A; c[2 * n_ + 1] = B;
-            if (a.g_new) {
-#pragma unroll
-                SMCB_LOCAL(i) c[2 * n_ + 2 + i] = ga[i];
-            }
+            double* c = cand(run_ref);
+            stv(c, xa); stv(c + nlp, ra);
+            D2 ab; ab.x = A; ab.y = B;
+            *reinterpret_cast<D2*>(c + 2 * nlp) = ab;
+            if (a.g_new) stv(c + 2 * nlp + 2, ga);
         }
         set_n(lv, run_n);
         set_ref(lv, run_ref);
@@ -415,6 +402,7 @@ struct Lane {
         return true;
     }
 #undef SMCB_LOCAL
+#undef SMCB_PAIRS
 };
 
 }  // namespace smcb

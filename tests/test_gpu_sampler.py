@@ -137,3 +137,26 @@ def test_estimates_agree_with_reference_within_mc_error_over_repeated_runs(tmp_p
         assert close.mean() >= 0.5, close.mean()
         # and both sit at the gold-standard posterior means within the run-to-run spread
         assert np.all(np.abs(dev_final.mean(axis=0) - truth) < 5 * dev_final.std(axis=0, ddof=1) / np.sqrt(R) + 0.02)
+
+
+def test_gradient_carry_over_gives_the_same_run():
+    """Opt-in carry of (A, B, grad) between iterations (skips the initial evaluation of every transition): identical
+    leapfrog counts and estimates."""
+    m = make_model("arma")
+    runs = []
+    for carry in (False, True):
+        s = SMCSampler(K=6, N=4096, target=m, step_size=0.01, sample_proposal=StdNormal(4), momentum_proposal=StdNormal(4),
+                       lkernel="forwardsLKernel", tempering=False, rng=10)
+        s.samples.carry_gradients = carry
+        s.sample(show_progress=False)
+        runs.append(s)
+    assert np.array_equal(runs[0].leapfrogs, runs[1].leapfrogs)
+    np.testing.assert_allclose(runs[0].mean_estimate, runs[1].mean_estimate, rtol=1e-12)
+    np.testing.assert_allclose(runs[0].ess, runs[1].ess, rtol=1e-12)
+
+
+def test_every_kernel_family_small_runs():
+    """tools/sanitize_smoke.py: tiny runs through all model / L-kernel / resampling combinations, incl. D = 110 (plain
+    Gaussian path) -- the exercise meant for compute-sanitizer (closed on this pool) doubles as a smoke test."""
+    import runpy
+    runpy.run_path(str(__import__("pathlib").Path(__file__).resolve().parents[1] / "tools" / "sanitize_smoke.py"), run_name="__main__")

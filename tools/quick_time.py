@@ -40,17 +40,20 @@ def probe():
     return fl / t
 
 
-def nuts(name, N, eps, flop_per_eval, spread, centre, iters=3):
+def nuts(name, N, eps, flop_per_eval, spread, centre, iters=3, carry_mode=False):
     m = make_model(name) if name != "gauss" else make_model("gauss", dim=100)
     D = m.dim
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     x = torch.randn(N, D, dtype=torch.float64, device="cuda", generator=g) * spread + torch.tensor(centre, dtype=torch.float64, device="cuda")
     k = NUTSProposal(m, StdNormal(D), eps, rng=10)
+    carry = None
     for it in range(iters):
         r = StdNormal(D, seed=10).rvs(N, iteration=it)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); o = k.transition(x, r, 1.0, iteration=it); b.record(); torch.cuda.synchronize()
+        a.record(); o = k.transition(x, r, 1.0, iteration=it, carry=carry, want_grad=carry_mode); b.record(); torch.cuda.synchronize()
+        if carry_mode:
+            carry = (o["A_new"], o["B_new"], o["g_new"])
         t = a.elapsed_time(b) * 1e-3
         nl = int(o["n_leapfrog"].sum().item())
         mx = int(o["n_leapfrog"].max().item())
@@ -75,6 +78,8 @@ if __name__ == "__main__":
                 t, _ = ev_time(lambda: _cabi.call("smcb_logp_grad", m.handle, dev.ptr(x), N, 1.0, dev.ptr(A), dev.ptr(B), dev.ptr(g),
                                                   dev.stream_ptr()))
                 print(f"logp_grad {name} N={N}: {t * 1e6:.1f} us -> {N * flop / t / 1e12:.2f} TFLOP/s")
+    if which == "armacarry":
+        nuts("arma", 1 << 20, 0.01, 3900, 0.02, [0.0068, 0.957, -0.034, float(np.log(0.1666))], iters=5, carry_mode=True)
     if which == "armaN":
         for lg in (18, 19, 20, 21, 22, 23):
             nuts("arma", 1 << lg, 0.01, 3900, 0.02, [0.0068, 0.957, -0.034, float(np.log(0.1666))], iters=3)
