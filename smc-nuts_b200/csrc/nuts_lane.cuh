@@ -70,13 +70,15 @@ struct alignas(16) D2 {
 
 // Workspace record of one LANE (global memory, 128-byte aligned; nlp = nl rounded up to even so that every vector is
 // 16-byte aligned):
-//   other edge: x[nlp] r[nlp] g[nlp] | slot 0: checkpoint x[nlp] r[nlp], candidate x[nlp] r[nlp] A B [g[nlp]] | slot 1 ...
-// Checkpoint s and candidate s are neighbours so that the hot low slots share cache lines (the L1 serves this
-// traffic); candidates carry their gradient only when the caller asked for g_new.
+//   other edge: x[nlp] r[nlp] g[nlp] | 2L+2 leaf slots, each x[nlp] r[nlp] A B [g[nlp]]
+// A leaf state is stored at most ONCE: the first leaf of a sub-tree (U-turn checkpoint) and a pending candidate are
+// the same record when they are the same leaf (every odd leaf of a doubling is both); checkpoints and candidates
+// are slot references handed out from one free mask.  Candidates carry their gradient only when the caller asked
+// for g_new.
 SMCB_HD int nuts_nlp(int nl) { return (nl + 1) & ~1; }
-SMCB_HD int nuts_slot_stride(int nl, bool carry) { return 4 * nuts_nlp(nl) + 2 + (carry ? nuts_nlp(nl) : 0); }
+SMCB_HD int nuts_slot_stride(int nl, bool carry) { return 2 * nuts_nlp(nl) + 2 + (carry ? nuts_nlp(nl) : 0); }
 SMCB_HD int nuts_ws_doubles(int nl, int L, bool carry = true) {
-    return ((3 * nuts_nlp(nl) + nuts_slot_stride(nl, carry) * (L + 1)) + 15) & ~15;
+    return ((3 * nuts_nlp(nl) + nuts_slot_stride(nl, carry) * (2 * L + 2)) + 15) & ~15;
 }
 
 enum LanePhase : int { kIdle = 0, kInit = 1, kLeaf = 2 };
@@ -89,13 +91,14 @@ struct Lane {
     static constexpr int G = M::GROUP;
     static constexpr int DM = M::NLOC;
     double xa[DM], ra[DM], ga[DM];  // active edge (this lane's coordinates)
-    double logu, A0, B0, As, Bs, ke0;
+    double logu, A0, B0, As, Bs, ke0, kes;
     long long pid;
     double* ws;       // per-lane record in global memory
     int nlp, slot_stride;
     int phase, dir, depth, D, L, nl, sub;
-    uint32_t leaf, n_tot, n_leapfrog, free_mask;
-    uint64_t pend_n, pend_ref;
+    uint32_t leaf, n_tot, n_leapfrog;
+    uint32_t ck_used, cand_used, ck_valid;   // slots referenced by live checkpoints / candidates; valid checkpoint ids
+    uint64_t pend_n, pend_ref, ck_ref;       // packed per-level counts, candidate slot refs, checkpoint slot refs (5 bits)
     StreamReader rng;
 
 #define SMCB_LOCAL(i) for (int i = 0; i < (M::STATIC_NL ? M::STATIC_NL : nl); ++i)
@@ -138,8 +141,21 @@ struct Lane {
     SMCB_HD double* other_x() const { return ws; }
     SMCB_HD double* other_r() const { return ws + nlp; }
     SMCB_HD double* other_g() const { return ws + 2 * nlp; }
-    SMCB_HD double* ckpt(int slot) const { return ws + 3 * nlp + slot_stride * slot; }             // x[nlp] r[nlp]
-    SMCB_HD double* cand(int slot) const { return ws + 3 * nlp + slot_stride * slot + 2 * nlp; }   // x r A B [g]
+    SMCB_HD double* slotp(int slot) const { return ws + 3 * nlp + slot_stride * slot; }   // x[nlp] r[nlp] A B [g[nlp]]
+    SMCB_HD int alloc_slot() {
+        const uint32_t free_ = ~(ck_used | cand_used);
+        return ctz32(free_);   // 2L+2 <= 22 slots, at most L checkpoints + L+1 candidates are live
+    }
+    // store the leaf in registers (active edge) into a fresh slot
+    SMCB_HD int store_leaf(const NutsArgs& a, double A, double B) {
+        const int sl = alloc_slot();
+        double* c = slotp(sl);
+        stv(c, xa); stv(c + nlp, ra);
+        D2 ab; ab.x = A; ab.y = B;
+        *reinterpret_cast<D2*>(c + 2 * nlp) = ab;
+        if (a.g_new) stv(c + 2 * nlp + 2, ga);
+        return sl;
+    }
 
     // ---- packed per-level pending counts: level l occupies bits [l(l+1)/2, +l+1)
     SMCB_HD uint32_t get_n(int l) const { return (uint32_t)(pend_n >> (l * (l + 1) / 2)) & ((2u << l) - 1u); }
@@ -148,8 +164,15 @@ struct Lane {
         const uint64_t mask = (uint64_t)((2u << l) - 1u) << sh;
         pend_n = (pend_n & ~mask) | ((uint64_t)v << sh);
     }
-    SMCB_HD int get_ref(int l) const { return (int)((pend_ref >> (4 * l)) & 15u); }
-    SMCB_HD void set_ref(int l, int s) { pend_ref = (pend_ref & ~((uint64_t)15 << (4 * l))) | ((uint64_t)s << (4 * l)); }
+    SMCB_HD int get_ref(int l) const { return (int)((pend_ref >> (5 * l)) & 31u); }
+    SMCB_HD void set_ref(int l, int s) { pend_ref = (pend_ref & ~((uint64_t)31 << (5 * l))) | ((uint64_t)s << (5 * l)); }
+    SMCB_HD int get_ck(int p) const { return (int)((ck_ref >> (5 * p)) & 31u); }
+    SMCB_HD void set_ck(int p, int s) {
+        if (ck_valid & (1u << p)) ck_used &= ~(1u << get_ck(p));   // the checkpoint it replaces is dead by construction
+        ck_ref = (ck_ref & ~((uint64_t)31 << (5 * p))) | ((uint64_t)s << (5 * p));
+        ck_valid |= 1u << p;
+        ck_used |= 1u << s;
+    }
 
     SMCB_HD void idle_init(const M& m, int sub_) {
         phase = kIdle; sub = sub_; D = m.dim(); nl = m.nloc(); nlp = nuts_nlp(nl); pid = -1;
@@ -197,8 +220,8 @@ struct Lane {
             SMCB_LOCAL(i) { xa[i] = tx[i]; ra[i] = tr[i]; ga[i] = tg[i]; }
         }
         dir = nd;
-        leaf = 0; pend_n = 0; pend_ref = 0;
-        free_mask = (2u << L) - 1u;
+        leaf = 0; pend_n = 0; pend_ref = 0; ck_ref = 0;
+        ck_used = cand_used = ck_valid = 0;
     }
 
     // U-turn test between a stored edge (x at c, r at c + nlp) and the active edge (nuts.py:152-160); the edge order
@@ -228,11 +251,11 @@ struct Lane {
         }
     }
 
-    SMCB_HD void write_sample_from_active(const NutsArgs& a, double A, double B) {
+    SMCB_HD void write_sample_from_active(const NutsArgs& a, double A, double B, double ke) {
         write_row(a.x_new, xa);
         write_row(a.r_new, ra);
         if (a.g_new) write_row(a.g_new, ga);
-        As = A; Bs = B;
+        As = A; Bs = B; kes = ke;
     }
 
     // nuts.py:66-87 given logp = A + phi*B and its gradient (already in `ga`) at the start point
@@ -246,7 +269,7 @@ struct Lane {
         A0 = A; B0 = B;
         const double H0 = lp - ke0;
         logu = H0 - (-log1p(-rng.next()));
-        write_sample_from_active(a, A, B);
+        write_sample_from_active(a, A, B, ke0);
         stv(other_x(), xa); stv(other_r(), ra); stv(other_g(), ga);
         n_tot = 1; depth = 0;
         start_doubling(true);
@@ -294,8 +317,10 @@ struct Lane {
         if (nleaves > 1u) {
             const uint32_t i0 = leaf - 1u;
             if ((i0 & 1u) == 0u) {
-                double* c = ckpt(popc32(i0));
-                stv(c, xa); stv(c + nlp, ra);
+                // first leaf of (at least) a two-leaf sub-tree: one record serves as its U-turn checkpoint and as
+                // the pending level-0 candidate
+                run_ref = store_leaf(a, A, B);
+                set_ck(popc32(i0), run_ref);
             } else {
                 const int tz = ctz32(leaf);
                 for (int l = 0; l < tz; ++l) {  // nuts.py:136-148, second child = running node
@@ -305,13 +330,13 @@ struct Lane {
                     const double u = rng.next();
                     const double denom = (double)tot > 1. ? (double)tot : 1.;
                     if (u < ((double)run_n / denom)) {
-                        free_mask |= 1u << ref1;
+                        cand_used &= ~(1u << ref1);
                     } else {
-                        if (run_ref >= 0) free_mask |= 1u << run_ref;
+                        if (run_ref >= 0) cand_used &= ~(1u << run_ref);
                         run_ref = ref1;
                     }
                     run_n = tot;
-                    if (uturn(ckpt(popc32(i0 - (2u << l) + 1u)))) { ++depth; return finish(a); }
+                    if (uturn(slotp(get_ck(popc32(i0 - (2u << l) + 1u))))) { ++depth; return finish(a); }
                 }
             }
         }
@@ -319,12 +344,16 @@ struct Lane {
             const double ratio = (double)run_n / (double)n_tot;
             if (rng.next() < (ratio < 1. ? ratio : 1.)) {
                 if (run_ref < 0) {
-                    write_sample_from_active(a, A, B);
+                    write_sample_from_active(a, A, B, 0.5 * rr);
                 } else {
-                    const double* c = cand(run_ref);
+                    const double* c = slotp(run_ref);
                     double t[DM];
                     ldv(c, t); write_row(a.x_new, t);
                     ldv(c + nlp, t); write_row(a.r_new, t);
+                    double k2 = 0.0;
+#pragma unroll
+                    SMCB_LOCAL(i) k2 += t[i] * t[i];
+                    kes = 0.5 * gsum(k2);
                     const D2 ab = *reinterpret_cast<const D2*>(c + 2 * nlp);
                     As = ab.x; Bs = ab.y;
                     if (a.g_new) { ldv(c + 2 * nlp + 2, t); write_row(a.g_new, t); }
@@ -339,15 +368,8 @@ struct Lane {
         }
         // park the running node as the pending first child of level ctz(leaf)
         const int lv = ctz32(leaf);
-        if (run_ref < 0) {
-            run_ref = ctz32(free_mask);
-            free_mask &= ~(1u << run_ref);
-            double* c = cand(run_ref);
-            stv(c, xa); stv(c + nlp, ra);
-            D2 ab; ab.x = A; ab.y = B;
-            *reinterpret_cast<D2*>(c + 2 * nlp) = ab;
-            if (a.g_new) stv(c + 2 * nlp + 2, ga);
-        }
+        if (run_ref < 0) run_ref = store_leaf(a, A, B);
+        cand_used |= 1u << run_ref;
         set_n(lv, run_n);
         set_ref(lv, run_ref);
         return false;
@@ -356,17 +378,17 @@ struct Lane {
     // End of transition: optional endpoint MH step (nuts_acc_rej.py:42-49, utils.py:22-34) and outputs.
     SMCB_HD bool finish(const NutsArgs& a) {
         const int d_ = D;
-        double rr = 0.0;
+        double ken = kes;
         int anyinf = 0;
-        SMCB_LOCAL(i) {
-            if (gd(i) < d_) {
-                const double rv = a.r_new[pid * d_ + gd(i)], xv = a.x_new[pid * d_ + gd(i)];
-                rr += rv * rv;
-                anyinf |= (xv == -neg_inf()) || (xv == neg_inf());
+        if (a.accrej) {   // np.any(np.isinf(x_prime)), utils.py:32
+            SMCB_LOCAL(i) {
+                if (gd(i) < d_) {
+                    const double xv = a.x_new[pid * d_ + gd(i)];
+                    anyinf |= (xv == -neg_inf()) || (xv == neg_inf());
+                }
             }
+            if (G > 1) anyinf = gsum((double)anyinf) > 0.0;
         }
-        double ken = 0.5 * gsum(rr);
-        if (G > 1) anyinf = gsum((double)anyinf) > 0.0;
         int acc = 1;
         if (a.accrej) {
             double lps = As + a.phi * Bs, lp0 = A0 + a.phi * B0;
