@@ -372,7 +372,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "kernel": "nuts_transition_kernel", "achieved": achieved / 1e12, "peak": peak / 1e12,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 486389760 if (args.workload == "arma" and log2n == 20) else None,
+                         "traffic": 368687872 if (args.workload == "arma" and log2n == 20) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture "
                                            "profiles/r1_nuts_arma_final_details.csv (algorithmic: 184 MB of particle rows and "
                                            "scalars; the rest is the per-lane tree workspace leaving L2)",
