@@ -38,15 +38,15 @@ static int blocks_per_sm_cap() {
     return v > 0 ? v : 1 << 20;
 }
 
-// NT threads per CTA, MIN_BLOCKS resident CTAs/SM (register budget), HC / HK = U-turn checkpoint / candidate slots of
-// the per-lane tree workspace that live in shared memory.  MEASURED (round 1, profiles/README.md): keeping the low
-// slots in shared memory (arma HC=3, HK=1: 44 KB/CTA) made the kernel 37 % SLOWER -- the carve-out leaves almost no L1,
-// and the L1 was already serving the workspace and particle-row traffic (long_scoreboard 1.2 -> 5.7 per issue).  The
-// hot path is therefore disabled; the global per-lane records stay L1/L2 resident.
-template <class M> struct LaunchCfg { static constexpr int NT = 256, MIN_BLOCKS = 1, HC = 0, HK = 0; static constexpr bool HOT = false; };   // GaussModelG: one CTA/SM, one copy of the B fragments, more L1
-template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4, HC = 3, HK = 1; static constexpr bool HOT = false; };
-template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2, HC = 2, HK = 0; static constexpr bool HOT = false; };
-template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1, HC = 0, HK = 0; static constexpr bool HOT = false; };
+// NT threads per CTA, MIN_BLOCKS resident CTAs/SM (register budget).
+// MEASURED (round 1, profiles/README.md): more resident warps do not help arma (94 registers / 5 CTAs: same time,
+// 64 registers / 8 CTAs: 12 % slower), and keeping the low slots of the per-lane tree workspace in shared memory made
+// the kernel 37 % SLOWER -- the carve-out leaves almost no L1, and the L1 already serves the workspace and
+// particle-row traffic.  The per-lane records therefore stay in global memory (L1/L2 resident).
+template <class M> struct LaunchCfg { static constexpr int NT = 256, MIN_BLOCKS = 1; };   // GaussModelG: one CTA/SM, one copy of the B fragments
+template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
+template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2; };
+template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1; };
 
 template <class M>
 static size_t nuts_smem_bytes(const ModelDesc& d) {
