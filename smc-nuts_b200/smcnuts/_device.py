@@ -71,6 +71,34 @@ def to_host_like(t, ref, tag="out"):
     return host.numpy().copy()
 
 
+def host_view(a, n, d):
+    """Host array / CPU tensor -> ([n, d] float64 CPU tensor sharing its memory when possible, is_pinned)."""
+    if isinstance(a, torch.Tensor):
+        t = a.to(dtype=F64).contiguous().reshape(n, d)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).reshape(n, d)
+    return t, t.is_pinned()
+
+
+def host_result(pinned, ref):
+    """Pinned staging buffer holding a result -> the container type of the host input `ref` (see to_host_like)."""
+    if isinstance(ref, torch.Tensor):
+        return pinned if ref.is_pinned() else pinned.clone()
+    return pinned.numpy().copy()
+
+
+_STREAMS = {}
+
+
+def side_streams(n):
+    """Reusable non-default streams of the current device (copy/compute pipelining)."""
+    key = torch.cuda.current_device()
+    pool = _STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream())
+    return pool[:n]
+
+
 def empty(*shape, dtype=F64):
     return torch.empty(*shape, dtype=dtype, device=device())
 

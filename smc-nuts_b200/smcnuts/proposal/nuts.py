@@ -33,13 +33,100 @@ class NUTSProposal:
         self.record_events = False  # bench.py: CUDA events tightly around the kernel launch
         self.events = []
 
+    # Host inputs of at least this many particles go through the pipelined path (copy/compute overlap)
+    PIPELINE_MIN_PARTICLES = 1 << 16
+    # Chunk sizes as fractions of N: small first and last chunks keep the exposed head (first H2D) and tail (last
+    # D2H) short, few large chunks in between keep the per-launch tail cost low (measured: tools/e2e_time.py)
+    PIPELINE_FRACTIONS = (1, 3, 3, 1)
+    PIPELINE_STREAMS = 3
+
     def rvs(self, x_cond, r_cond, phi: float = 1.0):
-        """Propagate particles through one NUTS transition each.  numpy in -> numpy out; CUDA tensors stay put."""
-        x = dev.to_device(x_cond).reshape(-1, self.target.dim)
-        r = dev.to_device(r_cond).reshape(-1, self.target.dim)
+        """Propagate particles through one NUTS transition each.  numpy in -> numpy out; CUDA tensors stay put.
+
+        Host inputs (numpy arrays or CPU tensors, the reference's calling convention) are processed in chunks on
+        side streams: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernel of chunk c (PCIe is
+        full duplex), and the next chunk's CTAs fill the SMs vacated while the previous chunk's last trees finish.
+        Philox streams are keyed by the global particle index, so the result does not depend on the chunking."""
+        D = self.target.dim
+        host_in = dev.is_host(x_cond) or not x_cond.is_cuda
+        n = (x_cond.size if dev.is_host(x_cond) else x_cond.numel()) // D if host_in else 0
+        if host_in and n >= self.PIPELINE_MIN_PARTICLES and (dev.is_host(r_cond) or not r_cond.is_cuda):
+            out = self._rvs_pipelined(x_cond, r_cond, float(phi), n)
+            self.iteration += 1
+            return out
+        x = dev.to_device(x_cond).reshape(-1, D)
+        r = dev.to_device(r_cond).reshape(-1, D)
         out = self.transition(x, r, phi)
         self.iteration += 1
         return dev.to_host_like(out["x_new"], x_cond, "x_new"), dev.to_host_like(out["r_new"], r_cond, "r_new")
+
+    def _rvs_pipelined(self, x_cond, r_cond, phi, N):
+        D = self.target.dim
+        xh, x_pinned = dev.host_view(x_cond, N, D)
+        rh, r_pinned = dev.host_view(r_cond, N, D)
+        if not x_pinned:
+            x_stage = dev.pinned_buffer("x_in", (N, D), torch.float64)
+        if not r_pinned:
+            r_stage = dev.pinned_buffer("r_in", (N, D), torch.float64)
+        xo_h = dev.pinned_buffer("x_new", (N, D), torch.float64)
+        ro_h = dev.pinned_buffer("r_new", (N, D), torch.float64)
+        x, r = dev.empty(N, D), dev.empty(N, D)
+        o = self._alloc_outputs(N, D, False)
+        fr = self.PIPELINE_FRACTIONS
+        bounds = [0]
+        for c in range(len(fr)):
+            bounds.append(N if c + 1 == len(fr) else max(bounds[-1], (sum(fr[:c + 1]) * N) // sum(fr)))
+        nchunk = len(fr)
+        nstream = min(self.PIPELINE_STREAMS, nchunk)
+        streams = dev.side_streams(nstream)
+        nbytes = _cabi._ll()
+        _cabi.call("smcb_nuts_workspace_bytes", self.target.handle, max(b - a for a, b in zip(bounds, bounds[1:])),
+                   self.max_tree_depth, nbytes)
+        wss = [dev.workspace(f"nuts_pipe{i}", nbytes.value) for i in range(nstream)]
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        for c in range(nchunk):
+            lo, hi = bounds[c], bounds[c + 1]
+            if hi == lo:
+                continue
+            s = streams[c % nstream]
+            if c < nstream:
+                s.wait_event(ready)
+            if not x_pinned:
+                x_stage[lo:hi].copy_(xh[lo:hi])      # pageable -> pinned on the host thread, overlaps earlier chunks
+            if not r_pinned:
+                r_stage[lo:hi].copy_(rh[lo:hi])
+            with torch.cuda.stream(s):
+                x[lo:hi].copy_((xh if x_pinned else x_stage)[lo:hi], non_blocking=True)
+                r[lo:hi].copy_((rh if r_pinned else r_stage)[lo:hi], non_blocking=True)
+                self._launch(x, r, o, lo, hi, phi, self.iteration, None, wss[c % nstream], s.cuda_stream)
+                xo_h[lo:hi].copy_(o["x_new"][lo:hi], non_blocking=True)
+                ro_h[lo:hi].copy_(o["r_new"][lo:hi], non_blocking=True)
+        for s in streams:
+            cur.wait_stream(s)
+        cur.synchronize()
+        self.last = o
+        return dev.host_result(xo_h, x_cond), dev.host_result(ro_h, r_cond)
+
+    def _alloc_outputs(self, N, D, want_grad):
+        o = dict(x_new=dev.empty(N, D), r_new=dev.empty(N, D), A_old=dev.empty(N), B_old=dev.empty(N),
+                 A_new=dev.empty(N), B_new=dev.empty(N), ke_old=dev.empty(N), ke_new=dev.empty(N),
+                 n_leapfrog=dev.empty(N, dtype=torch.int32), accepted=dev.empty(N, dtype=torch.int32),
+                 depth=dev.empty(N, dtype=torch.int32))
+        if want_grad:
+            o["g_new"] = dev.empty(N, D)
+        return o
+
+    def _launch(self, x, r, o, lo, hi, phi, it, carry, ws, stream):
+        """One kernel launch over particles [lo, hi) of the given arrays (row slices are contiguous)."""
+        cA, cB, cg = carry if carry is not None else (None, None, None)
+        sl = lambda t: dev.ptr(None if t is None else t[lo:hi])   # noqa: E731
+        _cabi.call("smcb_nuts_transition", self.target.handle, sl(x), sl(r), hi - lo, self.step_size, float(phi),
+                   self.max_tree_depth, int(self.accept_reject), self.seed, it, self.particle0 + lo,
+                   sl(o["x_new"]), sl(o["r_new"]), sl(o["A_old"]), sl(o["B_old"]), sl(o["A_new"]), sl(o["B_new"]),
+                   sl(o["ke_old"]), sl(o["ke_new"]), sl(o["n_leapfrog"]), sl(o["accepted"]), sl(o["depth"]),
+                   sl(cA), sl(cB), sl(cg), sl(o.get("g_new")), dev.ptr(ws), ws.numel(), stream)
 
     def transition(self, x, r, phi=1.0, iteration=None, carry=None, want_grad=False):
         """Device entry point: returns dict of device tensors (x_new, r_new, A_old, B_old, A_new, B_new,
@@ -49,28 +136,16 @@ class NUTSProposal:
         model evaluation of every transition; want_grad=True also returns g_new for the next call."""
         N, D = x.shape
         it = self.iteration if iteration is None else iteration
-        h = self.target.handle
         nbytes = _cabi._ll()
-        _cabi.call("smcb_nuts_workspace_bytes", h, N, self.max_tree_depth, nbytes)
+        _cabi.call("smcb_nuts_workspace_bytes", self.target.handle, N, self.max_tree_depth, nbytes)
         ws = dev.workspace("nuts", nbytes.value)
-        o = dict(x_new=dev.empty(N, D), r_new=dev.empty(N, D), A_old=dev.empty(N), B_old=dev.empty(N),
-                 A_new=dev.empty(N), B_new=dev.empty(N), ke_old=dev.empty(N), ke_new=dev.empty(N),
-                 n_leapfrog=dev.empty(N, dtype=torch.int32), accepted=dev.empty(N, dtype=torch.int32),
-                 depth=dev.empty(N, dtype=torch.int32))
         if self.accept_reject:
             carry, want_grad = None, False
-        if want_grad:
-            o["g_new"] = dev.empty(N, D)
-        cA, cB, cg = carry if carry is not None else (None, None, None)
+        o = self._alloc_outputs(N, D, want_grad)
         if self.record_events:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _cabi.call("smcb_nuts_transition", h, dev.ptr(x), dev.ptr(r), N, self.step_size, float(phi),
-                   self.max_tree_depth, int(self.accept_reject), self.seed, it, self.particle0,
-                   dev.ptr(o["x_new"]), dev.ptr(o["r_new"]), dev.ptr(o["A_old"]), dev.ptr(o["B_old"]),
-                   dev.ptr(o["A_new"]), dev.ptr(o["B_new"]), dev.ptr(o["ke_old"]), dev.ptr(o["ke_new"]),
-                   dev.ptr(o["n_leapfrog"]), dev.ptr(o["accepted"]), dev.ptr(o["depth"]), dev.ptr(cA), dev.ptr(cB),
-                   dev.ptr(cg), dev.ptr(o.get("g_new")), dev.ptr(ws), ws.numel(), dev.stream_ptr())
+        self._launch(x, r, o, 0, N, phi, it, carry, ws, dev.stream_ptr())
         if self.record_events:
             e1.record()
             self.events.append((e0, e1))

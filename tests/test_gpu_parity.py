@@ -166,6 +166,36 @@ def test_nuts_batch_matches_oracle(name, eps, N):
         assert abs(int(o["n_leapfrog"].sum()) - int(ref["n_leapfrog"].sum())) <= 0.01 * ref["n_leapfrog"].sum()
 
 
+@pytest.mark.parametrize("cls_name,phi", [("NUTSProposal", 1.0), ("NUTSProposalWithAccRej", 0.4)])
+def test_rvs_host_pipeline_is_bit_identical_to_one_launch(cls_name, phi):
+    """rvs() with host arrays runs in chunks on side streams (copy/compute overlap); Philox streams are keyed by the
+    global particle index, so the chunked result must equal the single-launch one bit for bit."""
+    m, _ = _models("arma")
+    cls = {"NUTSProposal": NUTSProposal, "NUTSProposalWithAccRej": NUTSProposalWithAccRej}[cls_name]
+    N = (1 << 17) + 1234                                   # ragged chunks
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(N, 4)) * 0.05 + np.array([0.0, 0.9, 0.0, -1.7])
+    r = rng.normal(size=(N, 4))
+    k1 = cls(m, StdNormal(4), 0.01, rng=7)
+    k1.particle0 = 99
+    one = k1.transition(dev.to_device(x), dev.to_device(r), phi, iteration=0)
+    k2 = cls(m, StdNormal(4), 0.01, rng=7)
+    k2.particle0 = 99
+    assert N >= k2.PIPELINE_MIN_PARTICLES
+    xn, rn = k2.rvs(x, r, phi)                             # numpy in -> numpy out
+    assert isinstance(xn, np.ndarray) and xn.shape == (N, 4)
+    assert np.array_equal(xn, one["x_new"].cpu().numpy()) and np.array_equal(rn, one["r_new"].cpu().numpy())
+    for key in ("n_leapfrog", "accepted", "depth", "A_new", "B_new", "ke_new"):
+        assert torch.equal(k2.last[key], one[key]), key
+    # pinned CPU tensors in -> pinned staging buffers out, same numbers; the iteration key advanced by one call
+    xp, rp = torch.from_numpy(x).pin_memory(), torch.from_numpy(r).pin_memory()
+    k2.iteration = 0
+    xt, rt = k2.rvs(xp, rp, phi)
+    assert isinstance(xt, torch.Tensor) and xt.is_pinned()
+    assert np.array_equal(xt.numpy(), xn) and np.array_equal(rt.numpy(), rn)
+    assert k2.iteration == 1
+
+
 def test_nuts_rejects_bad_arguments():
     m, _ = _models("arma")
     k = NUTSProposal(m, StdNormal(4), 0.01, rng=1, max_tree_depth=11)

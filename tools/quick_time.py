@@ -83,6 +83,10 @@ if __name__ == "__main__":
     if which == "armaN":
         for lg in (18, 19, 20, 21, 22, 23):
             nuts("arma", 1 << lg, 0.01, 3900, 0.02, [0.0068, 0.957, -0.034, float(np.log(0.1666))], iters=3)
+    if which.startswith("prmN"):   # prmN17,20 -> PRMwCD at the listed log2 sizes
+        for lg in which[4:].split(","):
+            nuts("PRMwCD", 1 << int(lg), 0.01, 5200, 0.02, [0.8925, 0.0946, 1.3969, 0.1151, -1.4883, -0.0898, 0.6766, -1.7521,
+                                                            -0.3014, 1.6721, -0.1868, -0.1491, float(np.log(0.3326))], iters=2)
     if which == "prm20":
         nuts("PRMwCD", 1 << 20, 0.01, 5200, 0.02, [0.8925, 0.0946, 1.3969, 0.1151, -1.4883, -0.0898, 0.6766, -1.7521, -0.3014,
                                                  1.6721, -0.1868, -0.1491, float(np.log(0.3326))], iters=2)
