@@ -45,6 +45,9 @@ long long smcb_launch_count(void);
 int smcb_model_create(int kind, const double* host_data, long long n, int dim, void** handle);
 int smcb_model_destroy(void* handle);
 int smcb_model_dim(void* handle);
+/* Host-only test hook (no GPU work): the tensor-core fragment packing of the PRMwCD NUTS kernel (csrc/models.cuh,
+ * PrmModelG) applied to a scalar blob [16 header doubles][n_obs rows of 12]; host_out gets 32 + tiles*288 doubles. */
+int smcb_debug_pack_prm(const double* host_scalar_blob, int n_obs, int tiles, double* host_out, long long n_out);
 
 /* StanModel.logpdf / logpdfgrad (bridgestan.py:28-90): A = log prior + Jacobian, B = log likelihood,
  * grad = d(A + phi*B)/dx with the failure mapping (non-finite logp -> grad row of -inf).  Any output may be NULL. */

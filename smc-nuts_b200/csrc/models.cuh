@@ -45,11 +45,30 @@ struct ArmaModel {
     // A, B and g = grad A + phi * grad B
     SMCB_HD void eval(const double (&x)[DMAX], double phi, double& A, double& B, double (&g)[DMAX]) const {
         const double mu = x[0], beta = x[1], theta = x[2], s = x[3];
+#if defined(__CUDA_ARCH__)
+        // Device fast path of the prior block (same formulas, a few ulp apart from the host/oracle statement order):
+        // sigma^2 and 1/sigma^2 from one interleaved exp pair instead of exp + multiply + divide, divisions by
+        // constants as multiplications, one division shared by the Cauchy gradient.  The whole block is ~12 % of the
+        // NUTS kernel's warp time when done with libm calls and four divisions.
+        double sig2, inv;
+        fast_exp_pair(2.0 * s, -2.0 * s, sig2, inv);
+        const double q = sig2 * 0.16;
+        const double cauchy_g = 2.0 * q / (1.0 + q);
+        const bool sigma_ok = (s > -745.13321910194122) && (s < 709.78271289338397);   // exp(s) finite and > 0
+        A = (-0.5 * kLog2Pi - 2.3025850929940456840 - mu * mu * 0.005) +
+            (-0.5 * kLog2Pi - 0.69314718055994530942 - beta * beta * 0.125) +
+            (-0.5 * kLog2Pi - 0.69314718055994530942 - theta * theta * 0.125) +
+            (-kLogPi - 0.91629073187415506518 - log1p(q)) + s;
+#else
         const double sigma = exp(s), sig2 = sigma * sigma, q = sig2 / 6.25;
+        const double inv = 1.0 / sig2;
+        const double cauchy_g = 2.0 * q / (1.0 + q);
+        const bool sigma_ok = is_finite(sigma) && sigma > 0.0;
         A = (-0.5 * kLog2Pi - 2.3025850929940456840 - mu * mu / 200.0) +
             (-0.5 * kLog2Pi - 0.69314718055994530942 - beta * beta / 8.0) +
             (-0.5 * kLog2Pi - 0.69314718055994530942 - theta * theta / 8.0) +
             (-kLogPi - 0.91629073187415506518 - log1p(q)) + s;
+#endif
         double ylag = y[0];
         double e = ylag - (mu + beta * mu);
         double dm = -(1.0 + beta), db = -mu, dt = 0.0;
@@ -68,13 +87,16 @@ struct ArmaModel {
             e = en; dm = dmn; db = dbn; dt = dtn; ylag = yt;
             S += e * e; Sm += e * dm; Sb += e * db; St += e * dt;
         }
-        const double inv = 1.0 / sig2;
         B = -0.5 * T * kLog2Pi - T * s - 0.5 * S * inv;
-        if (!is_finite(sigma) || sigma <= 0.0) A = neg_inf();
+        if (!sigma_ok) A = neg_inf();
+#if defined(__CUDA_ARCH__)
+        g[0] = -mu * 0.01 + phi * (-Sm * inv);
+#else
         g[0] = -mu / 100.0 + phi * (-Sm * inv);
+#endif
         g[1] = -beta / 4.0 + phi * (-Sb * inv);
         g[2] = -theta / 4.0 + phi * (-St * inv);
-        g[3] = (1.0 - 2.0 * q / (1.0 + q)) + phi * (-T + S * inv);
+        g[3] = (1.0 - cauchy_g) + phi * (-T + S * inv);
     }
 };
 
@@ -84,6 +106,38 @@ struct ArmaModel {
 //   per observation i, 12 doubles: X_i0..X_i10, y_i                                   -> 16-byte aligned rows
 // With the y-weighted sums hoisted, sum_i [y_i eta_i - exp(eta_i) - lgamma(y_i+1)] needs only exp(eta_i) and
 // 11 FMAs per observation for the gradient (PRMwCD.stan:24-33), two shorter eta chains instead of one.
+// Exponential-power prior term of one coefficient (PRMwCD.stan:36-37): aq = |b / Gamma|^q and d(-aq)/db = -q aq / b.
+// Device fast path for q = 1/2: with sg = Gamma^(-1/2) and r = rsqrt(|b|), aq = sg |b| r and aq / b = sg r sign(b): one
+// rsqrt instead of sqrt + divide (a few ulp apart from the host/oracle form).
+SMCB_HD void prm_prior_term(double b, double q, double ig, double sg, double& aq, double& dterm) {
+#if defined(__CUDA_ARCH__)
+    if (q == 0.5) {
+        const double ab = fabs(b), r = rsqrt(ab);
+        aq = (ab == 0.0) ? 0.0 : sg * ab * r;
+        dterm = -0.5 * sg * copysign(r, b);
+        (void)ig;
+        return;
+    }
+#endif
+    (void)sg;
+    const double a = fabs(b) * ig;
+    aq = (q == 0.5) ? sqrt(a) : pow(a, q);
+    dterm = -q * aq / b;
+}
+// Gamma^-1 and Gamma^-1/2 from log Gamma; finite, positive Gamma <=> exp(gg) neither overflows nor underflows
+SMCB_HD void prm_gamma_terms(double gg, double& ig, double& sg, bool& ok) {
+#if defined(__CUDA_ARCH__)
+    sg = fast_exp(-0.5 * gg);
+    ig = sg * sg;
+    ok = (gg > -745.13321910194122) && (gg < 709.78271289338397);
+#else
+    ig = exp(-gg);
+    sg = 0.0;
+    const double Gam = exp(gg);
+    ok = is_finite(Gam) && Gam > 0.0;
+#endif
+}
+
 struct PrmModel {
     static constexpr int DMAX = 13;
     static constexpr int STATIC_D = 13;
@@ -166,22 +220,180 @@ struct PrmModel {
             }
         }
         B = b;
-        const double ig = exp(-gg);
-        double sum = 0.0;
+        double ig, sg, sum = 0.0;
+        bool gam_ok;
+        prm_gamma_terms(gg, ig, sg, gam_ok);
         g[0] = phi * (hdr[0] - gl[0]);
 #pragma unroll
         for (int i = 1; i < M; ++i) {
-            const double a = fabs(x[i]) * ig;
-            const double aq = (q == 0.5) ? sqrt(a) : pow(a, q);
+            double aq, dterm;
+            prm_prior_term(x[i], q, ig, sg, aq, dterm);
             sum += aq;
-            g[i] = -q * aq / x[i] + phi * (hdr[i] - gl[i]);
+            g[i] = dterm + phi * (hdr[i] - gl[i]);
         }
         A = (2.0 * 0.26236426446749105204 - 0.0 - 3.0 * gg - 1.3 * ig) + gg + (-(M - 1) * gg - sum);
         g[M] = -3.0 + 1.3 * ig + 1.0 - (M - 1) + q * sum;
-        const double Gam = exp(gg);
-        if (!is_finite(Gam) || Gam <= 0.0) A = neg_inf();
+        if (!gam_ok) A = neg_inf();
     }
 };
+
+// Tensor-core variant of PRMwCD for the NUTS kernel: 4 lanes per particle, 8 particles per warp (the group layout of
+// GaussModelG below).  Lane `sub` of a group holds coordinates sub, sub+4, sub+8, sub+12 (coordinate 12 = log Gamma sits
+// in lane 0, 13..15 are padding).  With Xt = [1, X] (NO x 12) the evaluation is two small FP64 GEMMs over 8 particles,
+//     eta = Beta Xt'   (8 x 12 times 12 x NO)      lambda = exp(eta)      G = lambda Xt   (8 x NO times NO x 12)
+// issued as mma.m8n8k4 (DMMA) on tiles of 8 observations: the C fragment of an eta tile (lane (g,t) holds observations
+// 2t, 2t+1 of particle g) is, after the exp, directly the A fragment of two k-steps of the second product, because the
+// rows of its B fragments are packed in that order; the columns of the second product are permuted so that lane t
+// receives exactly the gradient entries of the coordinates it owns.  No shuffles, 7 DMMA + 2 exp per lane and tile;
+// per-particle latency is ~4x shorter than one-lane-per-particle, which is what the 2047-leapfrog trees need.
+// Padded observations (NO..8*NT-1) have all-zero rows in both products, so sum_i lambda_i is column 0 of G.
+//
+// Staged block (built by pack_prm_fragments, appended to the scalar blob):
+//   [0..15]  hy: sum y, (X'y)_1..11, 0...      [16] sum lgamma(y+1)    [17..31] 0
+//   pf1[NT][3][32]      B fragments of the first product  (k = 4kk + l%4, observation 8nt + l/4)
+//   pf2[NT][2][2][32]   B fragments of the second product (observation 8nt + 2(l%4) + h, column 8nt2 + 4(n%2) + n/2, n = l/4)
+//   ym [NT][2][32]      1.0 where that observation has y > 0 (only read on the lambda-underflow path)
+template <int NT>
+struct PrmModelG {
+    static constexpr int DMAX = 16;
+    static constexpr int STATIC_D = 0;
+    static constexpr int GROUP = 4, NLOC = 4, STATIC_NL = 4;
+    static constexpr int M = 12, HDRG = 32;
+    static constexpr int PF1 = HDRG, PF2 = PF1 + NT * 3 * 32, YM = PF2 + NT * 4 * 32, TOTAL = YM + NT * 2 * 32;
+    const double* blk;
+    double q;
+    SMCB_HD explicit PrmModelG(const ModelDesc& d, const double* staged) : blk(staged), q(d.q) {}
+    SMCB_HD static constexpr int dim_of(const ModelDesc&) { return 13; }
+    SMCB_HD constexpr int dim() const { return 13; }
+    SMCB_HD constexpr int nloc() const { return NLOC; }
+    static int staged_doubles(const ModelDesc&) { return TOTAL; }
+    static bool fits(const ModelDesc& d) { return d.T <= 8 * NT && d.T > 8 * (NT - 3); }
+
+#if defined(__CUDA_ARCH__)
+    static __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    }
+#endif
+
+    SMCB_HD void eval(const double (&x)[NLOC], double phi, double& A, double& B, double (&g)[NLOC]) const {
+#if defined(__CUDA_ARCH__)
+        constexpr unsigned kFull = 0xffffffffu;
+        constexpr double kExpZero = -745.13321910194122;   // exp(x) rounds to 0 below ln(2^-1075)
+        const int lane = threadIdx.x & 31, sub = lane & 3;
+        const double* p1 = blk + PF1 + lane;
+        const double* p2 = blk + PF2 + lane;
+        // ---- eta tiles: NT independent chains of 3 DMMA
+        double e[2 * NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            e[2 * nt] = 0.0; e[2 * nt + 1] = 0.0;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) dmma(e[2 * nt], e[2 * nt + 1], x[kk], p1[(nt * 3 + kk) * 32]);
+        }
+        double min_eta = 1e308;
+#pragma unroll
+        for (int i = 0; i < 2 * NT; ++i) min_eta = e[i] < min_eta ? e[i] : min_eta;
+        // ---- lambda = exp(eta), two interleaved chains at a time
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) fast_exp_pair(e[2 * nt], e[2 * nt + 1], e[2 * nt], e[2 * nt + 1]);
+        // ---- G = lambda Xt: four accumulator sets (tiles nt % 4) keep the DMMA chains short, folded at the end
+        double c[4][4];
+#pragma unroll
+        for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[a_][i] = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int nt2 = 0; nt2 < 2; ++nt2)
+                    dmma(c[nt & 3][2 * nt2], c[nt & 3][2 * nt2 + 1], e[2 * nt + h], p2[((nt * 2 + h) * 2 + nt2) * 32]);
+            }
+        }
+        double gl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gl[i] = (c[0][i] + c[1][i]) + (c[2][i] + c[3][i]);
+        // ---- group scalars: log Gamma lives in slot 3 of lane 0, sum lambda in slot 0 of lane 0
+        const int first = lane & ~3;
+        const double gg = __shfl_sync(kFull, x[3], first);
+        const double slam = __shfl_sync(kFull, gl[0], first);
+        min_eta = fmin(min_eta, __shfl_xor_sync(kFull, min_eta, 1));
+        min_eta = fmin(min_eta, __shfl_xor_sync(kFull, min_eta, 2));
+        double ig, sg;
+        bool gam_ok;
+        prm_gamma_terms(gg, ig, sg, gam_ok);
+        double ydot = 0.0, sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int j = sub + 4 * i;           // coordinates 0..11
+            const double hyj = blk[j];
+            ydot += x[i] * hyj;
+            if (j == 0) {
+                g[i] = phi * (hyj - gl[i]);
+            } else {
+                double aq, dterm;
+                prm_prior_term(x[i], q, ig, sg, aq, dterm);
+                sum += aq;
+                g[i] = dterm + phi * (hyj - gl[i]);
+            }
+        }
+        ydot += __shfl_xor_sync(kFull, ydot, 1); sum += __shfl_xor_sync(kFull, sum, 1);
+        ydot += __shfl_xor_sync(kFull, ydot, 2); sum += __shfl_xor_sync(kFull, sum, 2);
+        g[3] = (sub == 0) ? (-3.0 + 1.3 * ig + 1.0 - (M - 1) + q * sum) : 0.0;
+        double b = ydot - slam - blk[16];
+        // Stan's poisson_lpmf is -inf when lambda underflows to 0 with y > 0 (warp-uniform slow path: the DMMAs need
+        // every lane); lambda = inf gives slam = inf or, through a zero entry of Xt, NaN -> -inf as well
+        if (__any_sync(kFull, min_eta < kExpZero)) {
+            bool hit = false;
+            const double* pm = blk + YM + lane;
+#pragma unroll 1
+            for (int nt = 0; nt < NT; ++nt) {
+                double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) dmma(e0, e1, x[kk], p1[(nt * 3 + kk) * 32]);
+                hit |= (e0 < kExpZero && pm[(nt * 2) * 32] > 0.0) || (e1 < kExpZero && pm[(nt * 2 + 1) * 32] > 0.0);
+            }
+            const unsigned hits = __ballot_sync(kFull, hit);
+            if ((hits >> first) & 0xfu) b = neg_inf();
+        }
+        if (b != b) b = neg_inf();
+        B = b;
+        A = (2.0 * 0.26236426446749105204 - 0.0 - 3.0 * gg - 1.3 * ig) + gg + (-(M - 1) * gg - sum);
+        if (!gam_ok) A = neg_inf();
+#else
+        (void)x; (void)phi; A = B = 0.0; (void)g;
+#endif
+    }
+};
+
+// host-side packing of the staged block of PrmModelG from the scalar blob (PrmModel layout: header + NO rows of 12)
+inline void pack_prm_fragments(const double* scalar_blob, int NO, int nt_tiles, double* out) {
+    const double* hdr = scalar_blob;
+    const double* rows = scalar_blob + 16;
+    auto xt = [&](int o, int k) -> double {   // Xt = [1, X], zero outside the data
+        if (o >= NO || k >= 12) return 0.0;
+        return k == 0 ? 1.0 : rows[(size_t)o * 12 + (k - 1)];
+    };
+    const int PF1 = 32, PF2 = PF1 + nt_tiles * 3 * 32, YM = PF2 + nt_tiles * 4 * 32;
+    for (int i = 0; i < 32; ++i) out[i] = 0.0;
+    for (int j = 0; j < 12; ++j) out[j] = hdr[j];
+    out[16] = hdr[12];
+    for (int nt = 0; nt < nt_tiles; ++nt)
+        for (int l = 0; l < 32; ++l) {
+            for (int kk = 0; kk < 3; ++kk) out[PF1 + (nt * 3 + kk) * 32 + l] = xt(8 * nt + l / 4, 4 * kk + l % 4);
+            for (int h = 0; h < 2; ++h) {
+                const int o = 8 * nt + 2 * (l % 4) + h, n = l / 4;
+                for (int nt2 = 0; nt2 < 2; ++nt2)
+                    out[PF2 + ((nt * 2 + h) * 2 + nt2) * 32 + l] = xt(o, 8 * nt2 + 4 * (n % 2) + n / 2);
+                out[YM + (nt * 2 + h) * 32 + l] = (o < NO && rows[(size_t)o * 12 + 11] > 0.0) ? 1.0 : 0.0;
+            }
+        }
+}
 
 // ---------------------------------------------------------------------------------------------- Gaussian
 // data = P (D x D row-major, symmetric).  A = 0, B = -x'Px/2, grad B = -P x.  One thread per particle,

@@ -47,6 +47,8 @@ template <class M> struct LaunchCfg { static constexpr int NT = 256, MIN_BLOCKS 
 template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
 template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2; };
 template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1; };
+template <int T8> struct LaunchCfg<PrmModelG<T8>> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
+constexpr int kPrmTiles = 13;   // PrmModelG instantiation: 81..104 observations (the shipped PRMwCD has 100)
 
 template <class M>
 static size_t nuts_smem_bytes(const ModelDesc& d) {
@@ -55,6 +57,19 @@ static size_t nuts_smem_bytes(const ModelDesc& d) {
 
 template <class M> struct StageOffset { static int of(const ModelDesc&) { return 0; } };
 template <int NT8> struct StageOffset<GaussModelG<NT8>> { static int of(const ModelDesc& d) { return d.dim * d.dim; } };
+template <int T8> struct StageOffset<PrmModelG<T8>> { static int of(const ModelDesc& d) { return PrmModel::HDR + d.T * PrmModel::ROW; } };
+
+// PRMwCD runs on the tensor-core group kernel when the observation count fits the instantiated tile count
+// (SMCB_PRM_SCALAR=1 forces the one-lane-per-particle kernel: A/B experiments and the parity test of the two)
+// MEASURED (B200, tools/quick_time.py prmN17..20): the group kernel's trip latency is ~4x shorter, which wins while the
+// 2047-leapfrog trees set the makespan (N = 2^17: 33 vs 40 ms), but its tree bookkeeping is replicated on four lanes,
+// so the one-lane kernel has the higher throughput once the SMs are saturated (2^18: 49 vs 49 ms, 2^20: 190 vs 148 ms).
+static bool prm_use_group(const ModelDesc& d, long long N) {
+    const char* e = getenv("SMCB_PRM_SCALAR");   // 1: always one lane per particle, 0: always the group kernel
+    if (!PrmModelG<kPrmTiles>::fits(d)) return false;
+    if (e) return atoi(e) == 0;
+    return N <= 3ll << 16;
+}
 
 // Model data (y[200]; the 100 x 14 PRMwCD table; the Gaussian B-fragments) is staged once per CTA into shared memory,
 // where every lane reads the same address each step (broadcast / conflict-free).  The plain Gaussian precision
@@ -231,6 +246,11 @@ int smcb_model_create(int kind, const double* host_data, long long n, int dim, v
             for (int j = 0; j < 11; ++j) packed[1 + j] += y[i] * X[i * 11 + j];
             packed[12] += lg[i];
         }
+        if (PrmModelG<kPrmTiles>::fits(d)) {   // staged block of the tensor-core NUTS kernel, appended to the scalar blob
+            const size_t n0 = packed.size();
+            packed.resize(n0 + PrmModelG<kPrmTiles>::TOTAL);
+            pack_prm_fragments(packed.data(), NO, kPrmTiles, packed.data() + n0);
+        }
     } else if (kind == SMCB_MODEL_GAUSS) {
         SMCB_REQUIRE(dim >= 1 && dim <= GaussModel::DMAX && (long long)dim * dim == n, "gauss: need P[D*D], D <= 128");
         d.dim = dim;
@@ -265,6 +285,13 @@ int smcb_model_destroy(void* handle) {
 
 int smcb_model_dim(void* handle) { return handle ? ((Model*)handle)->desc.dim : -1; }
 
+int smcb_debug_pack_prm(const double* host_scalar_blob, int n_obs, int tiles, double* host_out, long long n_out) {
+    SMCB_REQUIRE(host_scalar_blob && host_out && n_obs > 0 && tiles > 0 && n_obs <= 8 * tiles, "bad argument");
+    SMCB_REQUIRE(n_out >= 32 + (long long)tiles * 9 * 32, "output too small: 32 + tiles * 288 doubles");
+    pack_prm_fragments(host_scalar_blob, n_obs, tiles, host_out);
+    return 0;
+}
+
 int smcb_logp_grad(void* handle, const double* x, long long N, double phi, double* A, double* B, double* grad,
                    void* stream) {
     SMCB_REQUIRE(handle && x && N >= 0, "bad argument");
@@ -292,7 +319,9 @@ int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long lon
     long long b;
     switch (m->desc.kind) {
         case kArma: b = nuts_ws_bytes<ArmaModel>(m, N, max_depth); break;
-        case kPRMwCD: b = nuts_ws_bytes<PrmModel>(m, N, max_depth); break;
+        case kPRMwCD:
+            b = prm_use_group(m->desc, N) ? nuts_ws_bytes<PrmModelG<kPrmTiles>>(m, N, max_depth) : nuts_ws_bytes<PrmModel>(m, N, max_depth);
+            break;
         default: {
 #define WS_G(K) nuts_ws_bytes<GaussModelG<K>>(m, N, max_depth)
             b = SMCB_GAUSS_DISPATCH(m->desc.dim, WS_G, nuts_ws_bytes<GaussModel>(m, N, max_depth));
@@ -331,7 +360,9 @@ int smcb_nuts_transition(void* handle, const double* x, const double* r, long lo
     cudaStream_t st = (cudaStream_t)stream;
     switch (m->desc.kind) {
         case kArma: return launch_nuts<ArmaModel>(m, a, workspace_bytes, st);
-        case kPRMwCD: return launch_nuts<PrmModel>(m, a, workspace_bytes, st);
+        case kPRMwCD:
+            return prm_use_group(m->desc, N) ? launch_nuts<PrmModelG<kPrmTiles>>(m, a, workspace_bytes, st)
+                                          : launch_nuts<PrmModel>(m, a, workspace_bytes, st);
         default: {
 #define LAUNCH_G(K) launch_nuts<GaussModelG<K>>(m, a, workspace_bytes, st)
             return SMCB_GAUSS_DISPATCH(m->desc.dim, LAUNCH_G, launch_nuts<GaussModel>(m, a, workspace_bytes, st));

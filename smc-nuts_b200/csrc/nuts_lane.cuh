@@ -211,7 +211,7 @@ struct Lane {
     }
 
     SMCB_HD void start_doubling(bool first) {
-        const int nd = (rng.next() < 0.5) ? 1 : -1;  // nuts.py:91
+        const int nd = (rng.next_bits() < (1ull << 52)) ? 1 : -1;  // u < 0.5, nuts.py:91
         if (!first && nd != dir) {                   // bring the other edge into registers
             double tx[DM], tr[DM], tg[DM];
             ldv(other_x(), tx); ldv(other_r(), tr); ldv(other_g(), tg);
@@ -327,9 +327,7 @@ struct Lane {
                     const uint32_t n1 = get_n(l);
                     const int ref1 = get_ref(l);
                     const uint32_t tot = n1 + run_n;
-                    const double u = rng.next();
-                    const double denom = (double)tot > 1. ? (double)tot : 1.;
-                    if (u < ((double)run_n / denom)) {
+                    if (rng.next_below_ratio(run_n, tot > 1u ? tot : 1u)) {   // u < n''/max(n'+n'', 1), nuts.py:142
                         cand_used &= ~(1u << ref1);
                     } else {
                         if (run_ref >= 0) cand_used &= ~(1u << run_ref);
@@ -341,8 +339,9 @@ struct Lane {
             }
         }
         if (leaf == nleaves) {  // doubling complete and not stopped: nuts.py:99-110
-            const double ratio = (double)run_n / (double)n_tot;
-            if (rng.next() < (ratio < 1. ? ratio : 1.)) {
+            // u < min(1, n'/n), nuts.py:99; u < 1 always, so only n' < n needs the comparison (the draw is consumed anyway)
+            const bool take = rng.next_below_ratio(run_n, n_tot) || run_n >= n_tot;
+            if (take) {
                 if (run_ref < 0) {
                     write_sample_from_active(a, A, B, 0.5 * rr);
                 } else {

@@ -19,6 +19,7 @@ _SIGS = {
     "smcb_model_create": [_i, _vp, _ll, _i, ctypes.POINTER(_vp)],
     "smcb_model_destroy": [_vp],
     "smcb_model_dim": [_vp],
+    "smcb_debug_pack_prm": [_vp, _i, _i, _vp, _ll],
     "smcb_logp_grad": [_vp, _vp, _ll, _d, _vp, _vp, _vp, _vp],
     "smcb_combine_logp": [_vp, _vp, _d, _ll, _vp, _vp],
     "smcb_nuts_workspace_bytes": [_vp, _ll, _i, ctypes.POINTER(_ll)],

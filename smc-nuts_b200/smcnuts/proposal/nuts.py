@@ -79,10 +79,13 @@ class NUTSProposal:
         nchunk = len(fr)
         nstream = min(self.PIPELINE_STREAMS, nchunk)
         streams = dev.side_streams(nstream)
-        nbytes = _cabi._ll()
-        _cabi.call("smcb_nuts_workspace_bytes", self.target.handle, max(b - a for a, b in zip(bounds, bounds[1:])),
-                   self.max_tree_depth, nbytes)
-        wss = [dev.workspace(f"nuts_pipe{i}", nbytes.value) for i in range(nstream)]
+        need = 0
+        for lo, hi in zip(bounds, bounds[1:]):      # the kernel variant (and its scratch) may depend on the chunk size
+            if hi > lo:
+                nbytes = _cabi._ll()
+                _cabi.call("smcb_nuts_workspace_bytes", self.target.handle, hi - lo, self.max_tree_depth, nbytes)
+                need = max(need, nbytes.value)
+        wss = [dev.workspace(f"nuts_pipe{i}", need) for i in range(nstream)]
         cur = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(cur)

@@ -153,3 +153,92 @@ print("rank", s.rank, "ok")
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+def _mma_m8n8k4(c0, c1, a, b):
+    """numpy emulation of mma.sync.m8n8k4.f64 on per-lane fragments (arrays of 32 lanes): A[row=l/4][k=l%4],
+    B[k=l%4][n=l/4], C[row=l/4][cols 2(l%4), 2(l%4)+1]."""
+    lanes = np.arange(32)
+    Am = np.zeros((8, 4)); Bm = np.zeros((4, 8))
+    Am[lanes // 4, lanes % 4] = a
+    Bm[lanes % 4, lanes // 4] = b
+    Cm = Am @ Bm
+    return c0 + Cm[lanes // 4, 2 * (lanes % 4)], c1 + Cm[lanes // 4, 2 * (lanes % 4) + 1]
+
+
+def test_prmwcd_tensor_core_fragment_packing_reproduces_the_model():
+    """The PRMwCD NUTS kernel evaluates the model as two FP64 tensor-core products on pre-packed fragments
+    (csrc/models.cuh, PrmModelG).  Emulate its exact dataflow on the CPU from the packing the library produces and
+    compare with the oracle's density: catches any fragment-layout error without a GPU."""
+    import ctypes
+    import json
+    import math
+    from smcnuts import _cabi
+    from smcnuts.model.device_model import DATA_DIR
+    data = json.loads((DATA_DIR / "PRMwCD" / "PRMwCD.json").read_text())
+    NO, NT = int(data["N"]), 13
+    y = np.asarray(data["y"], dtype=np.float64)
+    X = np.asarray(data["Xkernel"], dtype=np.float64).reshape(NO, 11)
+    scalar = np.zeros(16 + NO * 12)
+    scalar[0] = y.sum(); scalar[1:12] = X.T @ y; scalar[12] = sum(math.lgamma(v + 1.0) for v in y)
+    rows = scalar[16:].reshape(NO, 12); rows[:, :11] = X; rows[:, 11] = y
+    out = np.zeros(32 + NT * 288)
+    rc = _cabi.lib().smcb_debug_pack_prm(scalar.ctypes.data_as(ctypes.c_void_p), NO, NT,
+                                         out.ctypes.data_as(ctypes.c_void_p), out.size)
+    assert rc == 0
+    PF1, PF2 = 32, 32 + NT * 96
+    YM = PF2 + NT * 128
+    t = O.COracleTarget("PRMwCD")
+    rng = np.random.default_rng(5)
+    xs = rng.normal(size=(8, 13)) * 0.4
+    xs[:, 12] = rng.normal(size=8) * 0.3 - 1.0
+    lanes = np.arange(32)
+    grp, sub = lanes // 4, lanes % 4
+    xl = np.zeros((4, 32))                       # local slot i of every lane: coordinate sub + 4 i of particle grp
+    for i in range(4):
+        j = sub + 4 * i
+        xl[i] = np.where(j < 13, xs[grp, np.minimum(j, 12)], 0.0)
+    e = np.zeros((2 * NT, 32))
+    for kk in range(3):
+        for nt in range(NT):
+            e[2 * nt], e[2 * nt + 1] = _mma_m8n8k4(e[2 * nt], e[2 * nt + 1], xl[kk], out[PF1 + (nt * 3 + kk) * 32:][:32])
+    # eta of particle g, observation 8 nt + 2 t + h sits in e[2 nt + h] of lane (g, t)
+    eta_ref = xs[:, :1] + xs[:, 1:12] @ X.T
+    for nt in range(NT):
+        for h in range(2):
+            o = 8 * nt + 2 * sub + h
+            ok = o < NO
+            np.testing.assert_allclose(e[2 * nt + h][ok], eta_ref[grp[ok], o[ok]], rtol=1e-13, atol=1e-13)
+            assert np.all(e[2 * nt + h][~ok] == 0.0)
+            assert np.array_equal(out[YM + (nt * 2 + h) * 32:][:32], np.where(ok, y[np.minimum(o, NO - 1)] > 0, False).astype(float))
+    lam = np.exp(e)
+    c = np.zeros((4, 32))
+    for nt in range(NT):
+        for h in range(2):
+            for nt2 in range(2):
+                c[2 * nt2], c[2 * nt2 + 1] = _mma_m8n8k4(c[2 * nt2], c[2 * nt2 + 1], lam[2 * nt + h],
+                                                        out[PF2 + ((nt * 2 + h) * 2 + nt2) * 32:][:32])
+    # assemble A, B and the gradient exactly like the device epilogue and compare with the oracle at phi = 0.7
+    phi, q = 0.7, float(data["q"])
+    gg = xs[:, 12]
+    ig = np.exp(-gg)
+    grad = np.zeros((8, 13)); ydot = np.zeros(8); ssum = np.zeros(8)
+    for i in range(3):
+        for l in range(32):
+            j, g_ = sub[l] + 4 * i, grp[l]
+            hy = out[j]
+            ydot[g_] += xl[i][l] * hy
+            if j == 0:
+                grad[g_, j] = phi * (hy - c[i][l])
+            else:
+                aq = math.sqrt(abs(xl[i][l]) * ig[g_])
+                ssum[g_] += aq
+                grad[g_, j] = -q * aq / xl[i][l] + phi * (hy - c[i][l])
+    slam = c[0][lanes[sub == 0]]
+    grad[:, 12] = -3.0 + 1.3 * ig + 1.0 - 11 + q * ssum
+    Bv = ydot - slam - out[16]
+    Av = (2.0 * 0.26236426446749105204 - 3.0 * gg - 1.3 * ig) + gg + (-11 * gg - ssum)
+    Ao, Bo, _, _ = t.split(xs, grads=False)
+    np.testing.assert_allclose(Av, Ao, rtol=1e-12)
+    np.testing.assert_allclose(Bv, Bo, rtol=1e-12)
+    np.testing.assert_allclose(grad, t.logpdfgrad(xs, phi), rtol=1e-11, atol=1e-11)
