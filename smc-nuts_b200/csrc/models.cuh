@@ -276,6 +276,36 @@ struct PrmModelG {
     }
 #endif
 
+#if defined(__CUDA_ARCH__)
+    // W tiles starting at the fragment pointers q1 (first product) / q2 (second product): eta, lambda = exp(eta), and
+    // lambda's contribution to the two accumulator sets (tiles alternate between them to halve the DMMA chains)
+    template <int W>
+    static __device__ __forceinline__ void tile_block(const double (&x)[NLOC], const double* q1, const double* q2,
+                                                      double (&c)[2][4], double& min_eta) {
+        double e[2 * W];
+#pragma unroll
+        for (int u = 0; u < W; ++u) { e[2 * u] = 0.0; e[2 * u + 1] = 0.0; }
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+#pragma unroll
+            for (int u = 0; u < W; ++u) dmma(e[2 * u], e[2 * u + 1], x[kk], q1[(u * 3 + kk) * 32]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * W; ++i) min_eta = e[i] < min_eta ? e[i] : min_eta;
+#pragma unroll
+        for (int u = 0; u < W; ++u) fast_exp_pair(e[2 * u], e[2 * u + 1], e[2 * u], e[2 * u + 1]);
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int nt2 = 0; nt2 < 2; ++nt2)
+                    dmma(c[u & 1][2 * nt2], c[u & 1][2 * nt2 + 1], e[2 * u + h], q2[((u * 2 + h) * 2 + nt2) * 32]);
+            }
+        }
+    }
+#endif
+
     SMCB_HD void eval(const double (&x)[NLOC], double phi, double& A, double& B, double (&g)[NLOC]) const {
 #if defined(__CUDA_ARCH__)
         constexpr unsigned kFull = 0xffffffffu;
@@ -283,41 +313,25 @@ struct PrmModelG {
         const int lane = threadIdx.x & 31, sub = lane & 3;
         const double* p1 = blk + PF1 + lane;
         const double* p2 = blk + PF2 + lane;
-        // ---- eta tiles: NT independent chains of 3 DMMA
-        double e[2 * NT];
+        // ---- tiles of 8 observations in a ROLLED loop.  The kernel is instruction-fetch bound when this body is
+        //      unrolled (MEASURED at N = 2^20, 4 CTAs/SM: all 13 tiles unrolled 190 ms with `no_instruction` 3.3 stalls
+        //      per issue; 6 tiles per trip 153 ms; 4: 140 ms; 2: 132 ms; 1: 130.5 ms): with four warps per scheduler at
+        //      different places of a large kernel, the small loop body is what stays in the instruction cache, and the
+        //      other warps supply the parallelism that unrolling would have.
+        double c[2][4];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            e[2 * nt] = 0.0; e[2 * nt + 1] = 0.0;
-        }
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) dmma(e[2 * nt], e[2 * nt + 1], x[kk], p1[(nt * 3 + kk) * 32]);
-        }
-        double min_eta = 1e308;
-#pragma unroll
-        for (int i = 0; i < 2 * NT; ++i) min_eta = e[i] < min_eta ? e[i] : min_eta;
-        // ---- lambda = exp(eta), two interleaved chains at a time
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) fast_exp_pair(e[2 * nt], e[2 * nt + 1], e[2 * nt], e[2 * nt + 1]);
-        // ---- G = lambda Xt: four accumulator sets (tiles nt % 4) keep the DMMA chains short, folded at the end
-        double c[4][4];
-#pragma unroll
-        for (int a_ = 0; a_ < 4; ++a_)
+        for (int a_ = 0; a_ < 2; ++a_)
 #pragma unroll
             for (int i = 0; i < 4; ++i) c[a_][i] = 0.0;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int nt2 = 0; nt2 < 2; ++nt2)
-                    dmma(c[nt & 3][2 * nt2], c[nt & 3][2 * nt2 + 1], e[2 * nt + h], p2[((nt * 2 + h) * 2 + nt2) * 32]);
-            }
-        }
+        double min_eta = 1e308;
+        constexpr int U = 1;
+        int nt0 = 0;
+#pragma unroll 1
+        for (; nt0 + U <= NT; nt0 += U) tile_block<U>(x, p1 + nt0 * 96, p2 + nt0 * 128, c, min_eta);
+        if constexpr (NT % U != 0) tile_block<NT % U>(x, p1 + nt0 * 96, p2 + nt0 * 128, c, min_eta);
         double gl[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gl[i] = (c[0][i] + c[1][i]) + (c[2][i] + c[3][i]);
+        for (int i = 0; i < 4; ++i) gl[i] = c[0][i] + c[1][i];
         // ---- group scalars: log Gamma lives in slot 3 of lane 0, sum lambda in slot 0 of lane 0
         const int first = lane & ~3;
         const double gg = __shfl_sync(kFull, x[3], first);

@@ -61,14 +61,13 @@ template <int T8> struct StageOffset<PrmModelG<T8>> { static int of(const ModelD
 
 // PRMwCD runs on the tensor-core group kernel when the observation count fits the instantiated tile count
 // (SMCB_PRM_SCALAR=1 forces the one-lane-per-particle kernel: A/B experiments and the parity test of the two)
-// MEASURED (B200, tools/quick_time.py prmN17..20): the group kernel's trip latency is ~4x shorter, which wins while the
-// 2047-leapfrog trees set the makespan (N = 2^17: 33 vs 40 ms), but its tree bookkeeping is replicated on four lanes,
-// so the one-lane kernel has the higher throughput once the SMs are saturated (2^18: 49 vs 49 ms, 2^20: 190 vs 148 ms).
+// MEASURED (B200, tools/ab_time.py PRMwCD 16..20, fixed inputs): the group kernel wins at every size -- 13.2 vs 30.9 ms at
+// N = 2^16, 23.2 vs 36.8 ms at 2^17 (its trip latency is ~4x shorter, and the 2047-leapfrog trees set the makespan of a
+// small shard), 140.2 vs 150.7 ms at 2^20 -- once its tile loop is rolled so that the kernel fits the instruction cache.
 static bool prm_use_group(const ModelDesc& d, long long N) {
-    const char* e = getenv("SMCB_PRM_SCALAR");   // 1: always one lane per particle, 0: always the group kernel
-    if (!PrmModelG<kPrmTiles>::fits(d)) return false;
-    if (e) return atoi(e) == 0;
-    return N <= 3ll << 16;
+    const char* e = getenv("SMCB_PRM_SCALAR");   // 1: one lane per particle (A/B experiments, parity test of the two)
+    (void)N;
+    return PrmModelG<kPrmTiles>::fits(d) && !(e && atoi(e) != 0);
 }
 
 // Model data (y[200]; the 100 x 14 PRMwCD table; the Gaussian B-fragments) is staged once per CTA into shared memory,

@@ -4,7 +4,9 @@ import re
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "_lib" / "libsmcnuts_b200.so"
+import os
+# SMCB_LIB_PATH: load another build of the same library (A/B experiments of kernel variants on the GPU box)
+LIB_PATH = Path(os.environ.get("SMCB_LIB_PATH") or (_PKG / "_lib" / "libsmcnuts_b200.so"))
 HEADER = _PKG.parents[1] / "include" / "smcnuts_b200.h"
 
 MODEL_KINDS = {"arma": 0, "PRMwCD": 1, "gauss": 2}
