@@ -37,9 +37,10 @@ sys.path.insert(0, str(ROOT / "smc-nuts_b200"))
 WORKLOADS = {
     # name: (model, model kwargs, step size, lkernel, tempering, log2 particles per GPU, FLOP per fused value+grad)
     "arma": ("arma", {}, 0.01, "forwardsLKernel", False, 20, 3900.0),
-    # PRMwCD: 100 x (22 eta + 24 gradient + 6) = 5.2 kFLOP plus 100 exp; an fp64 exp is ~20 FMA-pipe instructions
-    # (range reduction + degree-13 polynomial + scaling) = 40 FLOP-slots, so 9.2 kFLOP of FP64-pipe work per evaluation
-    "PRMwCD": ("PRMwCD", {}, 0.01, "asymptoticLKernel", True, 20, 9200.0),
+    # PRMwCD: 100 x (22 eta + 24 gradient + 6) = 5.2 kFLOP plus 100 exp; an fp64 exp costs 12 FMA-pipe instructions in
+    # the table-driven csrc/common.cuh::fast_exp (libdevice: ~25) = 24 FLOP-slots, so 7.6 kFLOP of FP64-pipe work per
+    # evaluation (round-1 lines before the table exp counted 20 instructions per exp = 9.2 kFLOP)
+    "PRMwCD": ("PRMwCD", {}, 0.01, "asymptoticLKernel", True, 20, 7600.0),
     "gauss": ("gauss", {"dim": 100}, 0.1, "GaussianApproxLKernel", False, 22, 20200.0),
 }
 

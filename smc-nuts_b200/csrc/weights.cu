@@ -354,12 +354,15 @@ __global__ void __launch_bounds__(kRedThreads) weighted_moment_kernel(const doub
     if ((int)threadIdx.x < threads_used) {
         const double cen = center ? center[col] : 0.0;
         const bool do_exp = (constrain == SMCB_CONSTRAIN_EXP_LAST) && (col == D - 1);
-        for (long long e = (long long)blockIdx.x * threads_used + threadIdx.x; e < total; e += gstride) {
+        // the sweep stride is a multiple of D, so the row index advances by a constant: no 64-bit division per element
+        long long row = (long long)blockIdx.x * (threads_used / D) + (int)threadIdx.x / D;
+        const long long rstride = gstride / D;
+        for (long long e = (long long)blockIdx.x * threads_used + threadIdx.x; e < total; e += gstride, row += rstride) {
             double v = x[e];
-            if (do_exp) v = exp(v);
+            if (do_exp) v = fast_exp(v);
             v -= cen;
             if (power == 2) v *= v;
-            acc += wn[e / D] * v;
+            acc += wn[row] * v;
         }
     }
     sh[threadIdx.x] = acc;
