@@ -373,10 +373,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "kernel": "nuts_transition_kernel", "achieved": achieved / 1e12, "peak": peak / 1e12,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 368687872 if (args.workload == "arma" and log2n == 20) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture "
-                                           "profiles/r1_nuts_arma_final_details.csv (algorithmic: 184 MB of particle rows and "
-                                           "scalars; the rest is the per-lane tree workspace leaving L2)",
+                         "traffic": 364820992 if (args.workload == "arma" and log2n == 20) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch (108.7 MB + 256.2 MB), ncu "
+                                           "--set full capture profiles/r1b_nuts_arma_details.csv (algorithmic: 184 MB of "
+                                           "particle rows and scalars; the rest is the per-lane tree workspace leaving L2)",
                          "peak_source": "measured live: smcb_probe_fp64 DFMA loop on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                          "flop_per_eval": flop_per_eval, "evals": evals, "kernel_s": nuts_dt,
                          "kernel_share_of_step": nuts_dt / dt},

@@ -175,6 +175,8 @@ int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, v
 
 /* out[i] = exp(x[i]) with the library's in-kernel exp (test hook: accuracy of the hot-loop exp, <= 1.5 ulp) */
 int smcb_fast_exp(const double* x, long long N, double* out, void* stream);
+/* test hook: the hot-loop log (csrc/common.cuh::fast_log), element-wise */
+int smcb_fast_log(const double* x, long long N, double* out, void* stream);
 
 /* ---- measurement helper: dependent-chain-free DFMA loop; out_flops[0] = FLOPs executed (device double) */
 int smcb_probe_fp64(int blocks, int threads, int iters, double* out_sink, void* stream);

@@ -58,7 +58,7 @@ struct ArmaModel {
         A = (-0.5 * kLog2Pi - 2.3025850929940456840 - mu * mu * 0.005) +
             (-0.5 * kLog2Pi - 0.69314718055994530942 - beta * beta * 0.125) +
             (-0.5 * kLog2Pi - 0.69314718055994530942 - theta * theta * 0.125) +
-            (-kLogPi - 0.91629073187415506518 - log1p(q)) + s;
+            (-kLogPi - 0.91629073187415506518 - fast_log(1.0 + q)) + s;
 #else
         const double sigma = exp(s), sig2 = sigma * sigma, q = sig2 / 6.25;
         const double inv = 1.0 / sig2;
@@ -281,7 +281,7 @@ struct PrmModelG {
     // lambda's contribution to the two accumulator sets (tiles alternate between them to halve the DMMA chains)
     template <int W>
     static __device__ __forceinline__ void tile_block(const double (&x)[NLOC], const double* q1, const double* q2,
-                                                      double (&c)[2][4], double& min_eta) {
+                                                      double (&c)[2][4], unsigned& neg_hi) {
         double e[2 * W];
 #pragma unroll
         for (int u = 0; u < W; ++u) { e[2 * u] = 0.0; e[2 * u + 1] = 0.0; }
@@ -290,8 +290,10 @@ struct PrmModelG {
 #pragma unroll
             for (int u = 0; u < W; ++u) dmma(e[2 * u], e[2 * u + 1], x[kk], q1[(u * 3 + kk) * 32]);
         }
+        // most negative eta so far, tracked on the integer pipe: for negative doubles the high word grows (as an
+        // unsigned integer) with the magnitude; positive values have the sign bit clear and never win
 #pragma unroll
-        for (int i = 0; i < 2 * W; ++i) min_eta = e[i] < min_eta ? e[i] : min_eta;
+        for (int i = 0; i < 2 * W; ++i) neg_hi = max(neg_hi, (unsigned)__double2hiint(e[i]));
 #pragma unroll
         for (int u = 0; u < W; ++u) fast_exp_pair(e[2 * u], e[2 * u + 1], e[2 * u], e[2 * u + 1]);
 #pragma unroll
@@ -323,12 +325,12 @@ struct PrmModelG {
         for (int a_ = 0; a_ < 2; ++a_)
 #pragma unroll
             for (int i = 0; i < 4; ++i) c[a_][i] = 0.0;
-        double min_eta = 1e308;
+        unsigned neg_hi = 0u;
         constexpr int U = 1;
         int nt0 = 0;
 #pragma unroll 1
-        for (; nt0 + U <= NT; nt0 += U) tile_block<U>(x, p1 + nt0 * 96, p2 + nt0 * 128, c, min_eta);
-        if constexpr (NT % U != 0) tile_block<NT % U>(x, p1 + nt0 * 96, p2 + nt0 * 128, c, min_eta);
+        for (; nt0 + U <= NT; nt0 += U) tile_block<U>(x, p1 + nt0 * 96, p2 + nt0 * 128, c, neg_hi);
+        if constexpr (NT % U != 0) tile_block<NT % U>(x, p1 + nt0 * 96, p2 + nt0 * 128, c, neg_hi);
         double gl[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) gl[i] = c[0][i] + c[1][i];
@@ -336,8 +338,8 @@ struct PrmModelG {
         const int first = lane & ~3;
         const double gg = __shfl_sync(kFull, x[3], first);
         const double slam = __shfl_sync(kFull, gl[0], first);
-        min_eta = fmin(min_eta, __shfl_xor_sync(kFull, min_eta, 1));
-        min_eta = fmin(min_eta, __shfl_xor_sync(kFull, min_eta, 2));
+        neg_hi = max(neg_hi, __shfl_xor_sync(kFull, neg_hi, 1));
+        neg_hi = max(neg_hi, __shfl_xor_sync(kFull, neg_hi, 2));
         double ig, sg;
         bool gam_ok;
         prm_gamma_terms(gg, ig, sg, gam_ok);
@@ -362,7 +364,8 @@ struct PrmModelG {
         double b = ydot - slam - blk[16];
         // Stan's poisson_lpmf is -inf when lambda underflows to 0 with y > 0 (warp-uniform slow path: the DMMAs need
         // every lane); lambda = inf gives slam = inf or, through a zero entry of Xt, NaN -> -inf as well
-        if (__any_sync(kFull, min_eta < kExpZero)) {
+        // high word of kExpZero with the sign bit: a (slightly conservative) trigger, the slow path compares exactly
+        if (__any_sync(kFull, neg_hi >= 0xc0874910u)) {
             bool hit = false;
             const double* pm = blk + YM + lane;
 #pragma unroll 1

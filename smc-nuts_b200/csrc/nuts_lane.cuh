@@ -268,7 +268,11 @@ struct Lane {
         ke0 = 0.5 * gsum(rr);
         A0 = A; B0 = B;
         const double H0 = lp - ke0;
+#if defined(__CUDA_ARCH__)
+        logu = H0 + fast_log(1.0 - rng.next());      // 1 - u is exact; table-driven log (common.cuh), <= 2.2e-16 absolute
+#else
         logu = H0 - (-log1p(-rng.next()));
+#endif
         write_sample_from_active(a, A, B, ke0);
         stv(other_x(), xa); stv(other_r(), ra); stv(other_g(), ga);
         n_tot = 1; depth = 0;

@@ -490,6 +490,11 @@ __global__ void probe_fp64_kernel(int iters, double* sink) {
     if (s == 12345.678) sink[0] = s;  // never true; keeps the loop alive
 }
 
+__global__ void fast_log_kernel(const double* __restrict__ x, long long N, double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        out[i] = fast_log(x[i]);
+}
+
 __global__ void fast_exp_kernel(const double* __restrict__ x, long long N, double* __restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
         out[i] = fast_exp(x[i]);
@@ -711,6 +716,13 @@ int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, v
     if (reset_counter(workspace, st)) return -1;
     sum_int32_kernel<<<stride_grid(N, kRedThreads * 4, 4), kRedThreads, 0, st>>>(v, N, out, (double*)workspace);
     return check_launch("sum_int32_kernel");
+}
+
+int smcb_fast_log(const double* x, long long N, double* out, void* stream) {
+    SMCB_REQUIRE(x && out && N >= 0, "bad argument");
+    if (N == 0) return 0;
+    fast_log_kernel<<<stride_grid(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, N, out);
+    return check_launch("fast_log_kernel");
 }
 
 int smcb_fast_exp(const double* x, long long N, double* out, void* stream) {

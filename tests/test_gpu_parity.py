@@ -79,6 +79,28 @@ def test_hot_loop_exp_accuracy():
     np.testing.assert_allclose(got[:200_000], np.exp(x[:200_000]), rtol=4.5e-16)   # <= 2 ulp vs glibc everywhere
 
 
+def test_hot_loop_log_accuracy():
+    """csrc/common.cuh::fast_log (arma prior, slice variable): absolute error <= 3e-16 * max(1, |log u|) against
+    40-digit mpmath; special arguments fall through to libdevice's log."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(2)
+    x = np.concatenate([1.0 + np.exp(rng.uniform(-35, 35, 60_000)), 1.0 - rng.random(60_000), np.exp(rng.uniform(-700, 700, 30_000)),
+                        [1.0, 2.0, 0.5, 5e-324, 0.0, -1.0, np.inf]])
+    xd, out = dev.to_device(x), dev.empty(len(x))
+    _cabi.call("smcb_fast_log", dev.ptr(xd), len(x), dev.ptr(out), dev.stream_ptr())
+    got = out.cpu().numpy()
+    assert abs(got[-7]) <= 3e-16 and got[-3] == -np.inf and np.isnan(got[-2]) and got[-1] == np.inf
+    assert abs(got[-4] - math.log(5e-324)) < 1e-12
+    n = 150_000
+    with np.errstate(divide="ignore"):
+        ref = np.log(x[:n])
+    assert np.all(np.abs(got[:n] - ref) <= 4e-16 * np.maximum(1.0, np.abs(ref)))     # glibc log: <= 1 ulp
+    sel = rng.choice(n, 3000, replace=False)
+    err = [abs(mp.mpf(float(got[i])) - mp.log(mp.mpf(float(x[i])))) / max(1.0, abs(float(ref[i]))) for i in sel]
+    assert max(err) <= 3e-16, float(max(err))
+
+
 def test_philox_streams_match_oracle():
     n = 5000
     u = dev.empty(n)
