@@ -14,6 +14,16 @@ from .. import _cabi, _device as dev
 MAX_TREE_DEPTH = 10
 
 
+def chunk_bounds(n, fractions):
+    """Row boundaries [0, ..., n] of consecutive chunks whose sizes are proportional to `fractions` (empty chunks are
+    possible for tiny n and are skipped by the caller)."""
+    total, acc, bounds = sum(fractions), 0, [0]
+    for c, f in enumerate(fractions):
+        acc += f
+        bounds.append(n if c + 1 == len(fractions) else max(bounds[-1], (acc * n) // total))
+    return bounds
+
+
 class NUTSProposal:
     accept_reject = False
 
@@ -72,11 +82,8 @@ class NUTSProposal:
         ro_h = dev.pinned_buffer("r_new", (N, D), torch.float64)
         x, r = dev.empty(N, D), dev.empty(N, D)
         o = self._alloc_outputs(N, D, False)
-        fr = self.PIPELINE_FRACTIONS
-        bounds = [0]
-        for c in range(len(fr)):
-            bounds.append(N if c + 1 == len(fr) else max(bounds[-1], (sum(fr[:c + 1]) * N) // sum(fr)))
-        nchunk = len(fr)
+        bounds = chunk_bounds(N, self.PIPELINE_FRACTIONS)
+        nchunk = len(bounds) - 1
         nstream = min(self.PIPELINE_STREAMS, nchunk)
         streams = dev.side_streams(nstream)
         need = 0

@@ -242,3 +242,16 @@ def test_prmwcd_tensor_core_fragment_packing_reproduces_the_model():
     np.testing.assert_allclose(Av, Ao, rtol=1e-12)
     np.testing.assert_allclose(Bv, Bo, rtol=1e-12)
     np.testing.assert_allclose(grad, t.logpdfgrad(xs, phi), rtol=1e-11, atol=1e-11)
+
+
+def test_pipeline_chunk_bounds_cover_every_row_once():
+    """Host-side chunking of NUTSProposal.rvs (copy/compute pipeline): contiguous, ordered, complete for any N."""
+    from smcnuts.proposal.nuts import NUTSProposal, chunk_bounds
+    for n in (0, 1, 3, 7, 8, 1000, (1 << 17) + 1234, 1 << 20):
+        for fr in (NUTSProposal.PIPELINE_FRACTIONS, (1,), (1, 1, 1, 1), (1, 7, 7, 1), (5, 3)):
+            b = chunk_bounds(n, fr)
+            assert b[0] == 0 and b[-1] == n and len(b) == len(fr) + 1
+            assert all(lo <= hi for lo, hi in zip(b, b[1:]))
+            if n >= 64:
+                sizes = np.diff(b) / n
+                np.testing.assert_allclose(sizes, np.array(fr) / sum(fr), atol=2.0 / n)
