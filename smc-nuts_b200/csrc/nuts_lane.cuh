@@ -224,11 +224,29 @@ struct Lane {
         ck_used = cand_used = ck_valid = 0;
     }
 
+    // start_doubling(false) when x and r of the other edge are already in registers (only its gradient is loaded)
+    SMCB_HD void start_doubling_with(const double (&xo)[DM], const double (&ro)[DM]) {
+        const int nd = (rng.next_bits() < (1ull << 52)) ? 1 : -1;  // u < 0.5, nuts.py:91
+        if (nd != dir) {
+            double tg[DM];
+            ldv(other_g(), tg);
+            stv(other_x(), xa); stv(other_r(), ra); stv(other_g(), ga);
+#pragma unroll
+            SMCB_LOCAL(i) { xa[i] = xo[i]; ra[i] = ro[i]; ga[i] = tg[i]; }
+        }
+        dir = nd;
+        leaf = 0; pend_n = 0; pend_ref = 0; ck_ref = 0;
+        ck_used = cand_used = ck_valid = 0;
+    }
+
     // U-turn test between a stored edge (x at c, r at c + nlp) and the active edge (nuts.py:152-160); the edge order
     // (minus, plus) is restored through `dir`.
     SMCB_HD bool uturn(const double* c) const {
         double xc[DM], rc[DM];
         ldv(c, xc); ldv(c + nlp, rc);
+        return uturn_regs(xc, rc);
+    }
+    SMCB_HD bool uturn_regs(const double (&xc)[DM], const double (&rc)[DM]) const {
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
         SMCB_LOCAL(i) {
@@ -239,6 +257,14 @@ struct Lane {
         s1 = gsum(s1); s2 = gsum(s2);
         return (dir * s1 < 0) || (dir * s2 < 0);
     }
+    // Small records (<= 4 coordinates per lane: arma, the PRMwCD group kernel): the stored edge of a U-turn test is
+    // loaded BEFORE the Philox draw and the merge bookkeeping that precede the test, so the load latency (L2 more
+    // often than L1: the records of a CTA exceed its L1 share) is covered by ~80 independent instructions.  Larger
+    // records cannot afford the 4*DM extra live registers.
+#ifndef SMCB_NUTS_EARLY_LOADS
+#define SMCB_NUTS_EARLY_LOADS 1
+#endif
+    static constexpr bool kEarly = (SMCB_NUTS_EARLY_LOADS != 0) && DM <= 4;
 
     // rows of the caller's [N, D] arrays: 16-byte accesses when the row layout allows it
     SMCB_HD void write_row(double* base, const double (&v)[DM]) const {
@@ -328,6 +354,9 @@ struct Lane {
             } else {
                 const int tz = ctz32(leaf);
                 for (int l = 0; l < tz; ++l) {  // nuts.py:136-148, second child = running node
+                    const double* ck = slotp(get_ck(popc32(i0 - (2u << l) + 1u)));
+                    double xc[kEarly ? DM : 1], rc[kEarly ? DM : 1];
+                    if constexpr (kEarly) { ldv(ck, xc); ldv(ck + nlp, rc); }
                     const uint32_t n1 = get_n(l);
                     const int ref1 = get_ref(l);
                     const uint32_t tot = n1 + run_n;
@@ -338,11 +367,16 @@ struct Lane {
                         run_ref = ref1;
                     }
                     run_n = tot;
-                    if (uturn(slotp(get_ck(popc32(i0 - (2u << l) + 1u))))) { ++depth; return finish(a); }
+                    bool stop;
+                    if constexpr (kEarly) stop = uturn_regs(xc, rc);
+                    else stop = uturn(ck);
+                    if (stop) { ++depth; return finish(a); }
                 }
             }
         }
         if (leaf == nleaves) {  // doubling complete and not stopped: nuts.py:99-110
+            double xo[kEarly ? DM : 1], ro[kEarly ? DM : 1];   // the other edge: needed by the trajectory U-turn test
+            if constexpr (kEarly) { ldv(other_x(), xo); ldv(other_r(), ro); }   // and, on a direction flip, as the new active edge
             // u < min(1, n'/n), nuts.py:99; u < 1 always, so only n' < n needs the comparison (the draw is consumed anyway)
             const bool take = rng.next_below_ratio(run_n, n_tot) || run_n >= n_tot;
             if (take) {
@@ -363,10 +397,13 @@ struct Lane {
                 }
             }
             n_tot += run_n;
-            const bool stop = uturn(other_x());
+            bool stop;
+            if constexpr (kEarly) stop = uturn_regs(xo, ro);
+            else stop = uturn(other_x());
             ++depth;
             if (stop || depth > L) return finish(a);
-            start_doubling(false);
+            if constexpr (kEarly) start_doubling_with(xo, ro);
+            else start_doubling(false);
             return false;
         }
         // park the running node as the pending first child of level ctz(leaf)
