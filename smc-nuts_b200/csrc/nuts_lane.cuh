@@ -22,7 +22,9 @@
 //     sub-tree U-turn nuts.py:148) ends the transition at once, because the reference then never
 //     reads the sub-tree's candidate nor draws again from this particle's stream.
 //
-// The selected sample is written straight into the caller's x_new/r_new row (owned by this lane).
+// The selected sample: when a doubling is accepted and its candidate sits in a leaf slot, the lane only remembers the
+// slot (it stays allocated across doublings) and copies it into the caller's x_new/r_new row once, at the end of the
+// transition; a candidate that is the leaf in registers, and the start point, are written to the row at once.
 #pragma once
 #include "common.cuh"
 #include "models.cuh"
@@ -70,7 +72,7 @@ struct alignas(16) D2 {
 
 // Workspace record of one LANE (global memory, 128-byte aligned; nlp = nl rounded up to even so that every vector is
 // 16-byte aligned):
-//   other edge: x[nlp] r[nlp] g[nlp] | 2L+2 leaf slots, each x[nlp] r[nlp] A B [g[nlp]]
+//   other edge: x[nlp] r[nlp] g[nlp] | 2L+3 leaf slots, each x[nlp] r[nlp] A B [g[nlp]]
 // A leaf state is stored at most ONCE: the first leaf of a sub-tree (U-turn checkpoint) and a pending candidate are
 // the same record when they are the same leaf (every odd leaf of a doubling is both); checkpoints and candidates
 // are slot references handed out from one free mask.  Candidates carry their gradient only when the caller asked
@@ -78,7 +80,7 @@ struct alignas(16) D2 {
 SMCB_HD int nuts_nlp(int nl) { return (nl + 1) & ~1; }
 SMCB_HD int nuts_slot_stride(int nl, bool carry) { return 2 * nuts_nlp(nl) + 2 + (carry ? nuts_nlp(nl) : 0); }
 SMCB_HD int nuts_ws_doubles(int nl, int L, bool carry = true) {
-    return ((3 * nuts_nlp(nl) + nuts_slot_stride(nl, carry) * (2 * L + 2)) + 15) & ~15;
+    return ((3 * nuts_nlp(nl) + nuts_slot_stride(nl, carry) * (2 * L + 3)) + 15) & ~15;
 }
 
 enum LanePhase : int { kIdle = 0, kInit = 1, kLeaf = 2 };
@@ -98,6 +100,8 @@ struct Lane {
     int phase, dir, depth, D, L, nl, sub;
     uint32_t leaf, n_tot, n_leapfrog;
     uint32_t ck_used, cand_used, ck_valid;   // slots referenced by live checkpoints / candidates; valid checkpoint ids
+    uint32_t samp_used;                      // slot holding the currently selected sample (one bit, or 0: it is in the row)
+    int samp_ref;
     uint64_t pend_n, pend_ref, ck_ref;       // packed per-level counts, candidate slot refs, checkpoint slot refs (5 bits)
     StreamReader rng;
 
@@ -143,8 +147,8 @@ struct Lane {
     SMCB_HD double* other_g() const { return ws + 2 * nlp; }
     SMCB_HD double* slotp(int slot) const { return ws + 3 * nlp + slot_stride * slot; }   // x[nlp] r[nlp] A B [g[nlp]]
     SMCB_HD int alloc_slot() {
-        const uint32_t free_ = ~(ck_used | cand_used);
-        return ctz32(free_);   // 2L+2 <= 22 slots, at most L checkpoints + L+1 candidates are live
+        const uint32_t free_ = ~(ck_used | cand_used | samp_used);
+        return ctz32(free_);   // 2L+3 <= 23 slots: at most L checkpoints + L+1 candidates + the selected sample are live
     }
     // store the leaf in registers (active edge) into a fresh slot
     SMCB_HD int store_leaf(const NutsArgs& a, double A, double B) {
@@ -282,6 +286,24 @@ struct Lane {
         write_row(a.r_new, ra);
         if (a.g_new) write_row(a.g_new, ga);
         As = A; Bs = B; kes = ke;
+        samp_ref = -1; samp_used = 0u;
+    }
+
+    // the deferred copy of a sample that still sits in its leaf slot (see the header comment)
+    SMCB_HD void flush_sample(const NutsArgs& a) {
+        if (samp_ref < 0) return;
+        const double* c = slotp(samp_ref);
+        double t[DM];
+        ldv(c, t); write_row(a.x_new, t);
+        ldv(c + nlp, t); write_row(a.r_new, t);
+        double k2 = 0.0;
+#pragma unroll
+        SMCB_LOCAL(i) k2 += t[i] * t[i];
+        kes = 0.5 * gsum(k2);
+        const D2 ab = *reinterpret_cast<const D2*>(c + 2 * nlp);
+        As = ab.x; Bs = ab.y;
+        if (a.g_new) { ldv(c + 2 * nlp + 2, t); write_row(a.g_new, t); }
+        samp_ref = -1; samp_used = 0u;
     }
 
     // nuts.py:66-87 given logp = A + phi*B and its gradient (already in `ga`) at the start point
@@ -382,18 +404,8 @@ struct Lane {
             if (take) {
                 if (run_ref < 0) {
                     write_sample_from_active(a, A, B, 0.5 * rr);
-                } else {
-                    const double* c = slotp(run_ref);
-                    double t[DM];
-                    ldv(c, t); write_row(a.x_new, t);
-                    ldv(c + nlp, t); write_row(a.r_new, t);
-                    double k2 = 0.0;
-#pragma unroll
-                    SMCB_LOCAL(i) k2 += t[i] * t[i];
-                    kes = 0.5 * gsum(k2);
-                    const D2 ab = *reinterpret_cast<const D2*>(c + 2 * nlp);
-                    As = ab.x; Bs = ab.y;
-                    if (a.g_new) { ldv(c + 2 * nlp + 2, t); write_row(a.g_new, t); }
+                } else {   // keep the slot, copy it out once at the end of the transition (flush_sample)
+                    samp_ref = run_ref; samp_used = 1u << run_ref;
                 }
             }
             n_tot += run_n;
@@ -418,6 +430,7 @@ struct Lane {
     // End of transition: optional endpoint MH step (nuts_acc_rej.py:42-49, utils.py:22-34) and outputs.
     SMCB_HD bool finish(const NutsArgs& a) {
         const int d_ = D;
+        flush_sample(a);
         double ken = kes;
         int anyinf = 0;
         if (a.accrej) {   // np.any(np.isinf(x_prime)), utils.py:32
