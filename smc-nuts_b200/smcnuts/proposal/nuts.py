@@ -4,7 +4,6 @@ Mirrors smcnuts/proposal/nuts.py of the reference: `NUTSProposal(target, momentu
 `.rvs(x_cond, r_cond, phi) -> (x_prime, r_prime)`, `.logpdf(r)`.  The per-particle Python loop and the
 recursive build_tree (nuts.py:50-53,114-150) are one persistent CUDA kernel (csrc/nuts_kernel.cu).
 """
-import math
 
 import torch
 

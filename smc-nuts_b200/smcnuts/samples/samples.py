@@ -5,7 +5,6 @@ attributes), with every array a float64 CUDA tensor in the reference's row-major
 operation a kernel behind include/smcnuts_b200.h.  When a torch.distributed process group exists the
 particle set is sharded (rank p owns [p*N/P, (p+1)*N/P)); `N` is always the GLOBAL particle count.
 """
-import math
 
 import numpy as np
 import torch

@@ -255,3 +255,69 @@ def test_pipeline_chunk_bounds_cover_every_row_once():
             if n >= 64:
                 sizes = np.diff(b) / n
                 np.testing.assert_allclose(sizes, np.array(fr) / sum(fr), atol=2.0 / n)
+
+
+def _parse_table(text, name):
+    import re
+    body = re.search(name + r"\[\d+\] = \{(.*?)\};", text, re.S).group(1)
+    return [float.fromhex(v) for v in re.findall(r"-?0x[0-9a-fA-F.]+p[+-]?\d+", body)]
+
+
+def test_fast_exp_and_fast_log_tables_and_algorithms():
+    """csrc/common.cuh::fast_exp / fast_log restated in Python with exactly rounded FMAs, using the tables and constants
+    parsed from the header: the committed tables are the correctly rounded 2^(j/32), 1/c_j and -log(1/c_j), and the
+    algorithms meet the accuracy the device tests assert (exp <= 1 ulp, log <= 2.5e-16 * max(1, |log u|))."""
+    import math
+    import re
+    import struct
+    from fractions import Fraction as F
+    import mpmath as mp
+    mp.mp.dps = 50
+    text = (ROOT / "smc-nuts_b200" / "csrc" / "common.cuh").read_text()
+    T, INV, LOGC = _parse_table(text, "kExpT"), _parse_table(text, "kLogInvC"), _parse_table(text, "kLogC")
+    assert len(T) == 32 and len(INV) == 64 and len(LOGC) == 64
+    assert T == [float(mp.mpf(2) ** (mp.mpf(j) / 32)) for j in range(32)]
+    assert INV == [float(1 / (1 + (mp.mpf(j) + mp.mpf(1) / 2) / 64)) for j in range(64)]
+    assert LOGC == [float(-mp.log(mp.mpf(v))) for v in INV]
+    const = {k: float.fromhex(v) for k, v in re.findall(r"constexpr double (kExp\w+) = (0x[0-9a-fp.+-]+);", text)}
+    inv_l, l_hi, l_lo = const["kExpInvL"], const["kExpLHi"], const["kExpLLo"]
+    assert inv_l == float(32 / mp.log(2)) and abs(float(mp.mpf(l_hi) + mp.mpf(l_lo) - mp.log(2) / 32)) < 1e-28
+    magic = 6755399441055744.0
+
+    def fma(a, b, c):
+        return float(F(a) * F(b) + F(c))
+
+    def fexp(x):
+        t = fma(x, inv_l, magic)
+        kp = struct.unpack("<i", struct.pack("<d", t)[:4])[0]
+        t -= magic
+        r = fma(t, -l_lo, fma(t, -l_hi, x))
+        s = r * r
+        b1 = fma(1 / 720, s, fma(1 / 120, r, 1 / 24))
+        q = fma(s, fma(s, b1, fma(1 / 6, r, 0.5)), r)
+        return math.ldexp(fma(T[kp & 31], q, T[kp & 31]), kp >> 5)
+
+    ln2_hi, ln2_lo = (float.fromhex(v) for v in re.search(
+        r"fma\(e, (0x[0-9a-fp.+-]+), __ldg\(&kLogC\[j\]\)\) \+ fma\(e, (0x[0-9a-fp.+-]+), l1\)", text).groups())
+
+    def flog(u):
+        bits = struct.unpack("<q", struct.pack("<d", u))[0]
+        e, j = ((bits >> 52) & 0x7ff) - 1023, (bits >> 46) & 63
+        m = struct.unpack("<d", struct.pack("<q", (bits & ((1 << 52) - 1)) | (1023 << 52)))[0]
+        r = fma(m, INV[j], -1.0)
+        p = fma(1 / 7, r, -1 / 6)
+        for c in (0.2, -0.25, 1 / 3, -0.5):
+            p = fma(p, r, c)
+        return fma(float(e), ln2_hi, LOGC[j]) + fma(float(e), ln2_lo, fma(r * r, p, r))
+
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for x in np.concatenate([rng.uniform(-707, 707, 700), rng.normal(size=700) * 3]):
+        g, ref = fexp(float(x)), mp.exp(mp.mpf(float(x)))
+        worst = max(worst, float(abs(mp.mpf(g) - ref) / mp.mpf(float(np.spacing(g)))))
+    assert worst <= 1.0, worst
+    worst = 0.0
+    for u in np.concatenate([1 + np.exp(rng.uniform(-30, 30, 600)), 1 - rng.random(600), np.exp(rng.uniform(-700, 700, 300))]):
+        ref = mp.log(mp.mpf(float(u)))
+        worst = max(worst, float(abs(mp.mpf(flog(float(u))) - ref)) / max(1.0, abs(float(ref))))
+    assert worst <= 2.5e-16, worst
