@@ -17,7 +17,26 @@
 #pragma once
 #include "common.cuh"
 
+// Warp-level code (shuffles, votes, mma.sync) is compiled for the device and, with SMCB_SIMT_EMU, for the fiber-based
+// warp emulator of tests/hostsim (a test tool that runs the 4-lanes-per-particle kernels on the CPU; never part of the
+// product library).
+#if defined(__CUDA_ARCH__) || defined(SMCB_SIMT_EMU)
+#define SMCB_WARP_CODE 1
+#endif
+
 namespace smcb {
+
+#if defined(SMCB_WARP_CODE)
+// C[8x8] += A[8x4] * B[4x8] on FP64 tensor cores; per-lane fragments: A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4) + {0,1}]
+SMCB_D void dmma(double& c0, double& c1, double a, double b) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#else
+    simt_emu::dmma(c0, c1, a, b);
+#endif
+}
+#endif
 
 // Plain-old-data descriptor handed to kernels by value; `data` points at the packed device blob.
 struct ModelDesc {
@@ -269,18 +288,11 @@ struct PrmModelG {
     static int staged_doubles(const ModelDesc&) { return TOTAL; }
     static bool fits(const ModelDesc& d) { return d.T <= 8 * NT && d.T > 8 * (NT - 3); }
 
-#if defined(__CUDA_ARCH__)
-    static __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-    }
-#endif
-
-#if defined(__CUDA_ARCH__)
+#if defined(SMCB_WARP_CODE)
     // W tiles starting at the fragment pointers q1 (first product) / q2 (second product): eta, lambda = exp(eta), and
     // lambda's contribution to the two accumulator sets (tiles alternate between them to halve the DMMA chains)
     template <int W>
-    static __device__ __forceinline__ void tile_block(const double (&x)[NLOC], const double* q1, const double* q2,
+    static SMCB_D void tile_block(const double (&x)[NLOC], const double* q1, const double* q2,
                                                       double (&c)[2][4], unsigned& neg_hi) {
         double e[2 * W];
 #pragma unroll
@@ -309,7 +321,7 @@ struct PrmModelG {
 #endif
 
     SMCB_HD void eval(const double (&x)[NLOC], double phi, double& A, double& B, double (&g)[NLOC]) const {
-#if defined(__CUDA_ARCH__)
+#if defined(SMCB_WARP_CODE)
         constexpr unsigned kFull = 0xffffffffu;
         constexpr double kExpZero = -745.13321910194122;   // exp(x) rounds to 0 below ln(2^-1075)
         const int lane = threadIdx.x & 31, sub = lane & 3;
@@ -462,7 +474,7 @@ struct GaussModelG {
     static int frag_offset(const ModelDesc& d) { return d.dim * d.dim; }  // pfrag follows the plain matrix in the blob
 
     SMCB_HD void eval(const double (&x)[NLOC], double phi, double& A, double& B, double (&g)[NLOC]) const {
-#if defined(__CUDA_ARCH__)
+#if defined(SMCB_WARP_CODE)
         const int lane = threadIdx.x & 31;
         // k outer, n-tiles inner: NT8 independent accumulator chains per k-step keep the tensor pipe full
         double c[NLOC];
@@ -474,9 +486,7 @@ struct GaussModelG {
             const double av = x[kk];
 #pragma unroll
             for (int nt = 0; nt < NT8; ++nt) {
-                const double b = bp[(nt * KK + kk) * 32];
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                             : "+d"(c[2 * nt]), "+d"(c[2 * nt + 1]) : "d"(av), "d"(b));
+                dmma(c[2 * nt], c[2 * nt + 1], av, bp[(nt * KK + kk) * 32]);
             }
         }
         double qf = 0.0;

@@ -110,7 +110,7 @@ struct Lane {
 
     SMCB_HD int gd(int i) const { return G == 1 ? i : sub + G * i; }   // global coordinate of local slot i
     SMCB_HD double gsum(double v) const {
-#if defined(__CUDA_ARCH__)
+#if defined(SMCB_WARP_CODE)
         if (G > 1) {
             const unsigned mask = ((1u << G) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
 #pragma unroll

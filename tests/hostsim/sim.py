@@ -24,6 +24,23 @@ def lib():
     return _LIB
 
 
+_LIB_SIMT = None
+
+
+def lib_simt():
+    """The warp-emulated build (hostsim_simt.cpp + simt_emu.h): group kernels with shuffles / votes / mma on fibers."""
+    global _LIB_SIMT
+    if _LIB_SIMT is None:
+        so = HERE / "_hostsim_simt.so"
+        srcs = [HERE / "hostsim_simt.cpp", HERE / "simt_emu.h"]
+        hdrs = list((HERE.parents[1] / "smc-nuts_b200" / "csrc").glob("*.cuh"))
+        if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in srcs + hdrs):
+            subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                            "-o", str(so), str(srcs[0])], check=True)
+        _LIB_SIMT = ctypes.CDLL(str(so))
+    return _LIB_SIMT
+
+
 def pack_model(name, np_target):
     """Host blob -> (kind, packed data, dim, T, q) in the device layout of csrc/models.cuh."""
     if name == "arma":
@@ -63,4 +80,27 @@ def nuts(name, np_target, x, r, eps, phi, max_depth=10, accrej=False, seed=0, it
                        P(o["A_old"]), P(o["B_old"]), P(o["A_new"]), P(o["B_new"]), P(o["ke_old"]), P(o["ke_new"]),
                        I(o["n_leapfrog"]), I(o["accepted"]), I(o["depth"]), P(cA), P(cB), P(cg), P(o.get("g_new")),
                        ctypes.c_int(lanes))
+    return o
+
+
+def nuts_simt(name, np_target, x, r, eps, phi, max_depth=10, accrej=False, seed=0, iteration=0, particle0=0):
+    """One NUTS transition per particle on the EMULATED 4-lanes-per-particle kernels (PRMwCD: PrmModelG<13>; gauss:
+    GaussModelG<ceil(D/8)>), one persistent warp pulling particles from the work queue."""
+    kind, data, dim, T, q = pack_model(name, np_target)
+    assert kind in (1, 2)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    N = len(x)
+    o = dict(x_new=np.empty_like(x), r_new=np.empty_like(r), A_old=np.empty(N), B_old=np.empty(N), A_new=np.empty(N),
+             B_new=np.empty(N), ke_old=np.empty(N), ke_new=np.empty(N), n_leapfrog=np.empty(N, dtype=np.int32),
+             accepted=np.empty(N, dtype=np.int32), depth=np.empty(N, dtype=np.int32))
+    P = lambda a: a.ctypes.data_as(_dp)  # noqa: E731
+    I = lambda a: a.ctypes.data_as(_ip)  # noqa: E731
+    rc = lib_simt().hostsim_nuts_simt(
+        ctypes.c_int(kind), P(data), ctypes.c_int(data.size), ctypes.c_int(dim), ctypes.c_int(T), ctypes.c_double(q), P(x),
+        P(r), ctypes.c_longlong(N), ctypes.c_double(eps), ctypes.c_double(phi), ctypes.c_int(max_depth),
+        ctypes.c_int(int(accrej)), ctypes.c_ulonglong(seed), ctypes.c_uint(iteration), ctypes.c_ulonglong(particle0),
+        P(o["x_new"]), P(o["r_new"]), P(o["A_old"]), P(o["B_old"]), P(o["A_new"]), P(o["B_new"]), P(o["ke_old"]),
+        P(o["ke_new"]), I(o["n_leapfrog"]), I(o["accepted"]), I(o["depth"]))
+    assert rc == 0
     return o

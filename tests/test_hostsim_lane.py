@@ -92,3 +92,58 @@ def test_gradient_carry_over_skips_the_initial_evaluation_without_changing_anyth
                        carry=(a["A_new"], a["B_new"], a["g_new"]), want_grad=True)
     for k in ("x_new", "r_new", "A_old", "B_old", "A_new", "B_new", "n_leapfrog", "depth", "g_new", "ke_old", "ke_new"):
         assert np.array_equal(plain[k], carried[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ group kernels
+# The 4-lanes-per-particle kernels (GaussModelG, PrmModelG: FP64 tensor-core products, group folds by shuffle, the
+# warp-level work queue) run on the CPU through the fiber-based warp emulator tests/hostsim/simt_emu.h.
+
+@pytest.mark.parametrize("dim,eps,N", [(8, 0.1, 150), (33, 0.15, 50), (100, 0.1, 20)])
+def test_group_kernel_gauss_matches_c_oracle_bitwise(dim, eps, N):
+    """The emulated mma accumulates k = 0..3 in order, so -Px is summed in the oracle's order: trees, MH outcomes and the
+    returned states of the tensor-core group kernel must equal the recursive C oracle bit for bit (ragged work queue: N
+    is not a multiple of the 8 particles a warp holds)."""
+    t = O.COracleTarget("gauss", dim=dim)
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(N, dim)) * 0.3
+    r = rng.normal(size=(N, dim))
+    for accrej, phi in ((False, 1.0), (True, 0.7)):
+        ref = t.nuts_batch(x, r, eps, phi, 10, seed=77, iteration=3, particle0=1000, accrej=accrej)
+        o = sim.nuts_simt("gauss", t.np_target, x, r, eps, phi, 10, accrej, 77, 3, 1000)
+        for k in ("n_leapfrog", "depth", "accepted", "x_new", "r_new"):
+            assert np.array_equal(o[k], ref[k]), k
+        np.testing.assert_allclose(o["ke_old"], 0.5 * np.sum(r * r, axis=1), rtol=1e-14)
+        # the quadratic form is folded over the 4 lanes of a group by shuffles (a tree), the oracle sums it in order
+        np.testing.assert_allclose(o["A_new"] + phi * o["B_new"], ref["lp_new"], rtol=1e-13)
+
+
+def test_group_kernel_prmwcd_matches_c_oracle():
+    """PrmModelG: eta and the gradient are tensor-core products over tiles of 8 observations, so sums are associated
+    differently from the oracle's observation loop: values agree to rounding (1e-12), and the 250-leapfrog trajectories
+    amplify that to a few changed tree sizes (>= 90 % equal, as on the GPU)."""
+    import math
+    t = O.COracleTarget("PRMwCD")
+    rng = np.random.default_rng(21)
+    N = 44                                                   # ragged: 5.5 warps-full of particles
+    centre = np.array([0.8925, 0.0946, 1.3969, 0.1151, -1.4883, -0.0898, 0.6766, -1.7521, -0.3014, 1.6721, -0.1868,
+                       -0.1491, math.log(0.3326)])
+    x = centre + rng.normal(size=(N, 13)) * 0.05
+    x[:6] = rng.normal(size=(6, 13)) * 3.0                   # wild starts
+    x[6:9, 0] = -800.0                                       # lambda underflows to 0 with y > 0 -> logp = -inf
+    r = rng.normal(size=(N, 13))
+    phi = 0.6
+    ref = t.nuts_batch(x, r, 0.01, phi, 10, seed=3, iteration=1, accrej=True)
+    o = sim.nuts_simt("PRMwCD", t.np_target, x, r, 0.01, phi, 10, True, 3, 1, 0)
+    Ao, Bo, _, _ = t.split(x, grads=False)
+    assert np.all(np.isneginf(o["B_old"][6:9])) and np.array_equal(np.isfinite(o["B_old"]), np.isfinite(Bo))
+    fin = np.isfinite(Bo)
+    np.testing.assert_allclose(o["A_old"][fin], Ao[fin], rtol=1e-13)
+    np.testing.assert_allclose(o["B_old"][fin], Bo[fin], rtol=1e-12)
+    same = o["n_leapfrog"] == ref["n_leapfrog"]
+    assert same.mean() >= 0.9, same.mean()
+    assert np.array_equal(o["depth"][same], ref["depth"][same])
+    ok = same & (o["accepted"] == ref["accepted"]) & np.isfinite(ref["x_new"]).all(axis=1)
+    close = np.isclose(o["x_new"][ok], ref["x_new"][ok], rtol=1e-4, atol=1e-6).all(axis=1)
+    assert close.mean() >= 0.85, close.mean()
+    rej = o["accepted"] == 0
+    assert np.array_equal(o["x_new"][rej], x[rej]) and np.array_equal(o["r_new"][rej], r[rej])
