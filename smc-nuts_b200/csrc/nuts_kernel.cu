@@ -47,6 +47,7 @@ template <class M> struct LaunchCfg { static constexpr int NT = 256, MIN_BLOCKS 
 template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
 template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2; };
 template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1; };
+// PrmModelG, MEASURED (N = 2^20): 4 CTAs/SM at 118 registers 130.5 ms; 3 CTAs/SM 140+ ms; 5 CTAs/SM (96 registers, spills) 132-152 ms
 template <int T8> struct LaunchCfg<PrmModelG<T8>> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
 constexpr int kPrmTiles = 13;   // PrmModelG instantiation: 81..104 observations (the shipped PRMwCD has 100)
 
@@ -70,7 +71,7 @@ static bool prm_use_group(const ModelDesc& d, long long N) {
     return PrmModelG<kPrmTiles>::fits(d) && !(e && atoi(e) != 0);
 }
 
-// Model data (y[200]; the 100 x 14 PRMwCD table; the Gaussian B-fragments) is staged once per CTA into shared memory,
+// Model data (y[200]; the PRMwCD table or its tensor-core fragments; the Gaussian B-fragments) is staged once per CTA into shared memory,
 // where every lane reads the same address each step (broadcast / conflict-free).  The plain Gaussian precision
 // matrix of the one-lane-per-particle fallback stays in L1/L2.
 template <class M>
