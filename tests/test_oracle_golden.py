@@ -147,3 +147,66 @@ def test_full_run_matches_reference(golden, name, tname, kw, lk):
     np.testing.assert_allclose(s.logw_saved[int(K)], g[f"{name}_logw_final"], rtol=1e-7, atol=1e-7)
     np.testing.assert_allclose(s.mean_estimate, g[f"{name}_mean_estimate"], rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(s.variance_estimate, g[f"{name}_variance_estimate"], rtol=1e-5, atol=1e-10)
+
+
+def test_oracle_densities_equal_an_independent_scipy_restatement_of_the_stan_programs():
+    """BridgeStan cannot be installed here, so the oracle's model arithmetic is pinned twice over by independent
+    restatements: mpmath (golden fixture, 50 digits) and -- this test -- the `.stan` programs written out with
+    scipy.stats' lpdf/lpmf implementations (all normalising constants kept, as `target +=` does) plus the log-Jacobian
+    of the `<lower=0>` transform (Stan reference manual; BridgeStan's default jacobian=True).  Gradients are checked
+    against Richardson-extrapolated central differences of the scipy form."""
+    import json
+    from scipy import stats
+    from smcnuts.model.device_model import DATA_DIR          # the shipped arma.json / repaired PRMwCD.json
+    arma_json, prm_json = DATA_DIR / "arma" / "arma.json", DATA_DIR / "PRMwCD" / "PRMwCD.json"
+    y_arma = np.asarray(json.loads(arma_json.read_text())["y"], dtype=float)
+    prm = json.loads(prm_json.read_text())
+    y_prm = np.asarray(prm["y"], dtype=float)
+    Xk = np.asarray(prm["Xkernel"], dtype=float).reshape(int(prm["N"]), int(prm["Clength"]))
+    q = float(prm["q"])
+
+    def arma_logp(x, phi):                                   # arma.stan:14-31
+        mu, beta, theta, s = x
+        sigma = np.exp(s)
+        lp = stats.norm.logpdf(mu, 0, 10) + stats.norm.logpdf(beta, 0, 2) + stats.norm.logpdf(theta, 0, 2)
+        lp += stats.cauchy.logpdf(sigma, 0, 2.5) + s         # + log-Jacobian of sigma = exp(s)
+        err = np.empty_like(y_arma)
+        err[0] = y_arma[0] - (mu + beta * mu)
+        for t in range(1, len(y_arma)):
+            err[t] = y_arma[t] - (mu + beta * y_arma[t - 1] + theta * err[t - 1])
+        return lp + phi * stats.norm.logpdf(err, 0, sigma).sum()
+
+    def prm_logp(x, phi):                                    # PRMwCD.stan:17-39
+        B, g = x[:12], x[12]
+        Gam = np.exp(g)
+        lp = stats.invgamma.logpdf(Gam, 2, scale=1.3) + g
+        eta = B[0] + Xk @ B[1:]
+        lp += phi * stats.poisson.logpmf(y_prm, np.exp(eta)).sum()
+        return lp + np.sum(-np.log(Gam) - np.abs(B[1:] / Gam) ** q)
+
+    def num_grad(f, x):
+        g = np.empty_like(x)
+        for i in range(len(x)):
+            def d(h):
+                e = np.zeros_like(x); e[i] = h
+                return (f(x + e) - f(x - e)) / (2 * h)
+            h = 1e-4 * max(1.0, abs(x[i]))
+            g[i] = (4 * d(h / 2) - d(h)) / 3
+        return g
+
+    rng = np.random.default_rng(8)
+    t = O.COracleTarget("arma")
+    X = rng.normal(size=(12, 4)) * 0.2 + np.array([0.0, 0.9, 0.0, -1.7])
+    for phi in (0.0, 0.37, 1.0):
+        np.testing.assert_allclose(t.logpdf(X, phi), [arma_logp(x, phi) for x in X], rtol=1e-12)
+        G = t.logpdfgrad(X, phi)
+        for x, gr in zip(X[:4], G[:4]):
+            np.testing.assert_allclose(gr, num_grad(lambda v: arma_logp(v, phi), x), rtol=2e-6, atol=1e-6)
+    t = O.COracleTarget("PRMwCD")
+    X = rng.normal(size=(12, 13)) * 0.3
+    X[:, 12] = rng.normal(size=12) * 0.3 - 1.0
+    for phi in (0.0, 0.37, 1.0):
+        np.testing.assert_allclose(t.logpdf(X, phi), [prm_logp(x, phi) for x in X], rtol=1e-12)
+        G = t.logpdfgrad(X, phi)
+        for x, gr in zip(X[:4], G[:4]):
+            np.testing.assert_allclose(gr, num_grad(lambda v: prm_logp(v, phi), x), rtol=2e-6, atol=1e-5)
