@@ -147,3 +147,16 @@ def test_group_kernel_prmwcd_matches_c_oracle():
     assert close.mean() >= 0.85, close.mean()
     rej = o["accepted"] == 0
     assert np.array_equal(o["x_new"][rej], x[rej]) and np.array_equal(o["r_new"][rej], r[rej])
+
+
+def test_group_kernel_max_depth_cap_and_slot_pressure():
+    """A flat target never U-turns: the group kernel must run to the depth cap (2^(L+1) - 1 leapfrogs), which is also
+    the case with the most live checkpoints, candidates and the deferred sample slot at once."""
+    t = O.COracleTarget("gauss", dim=4)
+    x = np.zeros((11, 4)); r = np.ones((11, 4)) * 1e-3          # 11 particles: one full and one ragged octet
+    for L in (3, 10):
+        ref = t.nuts_batch(x, r, 1e-6, 1.0, L, seed=1)
+        o = sim.nuts_simt("gauss", t.np_target, x, r, 1e-6, 1.0, L, False, 1, 0, 0)
+        assert np.all(ref["n_leapfrog"] == 2 ** (L + 1) - 1) and np.array_equal(o["n_leapfrog"], ref["n_leapfrog"])
+        assert np.array_equal(o["x_new"], ref["x_new"]) and np.array_equal(o["r_new"], ref["r_new"])
+        assert np.array_equal(o["depth"], ref["depth"])
