@@ -37,6 +37,9 @@ extern "C" {
 #define SMCB_CONSTRAIN_EXP_LAST 1  /* bridgestan.py:93-120 for arma / PRMwCD: exp() on the last coordinate  */
 
 int smcb_version(void);
+/* 0: product build; 1: parity build (-DSMCB_PARITY=1 -fmad=false: the oracle's statement order in the model device
+ * functions, no FMA contraction) -- libsmcnuts_b200_parity.so, loaded only by the parity tests */
+int smcb_build_flavour(void);
 const char* smcb_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 long long smcb_launch_count(void);
@@ -177,6 +180,10 @@ int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, v
 int smcb_fast_exp(const double* x, long long N, double* out, void* stream);
 /* test hook: the hot-loop log (csrc/common.cuh::fast_log), element-wise */
 int smcb_fast_log(const double* x, long long N, double* out, void* stream);
+
+/* test hook: one mma.m8n8k4 (FP64 tensor core) per warp on caller-supplied fragments, a[32 w], b[32 w], c[64 w] ->
+ * out[64 w] (lane l holds a[l], b[l], c[2l], c[2l+1]); establishes the instruction's rounding against an exact CPU model */
+int smcb_debug_dmma(const double* a, const double* b, const double* c, double* out, int nwarps, void* stream);
 
 /* ---- measurement helper: dependent-chain-free DFMA loop; out_flops[0] = FLOPs executed (device double) */
 int smcb_probe_fp64(int blocks, int threads, int iters, double* out_sink, void* stream);

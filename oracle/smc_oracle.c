@@ -25,9 +25,24 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "devmath.h"
+
 #define MAXD 128
 #define LOG_2PI 1.8378770664093454835606594728112
 #define LOG_PI 1.1447298858494001741434273513531
+
+/* ------------------------------------------------------------------ elementary functions
+ * Default: glibc (the mode pinned against the reference goldens).  orc_set_devmath(1): the table-driven exp / log of
+ * the CUDA kernels restated in oracle/devmath.h, used to predict the parity device build bit for bit. */
+static int g_devmath = 0;
+void orc_set_devmath(int on) { g_devmath = on; }
+int orc_get_devmath(void) { return g_devmath; }
+static double m_exp(double x) { return g_devmath ? dm_exp(x) : exp(x); }
+static double m_log1p(double q) { return g_devmath ? dm_log(1.0 + q) : log1p(q); }
+/* log(1 - u) of the slice variable (nuts.py:69: logu = H0 - Exp(1), Exp(1) = -log1p(-u)) */
+static double m_log_1mu(double u) { return g_devmath ? dm_log(1.0 - u) : log1p(-u); }
+void orc_devmath_exp(const double* x, long n, double* out) { for (long i = 0; i < n; ++i) out[i] = dm_exp(x[i]); }
+void orc_devmath_log(const double* x, long n, double* out) { for (long i = 0; i < n; ++i) out[i] = dm_log(x[i]); }
 
 /* ------------------------------------------------------------------ Philox4x32-10 */
 static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
@@ -98,9 +113,9 @@ static void arma_split(const Model* m, const double* x, double* A, double* B, do
     const double* y = m->data;
     const int T = (int)m->n;
     double mu = x[0], beta = x[1], theta = x[2], s = x[3];
-    double sigma = exp(s), sig2 = sigma * sigma, q = sig2 / 6.25;
+    double sigma = m_exp(s), sig2 = sigma * sigma, q = sig2 / 6.25;
     *A = (-0.5 * LOG_2PI - log(10.0) - mu * mu / 200.0) + (-0.5 * LOG_2PI - log(2.0) - beta * beta / 8.0) +
-         (-0.5 * LOG_2PI - log(2.0) - theta * theta / 8.0) + (-LOG_PI - log(2.5) - log1p(q)) + s;
+         (-0.5 * LOG_2PI - log(2.0) - theta * theta / 8.0) + (-LOG_PI - log(2.5) - m_log1p(q)) + s;
     gA[0] = -mu / 100.0; gA[1] = -beta / 4.0; gA[2] = -theta / 4.0; gA[3] = 1.0 - 2.0 * q / (1.0 + q);
     double e = y[0] - (mu + beta * mu);
     double dm = -(1.0 + beta), db = -mu, dt = 0.0;
@@ -150,7 +165,7 @@ static void prm_split(const Model* m, const double* x, double* A, double* B, dou
         }
         double eta = e0 + e1;
         min_eta = eta < min_eta ? eta : min_eta;
-        double lam = exp(eta);
+        double lam = m_exp(eta);
         slam += lam;
         gl[0] += lam;
         for (int j = 0; j < C; ++j) gl[j + 1] += lam * row[j];
@@ -158,17 +173,17 @@ static void prm_split(const Model* m, const double* x, double* A, double* B, dou
     double ydot = x[0] * hdr[0];
     for (int j = 0; j < C; ++j) ydot += x[j + 1] * hdr[1 + j];
     double b = ydot - slam - hdr[12];
-    if (exp(min_eta) == 0.0) { /* Stan: lambda == 0 with y != 0 -> -inf */
+    if (m_exp(min_eta) == 0.0) { /* Stan: lambda == 0 with y != 0 -> -inf */
         for (int i = 0; i < NO; ++i) {
             double eta = x[0];
             for (int j = 0; j < C; ++j) eta += x[j + 1] * X[i * C + j];
-            if (exp(eta) == 0.0 && y[i] > 0.0) b = -INFINITY;
+            if (m_exp(eta) == 0.0 && y[i] > 0.0) b = -INFINITY;
         }
     }
     *B = b;
     for (int j = 0; j < M; ++j) gB[j] = hdr[j] - gl[j];
     gB[M] = 0.0;
-    double ig = exp(-g), sum = 0.0;
+    double ig = m_exp(-g), sum = 0.0;
     gA[0] = 0.0;
     for (int i = 1; i < M; ++i) {
         double aq = (q == 0.5) ? sqrt(fabs(x[i]) * ig) : pow(fabs(x[i]) * ig, q);
@@ -177,7 +192,7 @@ static void prm_split(const Model* m, const double* x, double* A, double* B, dou
     }
     *A = (2.0 * log(1.3) - lgamma(2.0) - 3.0 * g - 1.3 * ig) + g + (-(M - 1) * g - sum);
     gA[M] = -3.0 + 1.3 * ig + 1.0 - (M - 1) + q * sum;
-    double Gam = exp(g);
+    double Gam = m_exp(g);
     if (!isfinite(Gam) || Gam <= 0.0) *A = -INFINITY;
 }
 
@@ -315,8 +330,12 @@ static void nuts_one(Ctx* c, const double* x0, const double* r0, double* xo, dou
     double g0[MAXD];
     double logp = model_eval(c->m, x0, c->phi, g0);
     double H0 = logp - 0.5 * dot(r0, r0, D);
-    double expo = -log1p(-next_uniform(c));
-    c->logu = H0 - expo;
+    if (g_devmath) {
+        c->logu = H0 + m_log_1mu(next_uniform(c));
+    } else {
+        double expo = -log1p(-next_uniform(c));
+        c->logu = H0 - expo;
+    }
 
     double xm[MAXD], rm[MAXD], gm[MAXD], xp[MAXD], rp[MAXD], gp[MAXD];
     memcpy(xm, x0, sz); memcpy(xp, x0, sz); memcpy(rm, r0, sz); memcpy(rp, r0, sz);
@@ -372,7 +391,7 @@ void orc_nuts_batch(void* h, const double* x, const double* r, long N, double ep
             double *xn = x_new + i * D, *rn = r_new + i * D;
             double H1 = lps - (0.5 * dot(rn, rn, D));
             double H0 = lp0 - (0.5 * dot(rc, rc, D));
-            double ratio = exp(H1 - H0);
+            double ratio = m_exp(H1 - H0);
             double prob = (ratio < 1.) ? ratio : 1.; /* python min(1., ratio): nan -> 1. */
             double u = stream_uniform(seed, iter, 2u, particle0 + (uint64_t)i, 0);
             int anyinf = 0;

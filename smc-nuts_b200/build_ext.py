@@ -1,9 +1,15 @@
 """Build libsmcnuts_b200.so (hand-written sm_100a CUDA behind the C-ABI of include/smcnuts_b200.h) in-tree.
 
-    python smc-nuts_b200/build_ext.py [--force]
+    python smc-nuts_b200/build_ext.py [--force] [-v]
 
-nvcc cross-compiles without a GPU.  The shared object lands in smc-nuts_b200/smcnuts/_lib/ (git-ignored,
-but it travels to the GPU box with the repo snapshot).
+nvcc cross-compiles without a GPU.  The shared objects land in smc-nuts_b200/smcnuts/_lib/ (git-ignored,
+but they travel to the GPU box with the repo snapshot):
+
+  libsmcnuts_b200.so          the product library
+  libsmcnuts_b200_parity.so   the PARITY build of the same sources: -DSMCB_PARITY=1 -fmad=false, i.e. the oracle's
+                              statement order in the model device functions and no FMA contraction.  Same C-ABI; never
+                              loaded by the product path -- the `-m gpu` parity tests load it to show that the CUDA
+                              binary reproduces the oracle tree for tree and bit for bit.
 """
 import subprocess
 import sys
@@ -14,6 +20,8 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT_DIR = HERE / "smcnuts" / "_lib"
 OUT = OUT_DIR / "libsmcnuts_b200.so"
+OUT_PARITY = OUT_DIR / "libsmcnuts_b200_parity.so"
+PARITY_FLAGS = ["-DSMCB_PARITY=1", "-fmad=false"]
 SOURCES = ["nuts_kernel.cu", "weights.cu", "resample.cu", "gauss_lkernel.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]
@@ -24,16 +32,22 @@ def _stale(target, deps):
     return (not target.exists()) or target.stat().st_mtime < max(p.stat().st_mtime for p in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, parity=True):
+    out = _build_one(OUT, HERE / "build", [], force, verbose)
+    if parity:
+        _build_one(OUT_PARITY, HERE / "build_parity", PARITY_FLAGS, force, False)
+    return out
+
+
+def _build_one(OUT, obj_dir, extra_flags, force, verbose):
     OUT_DIR.mkdir(parents=True, exist_ok=True)
-    obj_dir = HERE / "build"
     obj_dir.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "smcnuts_b200.h"]
 
     def compile_one(src):
         obj = obj_dir / (src[:-3] + ".o")
         if force or _stale(obj, [CSRC / src] + headers):
-            cmd = ["nvcc", *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+            cmd = ["nvcc", *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             r = subprocess.run(cmd, capture_output=True, text=True)

@@ -7,6 +7,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define SMCB_HD __host__ __device__ __forceinline__
@@ -16,7 +17,57 @@
 #define SMCB_D inline
 #endif
 
+// Build flavours of the arithmetic:
+//   product device code      SMCB_FAST_PATH = 1: fused fast paths of the prior blocks, FMA contraction by nvcc
+//   parity device build      -DSMCB_PARITY=1 -fmad=false (libsmcnuts_b200_parity.so): the oracle's statement order, no
+//                            contraction; exp / log are the table-driven fast_exp / fast_log below, whose explicit FMAs
+//                            are reproducible on a CPU
+//   host, -DSMCB_DEVMATH     tests/hostsim only: the same fast_exp / fast_log arithmetic restated for the host, so the
+//                            g++ build of the lane code is the bit-for-bit twin of the parity device build
+//   host, default            std::exp / std::log / log1p: bit-identical to the default oracle (glibc)
+#if !defined(SMCB_PARITY)
+#define SMCB_PARITY 0
+#endif
+#if defined(__CUDA_ARCH__) && !SMCB_PARITY
+#define SMCB_FAST_PATH 1
+#else
+#define SMCB_FAST_PATH 0
+#endif
+#if defined(__CUDA_ARCH__) || defined(SMCB_DEVMATH)
+#define SMCB_TABLE_MATH 1
+#else
+#define SMCB_TABLE_MATH 0
+#endif
+
 namespace smcb {
+
+// bit-level access to a double, device intrinsics or (host) memcpy
+SMCB_HD int dbl_hi(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(v);
+#else
+    uint64_t b; std::memcpy(&b, &v, 8); return (int)(uint32_t)(b >> 32);
+#endif
+}
+SMCB_HD int dbl_lo(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(v);
+#else
+    uint64_t b; std::memcpy(&b, &v, 8); return (int)(uint32_t)b;
+#endif
+}
+SMCB_HD double dbl_make(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double v; std::memcpy(&v, &b, 8); return v;
+#endif
+}
+#if defined(__CUDA_ARCH__)
+#define SMCB_LDG(p) __ldg(p)
+#else
+#define SMCB_LDG(p) (*(p))
+#endif
 
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
 constexpr double kLogPi = 1.1447298858494001741434273513531;
@@ -64,7 +115,12 @@ SMCB_HD bool is_finite(double v) {
 // underflow come out of the multiplications themselves.  Host builds (tests/hostsim) use std::exp so that they stay
 // bit-identical to the oracle.
 #if defined(__CUDACC__)
-static __device__ const double kExpT[32] = {
+#define SMCB_TABLE static __device__ const double
+#else
+#define SMCB_TABLE static const double
+#endif
+#if defined(__CUDACC__) || defined(SMCB_DEVMATH)
+SMCB_TABLE kExpT[32] = {
     0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, 0x1.172b83c7d517bp+0,
     0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0, 0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0,
     0x1.3dea64c123422p+0, 0x1.44e086061892dp+0, 0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0,
@@ -79,22 +135,27 @@ constexpr double kExpLLo = 0x1.1cf79abc9e3b4p-41;
 constexpr double kExpMagic = 6755399441055744.0;   // 1.5 * 2^52: the low word of x/L + magic is round(x/L)
 
 // p * 2^k for out-of-range arguments (|x| >= 708, inf, nan); p = T[j] exp(r) of the reduced argument
-static __device__ __noinline__ double fast_exp_tail(double x, double p, int k) {
+#if defined(__CUDACC__)
+static __device__ __noinline__
+#else
+static inline
+#endif
+double fast_exp_tail(double x, double p, int k) {
     const int k1 = k >> 1, k2 = k - k1;
-    double res = p * __hiloint2double((k1 + 1023) << 20, 0) * __hiloint2double((k2 + 1023) << 20, 0);
-    res = (x > 709.782712893384) ? __longlong_as_double(0x7ff0000000000000LL) : res;
+    double res = p * dbl_make((k1 + 1023) << 20, 0) * dbl_make((k2 + 1023) << 20, 0);
+    res = (x > 709.782712893384) ? dbl_make(0x7ff00000, 0) : res;
     res = (x < -745.2) ? 0.0 : res;
     return (x != x) ? x : res;
 }
-__device__ __forceinline__ double fast_exp_scale(double p, int k) {
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+SMCB_HD double fast_exp_scale(double p, int k) {
+    return dbl_make(dbl_hi(p) + (int)((unsigned)k << 20), dbl_lo(p));
 }
 #endif
 SMCB_HD double fast_exp(double x) {
-#if defined(__CUDA_ARCH__)
+#if SMCB_TABLE_MATH
     double t = fma(x, kExpInvL, kExpMagic);
-    const int kp = __double2loint(t);
-    const double tj = __ldg(&kExpT[kp & 31]);
+    const int kp = dbl_lo(t);
+    const double tj = SMCB_LDG(&kExpT[kp & 31]);
     t -= kExpMagic;
     double r = fma(t, -kExpLHi, x);
     r = fma(t, -kExpLLo, r);
@@ -104,7 +165,7 @@ SMCB_HD double fast_exp(double x) {
     b1 = fma(1.0 / 720, s, b1);
     const double q = fma(s, fma(s, b1, b0), r);
     const double p = fma(tj, q, tj);
-    if ((__double2hiint(x) & 0x7fffffff) >= kExpFastHi) return fast_exp_tail(x, p, kp >> 5);
+    if ((dbl_hi(x) & 0x7fffffff) >= kExpFastHi) return fast_exp_tail(x, p, kp >> 5);
     return fast_exp_scale(p, kp >> 5);
 #else
     return std::exp(x);
@@ -114,10 +175,10 @@ SMCB_HD double fast_exp(double x) {
 // Two independent exps with their instruction streams interleaved statement by statement (the compiler keeps the
 // source order inside a basic block, so this doubles the ILP of the latency-bound chains).
 SMCB_HD void fast_exp_pair(double xa, double xb, double& ea, double& eb) {
-#if defined(__CUDA_ARCH__)
+#if SMCB_TABLE_MATH
     double ta = fma(xa, kExpInvL, kExpMagic), tb = fma(xb, kExpInvL, kExpMagic);
-    const int ka = __double2loint(ta), kb = __double2loint(tb);
-    const double ja = __ldg(&kExpT[ka & 31]), jb = __ldg(&kExpT[kb & 31]);
+    const int ka = dbl_lo(ta), kb = dbl_lo(tb);
+    const double ja = SMCB_LDG(&kExpT[ka & 31]), jb = SMCB_LDG(&kExpT[kb & 31]);
     ta -= kExpMagic; tb -= kExpMagic;
     double ra = fma(ta, -kExpLHi, xa), rb = fma(tb, -kExpLHi, xb);
     ra = fma(ta, -kExpLLo, ra); rb = fma(tb, -kExpLLo, rb);
@@ -127,7 +188,7 @@ SMCB_HD void fast_exp_pair(double xa, double xb, double& ea, double& eb) {
     a1 = fma(1.0 / 720, sa, a1); c1 = fma(1.0 / 720, sb, c1);
     const double qa = fma(sa, fma(sa, a1, a0), ra), qb = fma(sb, fma(sb, c1, c0), rb);
     const double pa = fma(ja, qa, ja), pb = fma(jb, qb, jb);
-    const int ha = __double2hiint(xa) & 0x7fffffff, hb = __double2hiint(xb) & 0x7fffffff;
+    const int ha = dbl_hi(xa) & 0x7fffffff, hb = dbl_hi(xb) & 0x7fffffff;
     ea = fast_exp_scale(pa, ka >> 5); eb = fast_exp_scale(pb, kb >> 5);
     if ((ha > hb ? ha : hb) >= kExpFastHi) {   // rare: out-of-range, inf or nan argument
         if (ha >= kExpFastHi) ea = fast_exp_tail(xa, pa, ka >> 5);
@@ -144,8 +205,8 @@ SMCB_HD void fast_exp_pair(double xa, double xb, double& ea, double& eb) {
 // for libdevice's log1p.  Absolute error <= 2.2e-16 * max(1, |log u|) (CPU emulation against mpmath, and
 // tests/test_gpu_parity.py): both uses add the result to O(1) terms.  Anything else (0, denormal, negative, inf, nan)
 // goes to libdevice's log.
-#if defined(__CUDACC__)
-static __device__ const double kLogInvC[64] = {
+#if defined(__CUDACC__) || defined(SMCB_DEVMATH)
+SMCB_TABLE kLogInvC[64] = {
     0x1.fc07f01fc07f0p-1, 0x1.f44659e4a4271p-1, 0x1.ecc07b301ecc0p-1, 0x1.e573ac901e574p-1,
     0x1.de5d6e3f8868ap-1, 0x1.d77b654b82c34p-1, 0x1.d0cb58f6ec074p-1, 0x1.ca4b3055ee191p-1,
     0x1.c3f8f01c3f8f0p-1, 0x1.bdd2b899406f7p-1, 0x1.b7d6c3dda338bp-1, 0x1.b2036406c80d9p-1,
@@ -162,7 +223,7 @@ static __device__ const double kLogInvC[64] = {
     0x1.19453808ca29cp-1, 0x1.16e0689427379p-1, 0x1.1485f0e0acd3bp-1, 0x1.12358e75d3033p-1,
     0x1.0fef010fef011p-1, 0x1.0db20a88f4696p-1, 0x1.0b7e6ec259dc8p-1, 0x1.0953f39010954p-1,
     0x1.073260a47f7c6p-1, 0x1.05197f7d73404p-1, 0x1.03091b51f5e1ap-1, 0x1.0101010101010p-1};
-static __device__ const double kLogC[64] = {
+SMCB_TABLE kLogC[64] = {
     0x1.fe02a6b106799p-8, 0x1.7b91b07d5b126p-6, 0x1.39e87b9febd68p-5, 0x1.b42dd711971b9p-5,
     0x1.16536eea37ae3p-4, 0x1.51b073f06183cp-4, 0x1.8c345d6319b23p-4, 0x1.c5e548f5bc743p-4,
     0x1.fec9131dbeabcp-4, 0x1.1b72ad52f67a2p-3, 0x1.371fc201e8f75p-3, 0x1.526e5e3a1b438p-3,
@@ -181,19 +242,29 @@ static __device__ const double kLogC[64] = {
     0x1.54b2467999498p-1, 0x1.58cadb5cd7989p-1, 0x1.5cdb1dc6c1765p-1, 0x1.60e32f44788d9p-1};
 #endif
 SMCB_HD double fast_log(double u) {
-#if defined(__CUDA_ARCH__)
-    const int hi = __double2hiint(u);
+#if SMCB_TABLE_MATH
+    const int hi = dbl_hi(u);
     if (hi < 0x00100000 || hi >= 0x7ff00000) return log(u);
     const int j = (hi >> 14) & 63;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(u));
+    const double m = dbl_make((hi & 0x000fffff) | 0x3ff00000, dbl_lo(u));
     const double e = (double)((hi >> 20) - 1023);
-    const double r = fma(m, __ldg(&kLogInvC[j]), -1.0);
+    const double r = fma(m, SMCB_LDG(&kLogInvC[j]), -1.0);
     double p = fma(1.0 / 7, r, -1.0 / 6);
     p = fma(p, r, 0.2); p = fma(p, r, -0.25); p = fma(p, r, 1.0 / 3); p = fma(p, r, -0.5);
     const double l1 = fma(r * r, p, r);
-    return fma(e, 0x1.62e42fefa2000p-1, __ldg(&kLogC[j])) + fma(e, 0x1.9ef35793c7673p-41, l1);
+    return fma(e, 0x1.62e42fefa2000p-1, SMCB_LDG(&kLogC[j])) + fma(e, 0x1.9ef35793c7673p-41, l1);
 #else
     return std::log(u);
+#endif
+}
+
+// log1p of the oracle's statement order (arma prior: log1p(sigma^2/6.25)): glibc log1p on a default host build, the
+// table-driven log of 1 + q wherever the table arithmetic is in force (parity device build and its host twin).
+SMCB_HD double ref_log1p(double q) {
+#if SMCB_TABLE_MATH
+    return fast_log(1.0 + q);
+#else
+    return log1p(q);
 #endif
 }
 

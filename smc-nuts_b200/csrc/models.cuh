@@ -64,7 +64,7 @@ struct ArmaModel {
     // A, B and g = grad A + phi * grad B
     SMCB_HD void eval(const double (&x)[DMAX], double phi, double& A, double& B, double (&g)[DMAX]) const {
         const double mu = x[0], beta = x[1], theta = x[2], s = x[3];
-#if defined(__CUDA_ARCH__)
+#if SMCB_FAST_PATH
         // Device fast path of the prior block (same formulas, a few ulp apart from the host/oracle statement order):
         // sigma^2 and 1/sigma^2 from one interleaved exp pair instead of exp + multiply + divide, divisions by
         // constants as multiplications, one division shared by the Cauchy gradient.  The whole block is ~12 % of the
@@ -79,14 +79,15 @@ struct ArmaModel {
             (-0.5 * kLog2Pi - 0.69314718055994530942 - theta * theta * 0.125) +
             (-kLogPi - 0.91629073187415506518 - fast_log(1.0 + q)) + s;
 #else
-        const double sigma = exp(s), sig2 = sigma * sigma, q = sig2 / 6.25;
+        // the oracle's statement order (oracle/smc_oracle.c::arma_split): host builds and the parity device build
+        const double sigma = fast_exp(s), sig2 = sigma * sigma, q = sig2 / 6.25;
         const double inv = 1.0 / sig2;
         const double cauchy_g = 2.0 * q / (1.0 + q);
         const bool sigma_ok = is_finite(sigma) && sigma > 0.0;
         A = (-0.5 * kLog2Pi - 2.3025850929940456840 - mu * mu / 200.0) +
             (-0.5 * kLog2Pi - 0.69314718055994530942 - beta * beta / 8.0) +
             (-0.5 * kLog2Pi - 0.69314718055994530942 - theta * theta / 8.0) +
-            (-kLogPi - 0.91629073187415506518 - log1p(q)) + s;
+            (-kLogPi - 0.91629073187415506518 - ref_log1p(q)) + s;
 #endif
         double ylag = y[0];
         double e = ylag - (mu + beta * mu);
@@ -108,7 +109,7 @@ struct ArmaModel {
         }
         B = -0.5 * T * kLog2Pi - T * s - 0.5 * S * inv;
         if (!sigma_ok) A = neg_inf();
-#if defined(__CUDA_ARCH__)
+#if SMCB_FAST_PATH
         g[0] = -mu * 0.01 + phi * (-Sm * inv);
 #else
         g[0] = -mu / 100.0 + phi * (-Sm * inv);
@@ -129,7 +130,7 @@ struct ArmaModel {
 // Device fast path for q = 1/2: with sg = Gamma^(-1/2) and r = rsqrt(|b|), aq = sg |b| r and aq / b = sg r sign(b): one
 // rsqrt instead of sqrt + divide (a few ulp apart from the host/oracle form).
 SMCB_HD void prm_prior_term(double b, double q, double ig, double sg, double& aq, double& dterm) {
-#if defined(__CUDA_ARCH__)
+#if SMCB_FAST_PATH
     if (q == 0.5) {
         const double ab = fabs(b), r = rsqrt(ab);
         aq = (ab == 0.0) ? 0.0 : sg * ab * r;
@@ -145,14 +146,14 @@ SMCB_HD void prm_prior_term(double b, double q, double ig, double sg, double& aq
 }
 // Gamma^-1 and Gamma^-1/2 from log Gamma; finite, positive Gamma <=> exp(gg) neither overflows nor underflows
 SMCB_HD void prm_gamma_terms(double gg, double& ig, double& sg, bool& ok) {
-#if defined(__CUDA_ARCH__)
+#if SMCB_FAST_PATH
     sg = fast_exp(-0.5 * gg);
     ig = sg * sg;
     ok = (gg > -745.13321910194122) && (gg < 709.78271289338397);
 #else
-    ig = exp(-gg);
+    ig = fast_exp(-gg);
     sg = 0.0;
-    const double Gam = exp(gg);
+    const double Gam = fast_exp(gg);
     ok = is_finite(Gam) && Gam > 0.0;
 #endif
 }
@@ -230,12 +231,12 @@ struct PrmModel {
         for (int j = 0; j < C; ++j) ydot += x[j + 1] * hdr[1 + j];
         double b = ydot - slam - hdr[12];
         // Stan's poisson_lpmf is -inf when lambda underflows to 0 with y > 0 (and when lambda = inf: slam = inf above)
-        if (exp(min_eta) == 0.0) {
+        if (fast_exp(min_eta) == 0.0) {
             for (int i = 0; i < NO; ++i) {
                 const double* row = rows + i * ROW;
                 double eta = x[0];
                 for (int j = 0; j < C; ++j) eta += x[j + 1] * row[j];
-                if (exp(eta) == 0.0 && row[11] > 0.0) b = neg_inf();
+                if (fast_exp(eta) == 0.0 && row[11] > 0.0) b = neg_inf();
             }
         }
         B = b;
@@ -378,6 +379,7 @@ struct PrmModelG {
         // every lane); lambda = inf gives slam = inf or, through a zero entry of Xt, NaN -> -inf as well
         // high word of kExpZero with the sign bit: a (slightly conservative) trigger, the slow path compares exactly
         if (__any_sync(kFull, neg_hi >= 0xc0874910u)) {
+            __syncwarp();
             bool hit = false;
             const double* pm = blk + YM + lane;
 #pragma unroll 1

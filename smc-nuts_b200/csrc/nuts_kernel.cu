@@ -118,6 +118,7 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
         //      executed by every lane (idle ones carry zeros) so that warp-wide tensor-core instructions stay legal.
         if (lane.phase != kIdle) lane.pre_eval(a);
         double A, B, g[M::NLOC];
+        if constexpr (G > 1) __syncwarp();   // the group models issue warp-wide mma.sync.aligned: reconverge explicitly
         model.eval(lane.xa, a.phi, A, B, g);
         lane.take_grad(g);
         if (lane.phase != kIdle) lane.post_eval(a, A, B);
@@ -200,9 +201,14 @@ static int launch_nuts(const Model* mdl, NutsArgs a, long long ws_bytes, cudaStr
     return check_launch("nuts_transition_kernel");
 }
 
-// Gaussian: tensor-core group kernel for D <= 104, one-lane-per-particle fallback above
+// Gaussian: tensor-core group kernel for D <= 104, one-lane-per-particle fallback above (SMCB_GAUSS_SCALAR=1 forces the
+// fallback: parity test of the two)
+static bool gauss_force_scalar() {
+    const char* e = getenv("SMCB_GAUSS_SCALAR");
+    return e && atoi(e) != 0;
+}
 #define SMCB_GAUSS_DISPATCH(D, CALL_G, CALL_PLAIN) \
-    ((D) <= 8 ? CALL_G(1) : (D) <= 16 ? CALL_G(2) : (D) <= 32 ? CALL_G(4) : (D) <= 64 ? CALL_G(8) : (D) <= 104 ? CALL_G(13) : CALL_PLAIN)
+    (gauss_force_scalar() ? CALL_PLAIN : (D) <= 8 ? CALL_G(1) : (D) <= 16 ? CALL_G(2) : (D) <= 32 ? CALL_G(4) : (D) <= 64 ? CALL_G(8) : (D) <= 104 ? CALL_G(13) : CALL_PLAIN)
 
 template <class M>
 static int launch_logp(const Model* mdl, const double* x, long long N, double phi, double* A, double* B, double* g,
@@ -221,6 +227,7 @@ using namespace smcb;
 extern "C" {
 
 int smcb_version(void) { return 100; }
+int smcb_build_flavour(void) { return SMCB_PARITY; }
 const char* smcb_last_error(void) { return last_error_ref().c_str(); }
 long long smcb_launch_count(void) { return g_launches.load(); }
 

@@ -316,7 +316,7 @@ struct Lane {
         ke0 = 0.5 * gsum(rr);
         A0 = A; B0 = B;
         const double H0 = lp - ke0;
-#if defined(__CUDA_ARCH__)
+#if SMCB_TABLE_MATH
         logu = H0 + fast_log(1.0 - rng.next());      // 1 - u is exact; table-driven log (common.cuh), <= 2.2e-16 absolute
 #else
         logu = H0 - (-log1p(-rng.next()));
@@ -448,7 +448,7 @@ struct Lane {
             if (!is_finite(lps)) lps = neg_inf();
             if (!is_finite(lp0)) lp0 = neg_inf();
             const double H1 = lps - ken, H0 = lp0 - ke0;
-            const double ratio = exp(H1 - H0);
+            const double ratio = fast_exp(H1 - H0);
             const double prob = (ratio < 1.) ? ratio : 1.;  // python min(1., ratio): nan -> 1.
             const double u = stream_uniform(a.seed, a.iteration, kStreamAccRej, a.particle0 + (uint64_t)pid, 0);
             if (u > prob || anyinf) {

@@ -518,6 +518,20 @@ __global__ void probe_dmma_kernel(int iters, double* sink) {
     if (s == 12345.678) sink[0] = s;
 }
 
+// One mma.m8n8k4 per warp on caller-supplied fragments (a[32], b[32], c[64] -> out[64]; lane l holds a[l], b[l],
+// c[2l], c[2l+1]): lets a test establish the rounding / association of the FP64 tensor-core instruction against an
+// exact CPU model.
+__global__ void debug_dmma_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                  const double* __restrict__ c, double* __restrict__ out, int nwarps) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
+    if (w >= nwarps) return;
+    double c0 = c[w * 64 + 2 * l], c1 = c[w * 64 + 2 * l + 1];
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a[w * 32 + l]), "d"(b[w * 32 + l]));
+    out[w * 64 + 2 * l] = c0;
+    out[w * 64 + 2 * l + 1] = c1;
+}
+
 static int reset_counter(void* ws, cudaStream_t st) {
     SMCB_CUDA(cudaMemsetAsync((char*)ws + (size_t)kRedMaxBlocks * kRedMaxVals * 8, 0, 8, st));
     return 0;
@@ -736,6 +750,12 @@ int smcb_probe_dmma(int blocks, int threads, int iters, double* out_sink, void* 
     SMCB_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && threads % 32 == 0 && iters > 0 && out_sink, "bad argument");
     probe_dmma_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, out_sink);
     return check_launch("probe_dmma_kernel");
+}
+
+int smcb_debug_dmma(const double* a, const double* b, const double* c, double* out, int nwarps, void* stream) {
+    SMCB_REQUIRE(a && b && c && out && nwarps > 0, "bad argument");
+    debug_dmma_kernel<<<(nwarps + 3) / 4, 128, 0, (cudaStream_t)stream>>>(a, b, c, out, nwarps);
+    return check_launch("debug_dmma_kernel");
 }
 
 int smcb_probe_fp64(int blocks, int threads, int iters, double* out_sink, void* stream) {

@@ -64,6 +64,8 @@ _SIGS = {
     "smcb_fast_log": [_vp, _ll, _vp, _vp],
     "smcb_probe_fp64": [_i, _i, _i, _vp, _vp],
     "smcb_probe_dmma": [_i, _i, _i, _vp, _vp],
+    "smcb_debug_dmma": [_vp, _vp, _vp, _vp, _i, _vp],
+    "smcb_build_flavour": [],
     "smcb_version": [],
     "smcb_last_error": [],
     "smcb_launch_count": [],
@@ -100,6 +102,28 @@ def lib():
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
         _LIB = L
     return _LIB
+
+
+PARITY_LIB_PATH = _PKG / "_lib" / "libsmcnuts_b200_parity.so"
+
+
+class use_library:
+    """Context manager for the parity tests: route the C-ABI calls of this process to another build of the library
+    (normally libsmcnuts_b200_parity.so).  Model handles are per library: create, use and drop models inside the block."""
+
+    def __init__(self, path):
+        self.path = Path(path)
+
+    def __enter__(self):
+        global _LIB, LIB_PATH
+        self._saved = (_LIB, LIB_PATH)
+        _LIB, LIB_PATH = None, self.path
+        return lib()
+
+    def __exit__(self, *exc):
+        global _LIB, LIB_PATH
+        _LIB, LIB_PATH = self._saved
+        return False
 
 
 def call(name, *args):

@@ -199,7 +199,11 @@ def golden_models():
 
 
 # ------------------------------------------------------------------ B. single NUTS transitions
-def golden_nuts():
+def golden_nuts(devmath=False):
+    """devmath=True: the duck-typed target (and nothing else) evaluates exp / log with the table-driven device
+    algorithms (oracle/devmath.h) -> nuts_devmath.npz, the fixtures the PARITY device build must reproduce exactly."""
+    from oracle import smc_oracle as _O
+    _O.lib().orc_set_devmath(int(devmath))
     cases = [
         # name, target, kwargs, eps, phi, centre, spread, P, iteration
         ("arma", "arma", {}, 0.01, 1.0, [0.0068, 0.957, -0.034, np.log(0.1666)], 0.02, 96, 3),
@@ -238,7 +242,8 @@ def golden_nuts():
             out[f"{name}_{k}"] = np.asarray(v)
         print(f"nuts {name}: leapfrogs min/mean/max = {nleap.min()}/{nleap.mean():.1f}/{nleap.max()}, "
               f"moved {np.mean(np.any(xn != x0, axis=1)):.2f}, accepted {acc.mean():.2f}")
-    np.savez_compressed(OUT / "nuts.npz", **out)
+    np.savez_compressed(OUT / ("nuts_devmath.npz" if devmath else "nuts.npz"), **out)
+    _O.lib().orc_set_devmath(0)
 
 
 # ------------------------------------------------------------------ C. rng.choice == cdf/searchsorted
@@ -387,6 +392,8 @@ if __name__ == "__main__":
         golden_models()
     if "nuts" in which:
         golden_nuts()
+    if "nuts_devmath" in which or not sys.argv[1:]:
+        golden_nuts(devmath=True)
     if "choice" in which:
         golden_choice()
     if "lkernel" in which:

@@ -8,20 +8,21 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
-_LIB = None
+_LIBS = {}
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        so = HERE / "_hostsim.so"
+def lib(devmath=False):
+    """devmath=True: the build with -DSMCB_DEVMATH, in which exp / log are the table-driven device algorithms restated
+    for the host (csrc/common.cuh) -- the CPU twin of the parity device build (libsmcnuts_b200_parity.so)."""
+    if devmath not in _LIBS:
+        so = HERE / ("_hostsim_devmath.so" if devmath else "_hostsim.so")
         src = HERE / "hostsim.cpp"
         hdrs = list((HERE.parents[1] / "smc-nuts_b200" / "csrc").glob("*.cuh"))
         if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in [src] + hdrs):
             subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                            "-o", str(so), str(src)], check=True)
-        _LIB = ctypes.CDLL(str(so))
-    return _LIB
+                            *(["-DSMCB_DEVMATH=1"] if devmath else []), "-o", str(so), str(src)], check=True)
+        _LIBS[devmath] = ctypes.CDLL(str(so))
+    return _LIBS[devmath]
 
 
 _LIB_SIMT = None
@@ -60,7 +61,7 @@ def pack_model(name, np_target):
 
 
 def nuts(name, np_target, x, r, eps, phi, max_depth=10, accrej=False, seed=0, iteration=0, particle0=0, lanes=32,
-         carry=None, want_grad=False):
+         carry=None, want_grad=False, devmath=False):
     kind, data, dim, T, q = pack_model(name, np_target)
     x = np.ascontiguousarray(x, dtype=np.float64)
     r = np.ascontiguousarray(r, dtype=np.float64)
@@ -73,7 +74,7 @@ def nuts(name, np_target, x, r, eps, phi, max_depth=10, accrej=False, seed=0, it
     cA, cB, cg = (np.ascontiguousarray(c, dtype=np.float64) for c in carry) if carry is not None else (None, None, None)
     P = lambda a: a.ctypes.data_as(_dp) if a is not None else None  # noqa: E731
     I = lambda a: a.ctypes.data_as(_ip)  # noqa: E731
-    lib().hostsim_nuts(ctypes.c_int(kind), P(data), ctypes.c_int(data.size), ctypes.c_int(dim), ctypes.c_int(T),
+    lib(devmath).hostsim_nuts(ctypes.c_int(kind), P(data), ctypes.c_int(data.size), ctypes.c_int(dim), ctypes.c_int(T),
                        ctypes.c_double(q), P(x), P(r), ctypes.c_longlong(N), ctypes.c_double(eps), ctypes.c_double(phi),
                        ctypes.c_int(max_depth), ctypes.c_int(int(accrej)), ctypes.c_ulonglong(seed),
                        ctypes.c_uint(iteration), ctypes.c_ulonglong(particle0), P(o["x_new"]), P(o["r_new"]),

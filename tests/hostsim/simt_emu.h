@@ -182,6 +182,7 @@ inline unsigned long long __shfl_sync(unsigned mask, unsigned long long v, int s
 inline unsigned __ballot_sync(unsigned mask, bool pred) { return simt_emu::ballot(mask, pred); }
 inline bool __any_sync(unsigned mask, bool pred) { return simt_emu::ballot(mask, pred) != 0u; }
 inline bool __all_sync(unsigned mask, bool pred) { return simt_emu::ballot(mask, pred) == mask; }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)simt_emu::ballot(mask, true); }
 inline int __double2hiint(double v) {
     uint64_t b;
     std::memcpy(&b, &v, 8);

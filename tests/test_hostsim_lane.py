@@ -36,9 +36,12 @@ def test_lane_matches_reference_golden(golden, case, accrej):
 @pytest.mark.parametrize("tname,kw,eps,N", [("arma", {}, 0.01, 400), ("PRMwCD", {}, 0.01, 40),
                                             ("gauss", {"dim": 8}, 0.1, 300), ("gauss", {"dim": 33}, 0.15, 60)])
 @pytest.mark.parametrize("lanes", [1, 32])
-def test_lane_matches_c_oracle_bitwise(tname, kw, eps, N, lanes):
+@pytest.mark.parametrize("devmath", [False, True])
+def test_lane_matches_c_oracle_bitwise(tname, kw, eps, N, lanes, devmath):
     """Same compiler flags, same expression order -> the lane machine must reproduce the recursive C
-    oracle bit for bit (x', r', split log-densities, tree sizes, depths, MH outcomes)."""
+    oracle bit for bit (x', r', split log-densities, tree sizes, depths, MH outcomes).  devmath: both sides evaluate
+    exp / log with the kernels' table-driven algorithms (csrc/common.cuh with -DSMCB_DEVMATH vs oracle/devmath.h) --
+    the CPU twin of the parity device build that tests/test_gpu_parity_build.py checks on the B200."""
     t = O.COracleTarget(tname, **kw)
     rng = np.random.default_rng(5)
     x = rng.normal(size=(N, t.dim)) * 0.3
@@ -49,8 +52,9 @@ def test_lane_matches_c_oracle_bitwise(tname, kw, eps, N, lanes):
     r = rng.normal(size=(N, t.dim))
     for accrej in (False, True):
         for phi in (1.0, 0.2):
-            ref = t.nuts_batch(x, r, eps, phi, 10, seed=77, iteration=3, particle0=1000, accrej=accrej)
-            o = sim.nuts(tname, t.np_target, x, r, eps, phi, 10, accrej, 77, 3, 1000, lanes=lanes)
+            with O.devmath(devmath):
+                ref = t.nuts_batch(x, r, eps, phi, 10, seed=77, iteration=3, particle0=1000, accrej=accrej)
+            o = sim.nuts(tname, t.np_target, x, r, eps, phi, 10, accrej, 77, 3, 1000, lanes=lanes, devmath=devmath)
             assert np.array_equal(o["n_leapfrog"], ref["n_leapfrog"])
             assert np.array_equal(o["depth"], ref["depth"])
             assert np.array_equal(o["accepted"], ref["accepted"])

@@ -210,3 +210,54 @@ def test_oracle_densities_equal_an_independent_scipy_restatement_of_the_stan_pro
         G = t.logpdfgrad(X, phi)
         for x, gr in zip(X[:4], G[:4]):
             np.testing.assert_allclose(gr, num_grad(lambda v: prm_logp(v, phi), x), rtol=2e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["arma", "arma_tempered", "arma_prior", "PRMwCD", "PRMwCD_tempered", "gauss8", "gauss100"])
+def test_c_nuts_devmath_mode_matches_reference_devmath_fixtures(golden, case):
+    """tests/golden/nuts_devmath.npz: the UNMODIFIED reference transitions with the devmath target (exp / log = the
+    kernels' table-driven algorithms, oracle/devmath.h).  The C oracle in the same mode reproduces them exactly; these
+    are the fixtures the parity device build is held to on the GPU (tests/test_gpu_parity_build.py)."""
+    g = golden("nuts_devmath")
+    tname, kw = case.split("_")[0], {}
+    if tname.startswith("gauss"):
+        kw, tname = {"dim": int(tname[5:])}, "gauss"
+    t = O.COracleTarget(tname, **kw)
+    x0, r0 = g[f"{case}_x0"], g[f"{case}_r0"]
+    eps, phi, it, seed = float(g[f"{case}_eps"]), float(g[f"{case}_phi"]), int(g[f"{case}_iteration"]), int(g[f"{case}_seed"])
+    with O.devmath():
+        o = t.nuts_batch(x0, r0, eps, phi, 10, seed=seed, iteration=it, accrej=True)
+    assert np.array_equal(o["n_leapfrog"], g[f"{case}_n_leapfrog"])
+    acc = g[f"{case}_accepted"]
+    assert np.array_equal(o["accepted"].astype(bool), acc)
+    np.testing.assert_allclose(o["x_new"][acc], g[f"{case}_x_new"][acc], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(o["r_new"][acc], g[f"{case}_r_new"][acc], rtol=1e-12, atol=1e-14)
+
+
+def test_devmath_tables_and_density_agreement():
+    """oracle/devmath_tables.h is what its generator writes, equals the tables of csrc/common.cuh, and the devmath mode
+    changes the model densities by rounding only (<= 1e-13 relative on A, B and the gradient)."""
+    import re
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root / "oracle"))
+    import gen_devmath_tables as G
+    assert (root / "oracle" / "devmath_tables.h").read_text() == G.render()
+    text = (root / "smc-nuts_b200" / "csrc" / "common.cuh").read_text()
+
+    def table(name):
+        body = re.search(name + r"\[\d+\] = \{(.*?)\};", text, re.S).group(1)
+        return [float.fromhex(v) for v in re.findall(r"-?0x[0-9a-fA-F.]+p[+-]?\d+", body)]
+    exp_t, inv_c, log_c = G.tables()
+    assert table("kExpT") == exp_t and table("kLogInvC") == inv_c and table("kLogC") == log_c
+    rng = np.random.default_rng(2)
+    for name in ("arma", "PRMwCD"):
+        t = O.COracleTarget(name)
+        x = rng.normal(size=(200, t.dim)) * 0.5
+        a = t.split(x)
+        with O.devmath():
+            b = t.split(x)
+        for u, v in zip(a, b):
+            fin = np.isfinite(u) & np.isfinite(v)
+            assert np.array_equal(np.isfinite(u), np.isfinite(v))
+            np.testing.assert_allclose(u[fin], v[fin], rtol=1e-13, atol=1e-13)
