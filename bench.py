@@ -6,7 +6,11 @@
 
 A "step" is one SMC iteration (normalise -> estimate -> ESS -> resample -> NUTS propose -> temper -> reweight,
 /root/reference/smcnuts/smc_sampler.py:109-140) over the whole particle set.  Default workload is
-BASELINE.json configs[1]: arma, N = 2^20 particles per GPU, forward-proposal L-kernel, fp64.  Prints ONE JSON line.
+BASELINE.json configs[1]: arma, N = 2^20 particles IN TOTAL (sharded over the N GPUs: strong scaling, as the metric
+"... at N=2^20 particles, 1/2/4/8 B200" states), forward-proposal L-kernel, fp64.  `--scaling weak` keeps 2^20 particles
+per GPU instead.  Prints ONE JSON line.  With more than one rank the warm-up also runs a small sharded case that rank 0
+repeats unsharded: `sharded_check` reports whether the leapfrog counts are identical and the largest relative
+difference of the estimates.
 
 `value`  : leapfrog gradient evaluations per second over the K timed steps, inputs resident in HBM,
            timed with CUDA events between barriers, max over ranks.
@@ -45,6 +49,14 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the NUTS kernel, from `ncu --set full` captures under
+# profiles/ (keyed by workload and particles per GPU); not measured live -> "traffic_live": false in the line
+TRAFFIC = {
+    ("arma", 1 << 20): (364820992, "profiles/r1b_nuts_arma_details.csv: 108.7 MB read + 256.2 MB written (algorithmic: 184 MB "
+                                    "of particle rows and scalars; the rest is the per-lane tree workspace leaving L2)"),
+}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -76,15 +88,36 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def workload_name(workload, model, n_global, lk, temp, eps, resampling):
+    cfg = {"arma": 1, "PRMwCD": 2, "gauss": 3}[workload]
+    return (f"{workload}: {model} N={n_global} particles in total, {lk} tempering={temp} eps={eps} resampling={resampling}, "
+            f"BASELINE.json configs[{cfg}]")
+
+
 def run_reference(args):
     """Reference arm: the oracle port of the SMC iteration on the host cores (all threads)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import smc_oracle as O
-    model, kw, eps, lk, temp, _, _ = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    n = 1 << args.ref_log2n
+    os.environ["OMP_NUM_THREADS"] = str(cores)     # torchrun exports OMP_NUM_THREADS=1 to its workers
+    from oracle import smc_oracle as O
+    model, kw, eps, lk, temp, log2n, _ = WORKLOADS[args.workload]
+    n_full_log2 = args.log2n or log2n
+    if args.ref_log2n is not None:
+        ref_log2n = args.ref_log2n
+    else:
+        # the largest power-of-two sample (up to the whole workload) whose W + K iterations fit ~2 minutes on this host:
+        # calibrated on two iterations of a small sample
+        cal_log2n = 13 if args.workload == "arma" else 9
+        cal = O.OracleSMC(2, 1 << cal_log2n, model, eps, lk, temp, seed=10, nthreads=cores, target_kw=kw, save_history=False).init()
+        c0 = time.perf_counter()
+        cal.step(0); cal.step(1)
+        per_particle_step = (time.perf_counter() - c0) / 2 / (1 << cal_log2n)
+        ref_log2n = cal_log2n
+        while ref_log2n < n_full_log2 and per_particle_step * (1 << (ref_log2n + 1)) * (args.warmup + args.steps) <= 120.0:
+            ref_log2n += 1
+    n = 1 << ref_log2n
     smc = O.OracleSMC(args.warmup + args.steps, n, model, eps, lk, temp, seed=10, nthreads=cores, target_kw=kw,
                       save_history=False).init()
     for k in range(args.warmup):
@@ -95,13 +128,16 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     lf = int(smc.n_leapfrog[args.warmup:].sum())
     val = lf / dt
-    sample = f"{n} particles x {args.steps} SMC iterations (of the 2^20-particle workload), oracle C port of NUTS + numpy weights"
+    n_full = 1 << (args.log2n or log2n)
+    sample = (f"{n} of the {n_full} particles x {args.steps} SMC iterations, oracle C port of NUTS (OpenMP, {cores} threads) "
+              "+ numpy weights/resampling")
     print(json.dumps({
         "impl": "reference", "metric": "leapfrog_grad_evals_per_s", "value": val, "unit": "grad-evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "smc_iters_per_s": args.steps / dt,
-        "config": {"workload": f"{args.workload}: {model} N={n} (bounded sample) {lk} tempering={temp} eps={eps}", "particles": n},
+        "config": {"workload": workload_name(args.workload, model, n_full, lk, temp, eps, "multinomial"),
+                   "particles_global": n_full, "particles_timed": n, "dim": smc.D},
         "cpu_baseline": {"value": val, "unit": "grad-evals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "grad-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = pure Python + BridgeStan (not installable offline); timed here: its C/numpy oracle port, all host cores",
@@ -226,7 +262,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="arma", choices=sorted(WORKLOADS) + ["micro"])
     ap.add_argument("--log2n", type=int, default=None, help="log2 particles PER GPU (default: the workload's)")
-    ap.add_argument("--ref-log2n", type=int, default=16, help="particles of the bounded CPU reference sample")
+    ap.add_argument("--ref-log2n", type=int, default=None, help="particles of the CPU reference arm (default: the largest "
+                    "power of two, up to the whole workload, that keeps the run within ~2 minutes on this host)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the workload's particle count in total over all GPUs (default); weak: per GPU")
     ap.add_argument("--cpu-log2n", type=int, default=18, help="particles of the bounded cpu_baseline sample")
     ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "systematic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -253,8 +292,12 @@ def main():
 
     model, kw, eps, lk, temp, log2n, flop_per_eval = WORKLOADS[args.workload]
     log2n = args.log2n or log2n
-    n_local = 1 << log2n
-    N = n_local * world
+    if args.scaling == "strong":
+        N = 1 << log2n
+        n_local = N // world
+    else:
+        n_local = 1 << log2n
+        N = n_local * world
     W, K = args.warmup, args.steps
     m = make_model(model, **kw)
     D = m.dim
@@ -273,6 +316,33 @@ def main():
         a.record(); _cabi.call("smcb_probe_fp64", pb, pt, pi, dev.ptr(sink), dev.stream_ptr()); b.record()
         torch.cuda.synchronize()
         peak = max(peak, pb * pt * pi * 16 / (a.elapsed_time(b) * 1e-3))
+
+    # ---------------------------------------------------------------- sharded correctness (part of the warm-up)
+    sharded_check = None
+    if world > 1:
+        from smcnuts.parallel import ShardContext
+
+        def small(shard):
+            mm = make_model(model, **({"dim": 8} if model == "gauss" else kw))
+            s_ = SMCSampler(K=4, N=1 << 14, target=mm, step_size=eps, sample_proposal=StdNormal(mm.dim),
+                            momentum_proposal=StdNormal(mm.dim), lkernel=lk, tempering=temp, rng=10,
+                            resampling=args.resampling, shard=shard)
+            s_.sample(show_progress=False)
+            return s_
+        sh_run = small(None)
+        if rank == 0:
+            one = small(ShardContext(enabled=False))
+            with np.errstate(all="ignore"):
+                rel = max(float(np.max(np.abs(sh_run.mean_estimate - one.mean_estimate) / (np.abs(one.mean_estimate) + 1e-300))),
+                          float(np.max(np.abs(sh_run.ess - one.ess) / one.ess)),
+                          float(np.max(np.abs(sh_run.log_likelihood - one.log_likelihood) / np.abs(one.log_likelihood))))
+            sharded_check = {"case": f"{model} N=16384 K=4 {lk} resampling={args.resampling}, {world} ranks vs 1 GPU (rank 0)",
+                             "leapfrogs_equal": bool(np.array_equal(sh_run.leapfrogs, one.leapfrogs)),
+                             "resampled_equal": list(sh_run.resampled) == list(one.resampled),
+                             "max_rel_err": rel}
+            del one
+        del sh_run
+        barrier()
 
     # ---------------------------------------------------------------- device-resident run: W warm-up + K timed steps
     smc = SMCSampler(K=W + K, N=N, target=m, step_size=eps, sample_proposal=StdNormal(D), momentum_proposal=StdNormal(D),
@@ -354,16 +424,22 @@ def main():
     if rank == 0:
         evals = lf_rank + K * n_local                      # leapfrogs + the initial evaluation of every transition
         achieved = evals * flop_per_eval / nuts_dt
+        extra_roofline = {"frac_vs_nominal_37.2": achieved / 37.2e12}
+        if args.workload == "PRMwCD":
+            # SURVEY 8d's algorithmic count: 5.2 kFLOP + 100 exp (one special each); the headline `frac` above counts the
+            # exp expansion (12 FP64 instructions each) because the FP64 pipe executes it
+            extra_roofline.update({"frac_algorithmic": evals * 5200.0 / nuts_dt / peak, "flop_per_eval_algorithmic": 5200.0,
+                                   "note": "frac counts 7.6 k FP64-pipe FLOP-slots per evaluation (exp expanded); "
+                                           "frac_algorithmic counts 5.2 kFLOP + 100 exp as one each"})
         hist = (K + W + 1) * n_local * (D + 1) * 8 if smc.save_history else 0
         ws_bytes = n_local * 8 * (4 * D + 12)
         line = {
             "metric": "leapfrog_grad_evals_per_s", "value": value, "unit": "grad-evals/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "smc_iters_per_s": K / dt,
             "leapfrogs_per_particle_per_step": lf_total / (K * N),
-            "config": {"workload": f"{args.workload}: {model} N={n_local}/GPU (global {N}) {lk} tempering={temp} eps={eps} "
-                                   f"resampling={args.resampling}, BASELINE.json configs[{ {'arma': 1, 'PRMwCD': 2, 'gauss': 3}[args.workload] }]",
+            "config": {"workload": workload_name(args.workload, model, N, lk, temp, eps, args.resampling),
                        "particles_per_gpu": n_local, "particles_global": N, "dim": D,
                        "l2": f"per-step working set {ws_bytes / 1e6:.0f} MB of particle arrays (> 126 MB L2 from N=2^20, D>=4: "
                              f"x, r, x_new, r_new + 12 per-particle scalars), inputs larger than L2; no explicit flush"},
@@ -373,13 +449,14 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "kernel": "nuts_transition_kernel", "achieved": achieved / 1e12, "peak": peak / 1e12,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 364820992 if (args.workload == "arma" and log2n == 20) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch (108.7 MB + 256.2 MB), ncu "
-                                           "--set full capture profiles/r1b_nuts_arma_details.csv (algorithmic: 184 MB of "
-                                           "particle rows and scalars; the rest is the per-lane tree workspace leaving L2)",
+                         "traffic": TRAFFIC.get((args.workload, n_local), (None, None))[0],
+                         "traffic_live": False,
+                         "traffic_source": TRAFFIC.get((args.workload, n_local), (None, "no ncu capture at this shard size"))[1],
+                         "algorithmic_bytes": n_local * 8 * (4 * D + 9) + n_local * 12,
                          "peak_source": "measured live: smcb_probe_fp64 DFMA loop on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                          "flop_per_eval": flop_per_eval, "evals": evals, "kernel_s": nuts_dt,
-                         "kernel_share_of_step": nuts_dt / dt},
+                         "kernel_share_of_step": nuts_dt / dt, **extra_roofline},
+            "sharded_check": sharded_check,
             "cpu_baseline": cpu,
             "clocks": clk,
             "history_bytes": hist,

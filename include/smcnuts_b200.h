@@ -118,6 +118,25 @@ int smcb_tempering_arrays(const double* A, const double* B, double phi_old, long
 int smcb_ess_multi_phi(const double* loglik, const double* logpri, const double* c, long long N,
                        const double* phis, int m, double* out, void* workspace, void* stream);
 
+/* Device-resident bisection (adaptive_tempering.py:58-63: phi = 1 if ESS(1) >= alpha N else scipy.optimize.bisect(f,
+ * old_phi, 1)).  The bracket, the speculative candidate temperatures of the next tree levels and the outcome live in
+ * an opaque device state (smcb_bisect_state_bytes() bytes); the host enqueues init, then smcb_bisect_passes() rounds of
+ * eval (+ an all-gather of the out arrays when sharded) + step, then read -- no host round trip in between; kernels
+ * are no-ops once the state is final.  target = alpha * N_total.
+ *   eval: out[smcb_bisect_max_candidates()][3] = (max, sum exp, sum exp^2) of phi*loglik + logpri - c per candidate,
+ *         formed from the split log density (A, B) on the fly (adaptive_tempering.py:38-54)
+ *   step: triples[P][max_candidates][3] in rank order -> f = ESS - target, walk, next candidates
+ *   read: out4 = (phi, status, iterations, abscissa of a NaN); status 1 ok, 2 NaN value, 3 same-sign bracket, 4 no
+ *         convergence (scipy's ValueError / RuntimeError cases) */
+long long smcb_bisect_state_bytes(void);
+int smcb_bisect_max_candidates(void);
+int smcb_bisect_passes(void);
+int smcb_bisect_init(void* state, double xa, double xb, double target, void* stream);
+int smcb_bisect_eval(const double* A, const double* B, double phi_old, long long N, const void* state, double* out,
+                     void* workspace, void* stream);
+int smcb_bisect_step(const double* triples, int P, void* state, void* stream);
+int smcb_bisect_read(const void* state, double* out4, void* stream);
+
 /* ---- resampling (samples.py:116-146; `rng.choice` == searchsorted(cumsum(wn)/total, u, 'right')) */
 long long smcb_scan_workspace_bytes(long long N);
 /* cdf = inclusive_scan(wn) / total; total -> total_out[0].  offset_in (nullable, device) is added to every
@@ -142,6 +161,17 @@ int smcb_resample_systematic(const double* cdf, long long N, double u0, const do
 int smcb_resample_systematic_push(const double* cdf, long long N, double u0, long long j0, long long M_total,
                                   long long M, const double* x, int D, double* const* peer_out, long long rows_per_rank,
                                   int64_t* idx, void* workspace, void* stream);
+/* Sharded MULTINOMIAL resampling, owner-push: slot j of the global output draws u_j from Philox stream (seed, iteration,
+ * stream_id, particle = j); the rank whose cdf segment holds u_j (ends[q-1] <= u_j < ends[q]; ends[P] = last cdf value of
+ * every rank, all-gathered) searches its local cdf and stores the ancestor's row into peer_out[j / rows_per_rank] and the
+ * global ancestor index (particle0 + local index) into peer_idx[...] (nullable).  Replaces samples.py:138-140 across
+ * GPUs without gathering the cdf and without any all-to-all. */
+int smcb_resample_multinomial_push(const double* cdf, long long n, const double* ends, int rank, int P, uint64_t seed,
+                                   uint32_t iteration, uint32_t stream_id, long long N_total, long long particle0,
+                                   const double* x, int D, double* const* peer_out, int64_t* const* peer_idx,
+                                   long long rows_per_rank, void* stream);
+/* out2 = (sum of totals[q] for q < rank, sum of all totals), sequential in rank order: the global-scan offsets */
+int smcb_rank_offsets(const double* totals, int P, int rank, double* out2, void* stream);
 /* peer-visible device buffers (CUDA IPC): alloc on the owner (64-byte handle out), open on the other ranks */
 int smcb_peer_alloc(long long bytes, void** ptr, void* handle64);
 int smcb_peer_open(const void* handle64, void** ptr);

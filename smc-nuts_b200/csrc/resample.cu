@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "capi.cuh"
+#include "philox.cuh"
 
 namespace smcb {
 
@@ -264,11 +265,72 @@ __global__ void __launch_bounds__(256) resample_systematic_fused_kernel(const do
     }
 }
 
+// Sharded multinomial resampling, owner-push formulation (samples.py:138-140 over P GPUs).
+// Output slot j of the GLOBAL particle set draws u_j from the Philox resampling stream keyed by j, so every rank can
+// regenerate every uniform.  The rank whose cdf segment contains u_j (ends[q-1] <= u_j < ends[q], ends = last cdf value of
+// each rank) is the only one that can resolve the ancestor: it searches its local segment and stores the ancestor's row
+// straight into the buffer of the rank that owns slot j (peer store over NVLink), together with the global ancestor
+// index.  No cdf all-gather, no sort / bincount, no request-response all-to-all: N Philox draws + compares per rank
+// (cheap, ~60 integer instructions each), then only the hits do memory work.
+__global__ void __launch_bounds__(256) resample_multinomial_push_kernel(
+    const double* __restrict__ cdf, long long n, const double* __restrict__ ends, int rank, int P, uint64_t seed,
+    uint32_t iteration, uint32_t stream_id, long long N_total, long long particle0, const double* __restrict__ x, int D,
+    double* const* __restrict__ peer_out, int64_t* const* __restrict__ peer_idx, long long rows_per_rank) {
+    const double lo = rank == 0 ? neg_inf() : ends[rank - 1];
+    const double hi = rank == P - 1 ? -neg_inf() : ends[rank];
+    const bool vec2 = (D % 2 == 0) && (((uintptr_t)x) % 16 == 0);
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < N_total; j += (long long)gridDim.x * blockDim.x) {
+        const double u = stream_uniform(seed, iteration, stream_id, (uint64_t)j, 0);
+        if (!(u >= lo && u < hi)) continue;
+        const long long a = upper_bound(cdf, n, u);
+        const long long dst = j / rows_per_rank, slot = j - dst * rows_per_rank;
+        const double* src = x + a * D;
+        double* out = peer_out[dst] + slot * D;
+        if (vec2) {
+            for (int d = 0; d < D; d += 2) *reinterpret_cast<double2*>(out + d) = *reinterpret_cast<const double2*>(src + d);
+        } else {
+            for (int d = 0; d < D; ++d) out[d] = src[d];
+        }
+        if (peer_idx) peer_idx[dst][slot] = particle0 + a;
+    }
+}
+
+// exclusive offset of this rank and the global total from the all-gathered rank totals (sequential fp64 sum in rank
+// order: identical on every rank) -- keeps the global scan free of host round trips
+__global__ void rank_offsets_kernel(const double* __restrict__ totals, int P, int rank, double* __restrict__ out2) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double acc = 0.0, off = 0.0;
+        for (int q = 0; q < P; ++q) {
+            if (q == rank) off = acc;
+            acc += totals[q];
+        }
+        out2[0] = off;
+        out2[1] = acc;
+    }
+}
+
 }  // namespace smcb
 
 using namespace smcb;
 
 extern "C" {
+
+int smcb_rank_offsets(const double* totals, int P, int rank, double* out2, void* stream) {
+    SMCB_REQUIRE(totals && out2 && P >= 1 && rank >= 0 && rank < P, "bad argument");
+    rank_offsets_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(totals, P, rank, out2);
+    return check_launch("rank_offsets_kernel");
+}
+
+int smcb_resample_multinomial_push(const double* cdf, long long n, const double* ends, int rank, int P, uint64_t seed,
+                                   uint32_t iteration, uint32_t stream_id, long long N_total, long long particle0,
+                                   const double* x, int D, double* const* peer_out, int64_t* const* peer_idx,
+                                   long long rows_per_rank, void* stream) {
+    SMCB_REQUIRE(cdf && ends && x && peer_out && n >= 1 && P >= 1 && rank >= 0 && rank < P && N_total >= 1 && D >= 1 &&
+                     rows_per_rank >= 1, "bad argument");
+    resample_multinomial_push_kernel<<<stride_grid(N_total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        cdf, n, ends, rank, P, seed, iteration, stream_id, N_total, particle0, x, D, peer_out, peer_idx, rows_per_rank);
+    return check_launch("resample_multinomial_push_kernel");
+}
 
 long long smcb_scan_workspace_bytes(long long N) {
     const long long ntiles = (N + kTile - 1) / kTile;

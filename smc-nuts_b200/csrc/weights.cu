@@ -3,6 +3,7 @@
 //
 // All are grid-stride over particles with the grid a multiple of the SM count; reductions finish in a
 // single launch ("last block reduces the per-block partials in a fixed order" -> deterministic).
+#include "bisect.cuh"
 #include "capi.cuh"
 #include "philox.cuh"
 
@@ -335,6 +336,63 @@ __global__ void __launch_bounds__(kRedThreads) ess_multi_phi_kernel(const double
             if (j < m) lse_push(v[j], (ph[j] * ll + pri) - cc);  // adaptive_tempering.py:43 (same association as numpy)
     }
     lse_block_finish<NV>(v, ws, out, m);
+}
+
+// ---- device-resident bisection (bisect.cuh): candidates come from, and results go back into, a BisectState in
+//      device memory; every kernel is a no-op once the state has left kBisectRunning, so the host can enqueue the
+//      whole fixed schedule of passes without looking at intermediate results.
+__global__ void bisect_init_kernel(BisectState* s, double xa, double xb, double target) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        bisect_init(*s, xa, xb, target, 2e-12, 8.881784197001252e-16, 100);   // scipy.optimize.bisect defaults
+}
+
+// objective pass straight from the split log density: logpri = A, loglik = (A + B) - A, c = A + phi_old B with the
+// -inf failure mapping (adaptive_tempering.py:38-43, samples.py:207) formed on the fly -- 16 bytes read per particle,
+// nothing written.  out[kBisectMaxCand][3] (unused candidates: empty states).
+__global__ void __launch_bounds__(kRedThreads) bisect_eval_kernel(const double* __restrict__ A,
+                                                                   const double* __restrict__ B, double phi_old,
+                                                                   long long N, const BisectState* s, double* out,
+                                                                   double* ws) {
+    if (s->status != kBisectRunning) return;
+    constexpr int NV = kBisectMaxCand;
+    const int m = s->n_cand;
+    Lse v[NV];
+    double ph[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { v[j] = lse_empty(); ph[j] = (j < m) ? s->cand[j] : 0.0; }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double a = A[i], b = B[i];
+        const double pri = map_lp(a + 0.0 * b);
+        const double ll = map_lp(a + b) - pri;
+        const double cc = map_lp(a + phi_old * b);
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            if (j < m) lse_push(v[j], (ph[j] * ll + pri) - cc);
+    }
+    lse_block_finish<NV>(v, ws, out, NV);
+}
+
+// merge the P rank states of every candidate (rank order), f = ESS - target, walk the tree, prepare the next pass
+__global__ void bisect_step_kernel(const double* __restrict__ triples, int P, BisectState* s) {
+    __shared__ double f[kBisectMaxCand];
+    if (s->status != kBisectRunning) return;
+    const int j = threadIdx.x;
+    if (j < kBisectMaxCand) {
+        Lse r = lse_empty();
+        for (int p = 0; p < P; ++p) {
+            const double* t = triples + ((size_t)p * kBisectMaxCand + j) * 3;
+            r = lse_merge(r, Lse{t[0], t[1], t[2]});
+        }
+        f[j] = (r.s1 * r.s1) / r.s2 - s->target;     // adaptive_tempering.py:54-56
+    }
+    __syncthreads();
+    if (j == 0) bisect_advance(*s, f);
+}
+
+__global__ void bisect_read_kernel(const BisectState* s, double* out4) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        out4[0] = s->result; out4[1] = (double)s->status; out4[2] = (double)s->iterations; out4[3] = s->nan_at;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ weighted moments
@@ -701,6 +759,38 @@ int smcb_ess_multi_phi(const double* loglik, const double* logpri, const double*
     else if (m <= 8) ess_multi_phi_kernel<8><<<grid, kRedThreads, 0, st>>>(loglik, logpri, c, N, phis, m, out, (double*)workspace);
     else ess_multi_phi_kernel<16><<<grid, kRedThreads, 0, st>>>(loglik, logpri, c, N, phis, m, out, (double*)workspace);
     return check_launch("ess_multi_phi_kernel");
+}
+
+long long smcb_bisect_state_bytes(void) { return (long long)((sizeof(BisectState) + 255) / 256 * 256); }
+int smcb_bisect_max_candidates(void) { return kBisectMaxCand; }
+int smcb_bisect_passes(void) { return kBisectPasses; }
+
+int smcb_bisect_init(void* state, double xa, double xb, double target, void* stream) {
+    SMCB_REQUIRE(state, "bad argument");
+    bisect_init_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((BisectState*)state, xa, xb, target);
+    return check_launch("bisect_init_kernel");
+}
+
+int smcb_bisect_eval(const double* A, const double* B, double phi_old, long long N, const void* state, double* out,
+                     void* workspace, void* stream) {
+    SMCB_REQUIRE(A && B && state && out && workspace && N >= 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (reset_counter(workspace, st)) return -1;
+    bisect_eval_kernel<<<stride_grid(N, kRedThreads * 2, 4), kRedThreads, 0, st>>>(A, B, phi_old, N, (const BisectState*)state,
+                                                                                  out, (double*)workspace);
+    return check_launch("bisect_eval_kernel");
+}
+
+int smcb_bisect_step(const double* triples, int P, void* state, void* stream) {
+    SMCB_REQUIRE(triples && state && P >= 1, "bad argument");
+    bisect_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(triples, P, (BisectState*)state);
+    return check_launch("bisect_step_kernel");
+}
+
+int smcb_bisect_read(const void* state, double* out4, void* stream) {
+    SMCB_REQUIRE(state && out4, "bad argument");
+    bisect_read_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const BisectState*)state, out4);
+    return check_launch("bisect_read_kernel");
 }
 
 int smcb_weighted_moment(const double* x, const double* wn, long long N, int D, int constrain, const double* center,

@@ -42,12 +42,21 @@ _SIGS = {
     "smcb_normalise": [_vp, _ll, _vp, _vp, _vp],
     "smcb_tempering_arrays": [_vp, _vp, _d, _ll, _vp, _vp, _vp, _vp],
     "smcb_ess_multi_phi": [_vp, _vp, _vp, _ll, _vp, _i, _vp, _vp, _vp],
+    "smcb_bisect_state_bytes": [],
+    "smcb_bisect_max_candidates": [],
+    "smcb_bisect_passes": [],
+    "smcb_bisect_init": [_vp, _d, _d, _d, _vp],
+    "smcb_bisect_eval": [_vp, _vp, _d, _ll, _vp, _vp, _vp, _vp],
+    "smcb_bisect_step": [_vp, _i, _vp, _vp],
+    "smcb_bisect_read": [_vp, _vp, _vp],
     "smcb_cdf": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp],
     "smcb_ancestors_multinomial": [_vp, _ll, _vp, _ll, _vp, _vp],
     "smcb_ancestors_systematic": [_vp, _ll, _d, _ll, _ll, _ll, _vp, _vp],
     "smcb_resample_systematic": [_vp, _ll, _d, _vp, _ll, _ll, _ll, _vp, _i, _vp, _vp, _vp, _vp],
     "smcb_resample_workspace_bytes": [_ll, _i],
     "smcb_resample_systematic_push": [_vp, _ll, _d, _ll, _ll, _ll, _vp, _i, _vp, _ll, _vp, _vp, _vp],
+    "smcb_resample_multinomial_push": [_vp, _ll, _vp, _i, _i, _u64, _u32, _u32, _ll, _ll, _vp, _i, _vp, _vp, _ll, _vp],
+    "smcb_rank_offsets": [_vp, _i, _i, _vp, _vp],
     "smcb_peer_alloc": [_ll, ctypes.POINTER(_vp), _vp],
     "smcb_peer_open": [_vp, ctypes.POINTER(_vp)],
     "smcb_peer_close": [_vp],
@@ -73,7 +82,7 @@ _SIGS = {
     "smcb_scan_workspace_bytes": [_ll],
 }
 _RESTYPES = {"smcb_last_error": ctypes.c_char_p, "smcb_launch_count": _ll, "smcb_reduce_workspace_bytes": _ll,
-             "smcb_scan_workspace_bytes": _ll, "smcb_resample_workspace_bytes": _ll}
+             "smcb_scan_workspace_bytes": _ll, "smcb_bisect_state_bytes": _ll, "smcb_resample_workspace_bytes": _ll}
 
 _LIB = None
 

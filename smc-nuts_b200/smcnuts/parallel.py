@@ -13,8 +13,10 @@ import torch.distributed as dist
 
 
 class ShardContext:
-    def __init__(self, group=None):
-        self.enabled = dist.is_available() and dist.is_initialized()
+    def __init__(self, group=None, enabled=True):
+        """enabled=False: a single-shard context even though a process group exists (a rank running an unsharded
+        control case next to the sharded job, e.g. bench.py's sharded_check)."""
+        self.enabled = bool(enabled) and dist.is_available() and dist.is_initialized()
         self.group = group
         self.world = dist.get_world_size(group) if self.enabled else 1
         self.rank = dist.get_rank(group) if self.enabled else 0
@@ -71,24 +73,30 @@ class ShardContext:
 class _RawDeviceArray:
     """Minimal __cuda_array_interface__ carrier so torch can view memory the C library allocated."""
 
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
                                          "strides": None}
 
 
 class PeerBuffers:
     """Double-buffered, peer-visible destination buffers for the fused particle migration.
 
-    Every rank allocates `nbuf` buffers of [rows, D] doubles through the C-ABI (cudaMalloc + CUDA IPC handle), the
-    handles are all-gathered, and every rank maps the other ranks' buffers (NVLink peer access).  The resampling
-    kernel then stores migrating rows directly into the destination's buffer (smcb_resample_systematic_push)."""
+    Every rank allocates `nbuf` buffers of [rows, D] doubles (+ [rows] int64 ancestor indices) through the C-ABI
+    (cudaMalloc + CUDA IPC handle), the handles are all-gathered, and every rank maps the other ranks' buffers (NVLink
+    peer access).  The resampling kernels then store migrating rows directly into the destination's buffer
+    (smcb_resample_systematic_push, smcb_resample_multinomial_push).
+
+    LIFETIME: `views[b]` is a window into buffer b, which the peers overwrite again two resamples later (double
+    buffering; the completion fence of the resample in between guarantees every rank has finished with it).  The
+    sampler consumes a resampled set within the iteration that produced it; callers that keep one longer must clone
+    it.  `close()` unmaps and frees the buffers (Resampler.close / SMCSampler.finish call it)."""
 
     def __init__(self, shard, rows, D, nbuf=2):
         import ctypes
         from . import _cabi
         self.shard, self.rows, self.D, self.nbuf, self.cur = shard, rows, D, nbuf, 0
         dev_ = torch.device("cuda", torch.cuda.current_device())
-        nbytes = rows * D * 8
+        nbytes = rows * D * 8 + rows * 8
         self.local, handles = [], torch.empty(nbuf * 64, dtype=torch.uint8)
         for b in range(nbuf):
             ptr, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
@@ -98,7 +106,7 @@ class PeerBuffers:
         allh = torch.empty(shard.world * nbuf * 64, dtype=torch.uint8, device=dev_)
         dist.all_gather_into_tensor(allh, handles.to(dev_), group=shard.group)
         allh = allh.cpu().numpy().reshape(shard.world, nbuf, 64)
-        self.opened, tables = [], []
+        self.opened, tables, idx_tables = [], [], []
         for b in range(nbuf):
             ptrs = []
             for q in range(shard.world):
@@ -111,8 +119,10 @@ class PeerBuffers:
                     self.opened.append(p.value)
                     ptrs.append(p.value)
             tables.append(torch.tensor(ptrs, dtype=torch.int64).to(dev_))
-        self.tables = tables
+            idx_tables.append(torch.tensor([q + rows * D * 8 for q in ptrs], dtype=torch.int64).to(dev_))
+        self.tables, self.idx_tables = tables, idx_tables
         self.views = [torch.as_tensor(_RawDeviceArray(p, (rows, D)), device=dev_) for p in self.local]
+        self.idx_views = [torch.as_tensor(_RawDeviceArray(p + rows * D * 8, (rows,), "<i8"), device=dev_) for p in self.local]
         self._token = torch.zeros(1, dtype=torch.float64, device=dev_)
 
     def next(self):
@@ -125,6 +135,9 @@ class PeerBuffers:
 
     def close(self):
         from . import _cabi
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self.views, self.idx_views = [], []
         for p in self.opened:
             _cabi.lib().smcb_peer_close(p)
         for p in self.local:

@@ -48,7 +48,7 @@ class Resampler:
         self.use_peer_push = True
         self.keep_idx = True          # materialise the ancestor indices (diagnostic; bench.py turns it off)
         self.last_idx = None          # ancestors of the last resample (global indices for this rank's slots)
-        self.last_migrated_rows = 0   # rows this rank received from other ranks (diagnostic)
+        self._migrated = 0            # rows this rank received from other ranks in the last resample (diagnostic)
 
     def _cdf(self, wn):
         n, st, sh = wn.shape[0], dev.stream_ptr(), self.shard
@@ -57,12 +57,12 @@ class Resampler:
         if sh.world == 1:
             _cabi.call("smcb_cdf", dev.ptr(wn), n, 0, 0, dev.ptr(cdf), dev.ptr(total), dev.ptr(ws), st)
             return cdf
-        # rank totals -> exclusive offsets (sequential fp64 sum in rank order, identical on every rank)
+        # rank totals -> exclusive offsets (sequential fp64 sum in rank order, identical on every rank), all on the device
         tmp = dev.empty(n)
         _cabi.call("smcb_cdf", dev.ptr(wn), n, 0, 0, dev.ptr(tmp), dev.ptr(total), dev.ptr(ws), st)
-        totals = sh.all_gather_vec(total).view(-1).cpu().numpy()
-        off = np.concatenate([[0.0], np.cumsum(totals)])
-        off_t = torch.tensor([off[sh.rank], off[-1]], dtype=torch.float64).to(wn.device)
+        totals = sh.all_gather_vec(total).view(-1).contiguous()
+        off_t = dev.empty(2)
+        _cabi.call("smcb_rank_offsets", dev.ptr(totals), sh.world, sh.rank, dev.ptr(off_t), st)
         _cabi.call("smcb_cdf", dev.ptr(wn), n, off_t.data_ptr(), off_t.data_ptr() + 8, dev.ptr(cdf), dev.ptr(total),
                    dev.ptr(ws), st)
         return cdf
@@ -119,12 +119,10 @@ class Resampler:
         m = hi - lo
         mylo, myhi = sh.rank * self.n_local, (sh.rank + 1) * self.n_local
         recv_counts = [max(0, min(myhi, int(bounds[q + 1])) - max(mylo, int(bounds[q]))) for q in range(sh.world)]
-        self.last_migrated_rows = sum(c for q, c in enumerate(recv_counts) if q != sh.rank)
+        self._migrated = sum(c for q, c in enumerate(recv_counts) if q != sh.rank)
         if self.use_peer_push and D in (2, 4, 8, 16, 32, 64):
             # fused path: gather + migration in one kernel, rows stored straight into the destination GPU over NVLink
-            if self.peers is None or self.peers.D != D:
-                from ..parallel import PeerBuffers
-                self.peers = PeerBuffers(sh, self.n_local, D)
+            self._peer_buffers(D)
             b = self.peers.next()
             keep = dev.empty(max(m, 1), dtype=torch.int64) if self.keep_idx else None
             if m:
@@ -144,36 +142,45 @@ class Resampler:
         self.last_idx = idx[:m] + self.offset
         return sh.all_to_all_rows(send[:m], send_counts, recv_counts)
 
+    def _peer_buffers(self, D):
+        if self.peers is None or self.peers.D != D:
+            from ..parallel import PeerBuffers
+            if self.peers is not None:
+                self.peers.close()
+            self.peers = PeerBuffers(self.shard, self.n_local, D)
+        return self.peers
+
     def _multinomial_sharded(self, x, cdf, iteration):
-        """Unsorted uniforms: all-gather the cdf (8N bytes), search locally, fetch rows from their owners with a
-        request/response all-to-all-v pair."""
-        import torch.distributed as dist
+        """Owner-push: every rank regenerates the N uniforms of the global slots from the Philox stream, resolves the ones
+        that fall into its own cdf segment and stores the ancestors' rows straight into the slot owners' buffers over
+        NVLink (smcb_resample_multinomial_push).  One tiny all-gather (the P segment ends) and the completion fence are
+        the only collectives; nothing touches the host."""
         sh, st = self.shard, dev.stream_ptr()
         n, D = x.shape
-        full = torch.empty(self.N, dtype=torch.float64, device=x.device)
-        dist.all_gather_into_tensor(full, cdf, group=sh.group)
-        u, idx = dev.empty(n), dev.empty(n, dtype=torch.int64)
-        _cabi.call("smcb_uniforms", self.seed, iteration, self.stream, self.offset, n, 0, dev.ptr(u), st)
-        _cabi.call("smcb_ancestors_multinomial", dev.ptr(full), self.N, dev.ptr(u), n, dev.ptr(idx), st)
-        self.last_idx = idx
-        owner = torch.div(idx, self.n_local, rounding_mode="floor")
-        order = torch.argsort(owner, stable=True)
-        req_counts = torch.bincount(owner, minlength=sh.world)
-        got_counts = torch.empty_like(req_counts)
-        dist.all_to_all_single(got_counts, req_counts, group=sh.group)
-        rc, gc = req_counts.tolist(), got_counts.tolist()
-        want = (idx[order] - owner[order] * self.n_local).contiguous()
-        asked = sh.all_to_all_rows(want.view(-1, 1), rc, gc).view(-1).contiguous()
-        rows = dev.empty(max(asked.numel(), 1), D)
-        if asked.numel():
-            _cabi.call("smcb_gather_rows", dev.ptr(x), dev.ptr(asked), asked.numel(), D, dev.ptr(rows), st)
-        back = sh.all_to_all_rows(rows[:asked.numel()], gc, rc)
-        out = dev.empty(n, D)
-        inv = torch.empty_like(order)
-        inv[order] = torch.arange(n, device=order.device)
-        _cabi.call("smcb_gather_rows", dev.ptr(back), dev.ptr(inv), n, D, dev.ptr(out), st)
-        self.last_migrated_rows = n - rc[sh.rank]
-        return out
+        ends = sh.all_gather_vec(cdf[-1:].contiguous()).view(-1).contiguous()
+        peers = self._peer_buffers(D)
+        b = peers.next()
+        _cabi.call("smcb_resample_multinomial_push", dev.ptr(cdf), n, dev.ptr(ends), sh.rank, sh.world, self.seed,
+                   iteration, self.stream, self.N, self.offset, dev.ptr(x), D, dev.ptr(peers.tables[b]),
+                   dev.ptr(peers.idx_tables[b]) if self.keep_idx else 0, self.n_local, st)
+        peers.fence()
+        self.last_idx = peers.idx_views[b] if self.keep_idx else None
+        self._migrated = None         # counted lazily from last_idx (no host synchronisation on the hot path)
+        return peers.views[b]
+
+    @property
+    def last_migrated_rows(self):
+        if self._migrated is None:
+            if self.last_idx is None:
+                return -1
+            i = self.last_idx
+            self._migrated = int(((i < self.offset) | (i >= self.offset + self.n_local)).sum().item())
+        return self._migrated
+
+    def close(self):
+        if self.peers is not None:
+            self.peers.close()
+            self.peers = None
 
 
 class Samples:

@@ -24,14 +24,14 @@ from .samples.samples import Samples
 class SMCSampler:
     def __init__(self, K: int, N: int, target, step_size=None, sample_proposal=None, momentum_proposal=None,
                  lkernel="forwardsLKernel", tempering=False, rng=None, forward_kernel=None, verbose=False,
-                 resampling="multinomial", save_history=None, history_budget_bytes=48 << 30):
+                 resampling="multinomial", save_history=None, history_budget_bytes=48 << 30, shard=None):
         self.K = K  # Number of iterations
         self.N = N  # Number of particles (global)
         self.target = target
         self.rng = rng
         self.lkernel = lkernel
         self.verbose = verbose
-        self.shard = ShardContext()
+        self.shard = shard if shard is not None else ShardContext()
         D = target.dim
 
         # README form: the 4th positional argument is a forward-kernel plugin, not a step size

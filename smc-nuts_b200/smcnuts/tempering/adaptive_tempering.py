@@ -1,12 +1,18 @@
 """ESSTempering -- adaptive temperature by ESS bisection (reference: smcnuts/tempering/adaptive_tempering.py).
 
 The reference calls scipy.optimize.bisect on a Python closure that does three full model sweeps and ~41
-O(N) numpy passes.  Here the per-particle arrays come from the split log density the NUTS kernel already
-emitted, and each pass evaluates the ESS objective at up to 16 candidate temperatures at once
-(smcb_ess_multi_phi): the candidates are the nodes of the next 4 levels of the bisection tree, which is a
-deterministic function of the bracket (dm *= .5; xm = xa + dm), so walking the evaluated tree on the host
-reproduces scipy's iterates exactly while needing ~10 launches (and ~10 small all-gathers when sharded)
-instead of 41.
+O(N) numpy passes.  Here the per-particle quantities come from the split log density the NUTS kernel already
+emitted, and each pass evaluates the ESS objective at up to 16 candidate temperatures at once: the candidates are
+the nodes of the next 4 levels of the bisection tree, which is a deterministic function of the bracket
+(dm *= .5; xm = xa + dm), so walking the evaluated tree reproduces scipy's iterates exactly.
+
+The whole search is DEVICE-RESIDENT (csrc/bisect.cuh): the bracket, the candidates and the outcome live in a small
+device state; the host enqueues a fixed schedule of `eval` (one sweep over the particles) -> all-gather of the
+per-rank partial states when sharded (stream-ordered NCCL) -> `step` (one thread walks the tree and writes the next
+candidates), and reads phi once at the end.  Round 1 walked the tree on the host -- ~10 device->host round trips per
+SMC iteration, 25 % of a PRMwCD iteration on a 2^17-particle shard.  `bisect_batched` below is that host walk, kept
+as the CPU-testable statement of the algorithm (tests/test_host_logic.py checks it and the device walk, compiled for
+the host, against scipy bit for bit).
 """
 import math
 
@@ -49,6 +55,32 @@ class ESSTempering:
 
     # ---- device entry point: reuse the split the NUTS kernel carried
     def calculate_phi_from_split(self, A, B, old_phi):
+        """phi_new from (A, B) at x_new; one device->host read (of the result) in total."""
+        L, n, st, sh = _cabi.lib(), A.shape[0], dev.stream_ptr(), self.shard
+        mc = L.smcb_bisect_max_candidates()
+        state = dev.workspace("bisect_state", L.smcb_bisect_state_bytes())
+        _cabi.call("smcb_bisect_init", dev.ptr(state), float(old_phi), 1.0, float(self.N * self.alpha), st)
+        self.passes = L.smcb_bisect_passes()
+        for _ in range(self.passes):
+            tri = dev.empty(mc * 3)
+            _cabi.call("smcb_bisect_eval", dev.ptr(A), dev.ptr(B), float(old_phi), n, dev.ptr(state), dev.ptr(tri),
+                       dev.ptr(dev.reduce_ws()), st)
+            tris = sh.all_gather_vec(tri).contiguous()
+            _cabi.call("smcb_bisect_step", dev.ptr(tris), sh.world, dev.ptr(state), st)
+        out = dev.empty(4)
+        _cabi.call("smcb_bisect_read", dev.ptr(state), dev.ptr(out), st)
+        phi, status, _iters, nan_at = out.cpu().tolist()
+        status = int(status)
+        if status == 1:
+            return float(phi)
+        if status == 2:
+            raise ValueError(f"The function value at x={nan_at} is NaN; solver cannot continue.")
+        if status == 3:
+            raise ValueError("f(a) and f(b) must have different signs")
+        raise RuntimeError("bisect failed to converge")
+
+    # ---- the round-1 host walk (one round trip per pass); kept for A/B timing and as the host statement of the search
+    def calculate_phi_from_split_host(self, A, B, old_phi):
         n = A.shape[0]
         logpri, loglik, c = dev.empty(n), dev.empty(n), dev.empty(n)
         _cabi.call("smcb_tempering_arrays", dev.ptr(A), dev.ptr(B), float(old_phi), n, dev.ptr(logpri),

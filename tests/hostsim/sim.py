@@ -105,3 +105,28 @@ def nuts_simt(name, np_target, x, r, eps, phi, max_depth=10, accrej=False, seed=
         P(o["ke_new"]), I(o["n_leapfrog"]), I(o["accepted"]), I(o["depth"]))
     assert rc == 0
     return o
+
+
+_LIB_BISECT = None
+
+
+def bisect(f, xa, xb):
+    """The device bisection walk (csrc/bisect.cuh compiled with g++) on a Python objective f(array) -> array.
+    Returns (root, status, iterations, nan_at, passes)."""
+    global _LIB_BISECT
+    if _LIB_BISECT is None:
+        so, src = HERE / "_hostsim_bisect.so", HERE / "hostsim_bisect.cpp"
+        hdrs = list((HERE.parents[1] / "smc-nuts_b200" / "csrc").glob("*.cuh"))
+        if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in [src] + hdrs):
+            subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                            "-o", str(so), str(src)], check=True)
+        _LIB_BISECT = ctypes.CDLL(str(so))
+    cb_t = ctypes.CFUNCTYPE(None, _dp, ctypes.c_int, _dp)
+
+    def cb(xp, m, fp):
+        vals = np.asarray(f(np.array([xp[i] for i in range(m)])), dtype=np.float64)
+        for i in range(m):
+            fp[i] = vals[i]
+    out = (ctypes.c_double * 4)()
+    passes = _LIB_BISECT.hostsim_bisect(ctypes.c_double(xa), ctypes.c_double(xb), cb_t(cb), out, None)
+    return out[0], int(out[1]), int(out[2]), out[3], passes

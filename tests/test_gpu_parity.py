@@ -369,6 +369,14 @@ def test_tempering_matches_reference_golden(golden):
         phi = ts.calculate_phi_from_split(lpri_d, ll_d, old)
         assert math.isclose(phi, float(g[f"temper_{j}_phi"]), rel_tol=1e-9), (phi, float(g[f"temper_{j}_phi"]))
         assert ts.passes <= 12
+        # the device-resident walk and the round-1 host walk evaluate the same objective at the same points: same root
+        assert phi == ts.calculate_phi_from_split_host(lpri_d, ll_d, old)
+    # scipy's error cases surface as the same exceptions (status codes of the device state)
+    ts = ESSTempering(8, m, alpha=0.5)
+    nan_ll = dev.to_device(np.full(8, np.nan))
+    with pytest.raises(ValueError, match="NaN"):
+        ts.calculate_phi_from_split(dev.to_device(np.zeros(8)), nan_ll, 0.0)
+    assert ESSTempering(16, m, alpha=0.5).calculate_phi_from_split(dev.to_device(np.zeros(16)), dev.to_device(np.zeros(16)), 0.3) == 1.0
     # the reference entry point: calculate_phi([x_new, lp_old, old_phi]) on real model values
     t = O.COracleTarget("arma")
     x = np.random.default_rng(2).normal(size=(4000, 4)) * 0.3 + np.array([0.0, 0.5, 0.0, -1.0])

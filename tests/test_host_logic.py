@@ -40,6 +40,34 @@ def test_batched_bisect_edge_cases():
         bisect_batched(lambda ps: [float("nan") if p < 1 else -1.0 for p in ps], 0.2, 1.0)
 
 
+def test_device_bisection_walk_reproduces_scipy_bit_for_bit(golden):
+    """csrc/bisect.cuh (the walk the GPU runs, compiled here with g++) against scipy.optimize.bisect: same roots, same
+    iteration counts, same error cases, and the reference's tempering goldens -- within the fixed schedule of passes."""
+    from tests.hostsim import sim
+    rng = np.random.default_rng(0)
+    for _ in range(80):
+        a, sc = rng.uniform(0.02, 0.98), rng.uniform(0.5, 30)
+        lo = rng.uniform(0.0, a * 0.9)
+        f = lambda p: -(np.tanh(sc * (p - a)) + 0.01 * (p - a))   # noqa: E731  positive at lo, negative at 1
+        root, status, iters, _, passes = sim.bisect(f, lo, 1.0)
+        ref, info = scipy_bisect(f, lo, 1.0, full_output=True)
+        assert status == 1 and root == ref and iters == info.iterations and passes <= 11
+    # worst case for the schedule: the full interval and a root that is never hit exactly
+    root, status, iters, _, passes = sim.bisect(lambda p: 0.3 - p + 1e-13, 0.0, 1.0)
+    assert status == 1 and root == scipy_bisect(lambda p: 0.3 - p + 1e-13, 0.0, 1.0) and passes <= 11
+    assert sim.bisect(lambda p: np.ones_like(p), 0.2, 1.0)[:2] == (1.0, 1)                 # f(1) >= 0 -> phi = 1
+    assert sim.bisect(lambda p: -np.ones_like(p), 0.2, 1.0)[1] == 3                         # same sign -> ValueError
+    assert sim.bisect(lambda p: np.where(p < 1, np.nan, -1.0), 0.2, 1.0)[1] == 2           # NaN -> ValueError
+    assert sim.bisect(lambda p: np.where(p == 0.2, 0.0, -1.0), 0.2, 1.0)[:2] == (0.2, 1)   # f(a) == 0 -> a
+    g = golden("tempering")
+    for j in range(4):
+        ll, lpri, c = g[f"temper_{j}_loglik"], g[f"temper_{j}_logpri"], g[f"temper_{j}_lp_old"]
+        N = len(ll)
+        fb = lambda ps: np.array([O.ess_at_phi(p, ll, lpri, c) - N * 0.5 for p in ps])   # noqa: E731
+        root, status, _, _, _ = sim.bisect(fb, float(g[f"temper_{j}_old_phi"]), 1.0)
+        assert status == 1 and root == float(g[f"temper_{j}_phi"])
+
+
 def test_tempering_golden_through_batched_bisect(golden):
     g = golden("tempering")
     for j in range(4):
