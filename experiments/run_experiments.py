@@ -35,10 +35,18 @@ def save_output(smc, strategy, i, output_dir):
     np.savetxt(path / f"acceptance_rate_{i}.csv", smc.acceptance_rate, delimiter=",")
 
 
+def mse_mean_var(x, ground_truth):
+    """plot_experiments.py:60-78: x is [M runs, K+1 iterations, D]; the squared error of every run and iteration is
+    averaged over the D parameters, then its mean and its (population, ddof = 0) variance are taken over the M runs.
+    Returns (mse_mean[K+1], mse_var[K+1])."""
+    x = np.asarray(x, dtype=np.float64)
+    mse_per_run_iter = np.mean(np.square(x - np.asarray(ground_truth, dtype=np.float64)[None, None, :]), axis=2)
+    return np.mean(mse_per_run_iter, axis=0), np.var(mse_per_run_iter, axis=0)
+
+
 def mse_per_iteration(means, truth):
-    """plot_experiments.py:61-79: per-iteration squared error of the mean estimate, averaged over runs and parameters."""
-    means = np.asarray(means)                       # [runs, K+1, D]
-    return np.mean((means - truth[None, None, :]) ** 2, axis=(0, 2))
+    """First output of mse_mean_var: per-iteration squared error averaged over runs and parameters."""
+    return mse_mean_var(means, truth)[0]
 
 
 def run(model_name="arma", runs=25, N=100, K=15, out=None, configs=CONFIGS, verbose=True):
@@ -61,7 +69,8 @@ def run(model_name="arma", runs=25, N=100, K=15, out=None, configs=CONFIGS, verb
             if out:
                 save_output(smc, strategy, i, Path(out) / model_name)
             means.append(smc.mean_estimate)
-        results[strategy] = dict(means=np.array(means), mse=mse_per_iteration(means, truth))
+        mse, mse_var = mse_mean_var(means, truth)
+        results[strategy] = dict(means=np.array(means), mse=mse, mse_var=mse_var)
         if verbose:
             print(f"{model_name} {strategy}: final-iteration MSE vs gold means = {results[strategy]['mse'][-1]:.3e} "
                   f"({runs} runs, N={N}, K={K})")

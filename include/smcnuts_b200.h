@@ -195,7 +195,10 @@ int smcb_gaussL_sums(const double* r_new, const double* x_new, long long N, int 
 int smcb_gaussL_gram(const double* r_new, const double* x_new, long long N, int D, const double* mean, double* gram,
                      void* stream);
 /* cov = gram/(N_total-1) -> S = C_rr - C_rx C_xx^-1 C_xr + ridge*I = L L';  G = L^-1 [I, -C_rx C_xx^-1] (D x 2D);
- * out_logdet[0] = log det S.  scratch: 6*D*D doubles. */
+ * out_logdet[2] = (log det S, path).  C_xx is inverted by Cholesky (path 0); when a pivot is not safely positive
+ * (rank-deficient C_xx: N <= D+1, collapsed particles) by the pseudo-inverse with numpy's cutoff, as the reference's
+ * np.linalg.pinv (gaussian_lkernel.py:64-75) (path 1); path -1: S is not positive definite, G and logdet are NaN.
+ * scratch: 6*D*D doubles. */
 int smcb_gaussL_factor(const double* gram, long long N_total, int D, double ridge, double* G, double* out_logdet,
                        double* scratch, void* stream);
 /* out_i = -0.5*(D log 2pi + logdet + |G (X_i - mean)|^2).  scratch (nullable): 2*D*(D+8) doubles; when given and

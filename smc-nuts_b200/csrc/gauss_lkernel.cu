@@ -211,11 +211,19 @@ __global__ void __launch_bounds__(256) gaussL_logpdf_dmma_kernel(const double* _
 }
 
 // In-place lower Cholesky of the n x n row-major matrix a (only the lower triangle is read).  One CTA.
-__device__ void chol_inplace(double* a, int n) {
+// A pivot that is not safely positive (<= tol, or NaN) sets *fail and stops: the caller then takes the pseudo-inverse
+// path (a rank-deficient C_xx: N <= D + 1, or particles collapsed onto few distinct rows after resampling -- the
+// reference inverts with np.linalg.pinv, gaussian_lkernel.py:64-75, and stays finite there).
+__device__ void chol_inplace(double* a, int n, double tol, int* fail) {
     for (int j = 0; j < n; ++j) {
         __syncthreads();
-        if (threadIdx.x == 0) a[j * n + j] = sqrt(a[j * n + j]);
+        if (threadIdx.x == 0) {
+            const double d = a[j * n + j];
+            if (!(d > tol)) *fail = 1;
+            a[j * n + j] = sqrt(d);
+        }
         __syncthreads();
+        if (*fail) return;
         const double dj = a[j * n + j];
         for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) a[i * n + j] /= dj;
         __syncthreads();
@@ -225,6 +233,94 @@ __device__ void chol_inplace(double* a, int n) {
             const int i = j + 1 + t / rem, k = j + 1 + t % rem;
             if (k <= i) a[i * n + k] -= a[i * n + j] * a[k * n + j];
         }
+    }
+    __syncthreads();
+}
+
+// Moore-Penrose pseudo-inverse of the symmetric n x n matrix A (full storage, destroyed) by cyclic Jacobi with a
+// round-robin parallel ordering: every round rotates n/2 disjoint (p, q) pairs at once.  pinv = sum over
+// |lambda_i| > rcond * max|lambda| of v_i v_i' / lambda_i with rcond = 1e-15, numpy.linalg.pinv's default cutoff
+// (for a symmetric matrix the singular values are |lambda_i|).  One CTA; V and out are n x n scratch / result.
+__device__ void pinv_sym_jacobi(double* A, double* V, double* out, int n) {
+    __shared__ double rot_c[64], rot_s[64];
+    __shared__ int rot_p[64], rot_q[64];
+    __shared__ double lam_max, scale0;
+    __shared__ int active;
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) V[t] = (t / n == t % n) ? 1.0 : 0.0;
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(A[i * n + i]));
+        scale0 = mx;
+    }
+    __syncthreads();
+    const int ne = (n + 1) & ~1, m = ne - 1, npairs = ne / 2;   // ne players (index n = bye when n is odd)
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        if (threadIdx.x == 0) active = 0;
+        __syncthreads();
+        for (int r = 0; r < m; ++r) {
+            if ((int)threadIdx.x < npairs) {
+                const int k = threadIdx.x;
+                int pp = (k == 0) ? m : (r + k) % m;
+                int qq = (k == 0) ? r % m : (r - k + m) % m;
+                if (pp > qq) { const int t_ = pp; pp = qq; qq = t_; }
+                double c = 1.0, sn = 0.0;
+                if (qq < n) {
+                    const double apq = A[pp * n + qq], app = A[pp * n + pp], aqq = A[qq * n + qq];
+                    // rotate while the off-diagonal entry matters relative to its diagonal pair and to the matrix scale
+                    if (fabs(apq) > 1e-22 * scale0 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double tt = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = rsqrt(1.0 + tt * tt);
+                        sn = tt * c;
+                        active = 1;
+                    }
+                } else {
+                    qq = pp;   // bye
+                }
+                rot_p[k] = pp; rot_q[k] = qq; rot_c[k] = c; rot_s[k] = sn;
+            }
+            __syncthreads();
+            // rows:  A <- J' A
+            for (int t = threadIdx.x; t < npairs * n; t += blockDim.x) {
+                const int k = t / n, j = t % n, pp = rot_p[k], qq = rot_q[k];
+                if (pp == qq) continue;
+                const double c = rot_c[k], sn = rot_s[k], x = A[pp * n + j], y = A[qq * n + j];
+                A[pp * n + j] = c * x - sn * y;
+                A[qq * n + j] = sn * x + c * y;
+            }
+            __syncthreads();
+            // columns:  A <- A J,  V <- V J
+            for (int t = threadIdx.x; t < npairs * n; t += blockDim.x) {
+                const int k = t / n, i = t % n, pp = rot_p[k], qq = rot_q[k];
+                if (pp == qq) continue;
+                const double c = rot_c[k], sn = rot_s[k];
+                double x = A[i * n + pp], y = A[i * n + qq];
+                A[i * n + pp] = c * x - sn * y;
+                A[i * n + qq] = sn * x + c * y;
+                x = V[i * n + pp]; y = V[i * n + qq];
+                V[i * n + pp] = c * x - sn * y;
+                V[i * n + qq] = sn * x + c * y;
+            }
+            __syncthreads();
+        }
+        if (!active) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(A[i * n + i]));
+        lam_max = mx;
+    }
+    __syncthreads();
+    const double cutoff = 1e-15 * lam_max;
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+        const int i = t / n, j = t % n;
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double lam = A[k * n + k];
+            if (fabs(lam) > cutoff) acc += V[i * n + k] * V[j * n + k] / lam;
+        }
+        out[t] = acc;
     }
     __syncthreads();
 }
@@ -253,6 +349,8 @@ __device__ void trsm_lower_t(const double* L, double* B, int n, int m) {
 __global__ void __launch_bounds__(256) gaussL_factor_kernel(const double* __restrict__ gram, long long N_total, int D,
                                                             double ridge, double* G, double* out_logdet,
                                                             double* scratch) {
+    __shared__ int fail;
+    __shared__ double scale;
     const int D2 = 2 * D, DD = D * D;
     double* Lx = scratch;           // C_xx -> chol
     double* Wt = scratch + DD;      // C_xr (D x D) -> C_xx^-1 C_xr = W'
@@ -264,10 +362,38 @@ __global__ void __launch_bounds__(256) gaussL_factor_kernel(const double* __rest
         Lx[t] = cov(D + i, D + j);
         Wt[t] = cov(D + i, j);  // C_xr[i][j]
     }
+    if (threadIdx.x == 0) {
+        fail = 0;
+        double mx = 0.0;
+        for (int i = 0; i < D; ++i) mx = fmax(mx, cov(D + i, D + i));
+        scale = mx;
+    }
     __syncthreads();
-    chol_inplace(Lx, D);
-    trsm_lower(Lx, Wt, D, D);
-    trsm_lower_t(Lx, Wt, D, D);  // Wt = C_xx^-1 C_xr, i.e. W = Wt'
+    int path = 0;
+    chol_inplace(Lx, D, 1e-13 * scale, &fail);
+    __syncthreads();
+    if (!fail) {
+        trsm_lower(Lx, Wt, D, D);
+        trsm_lower_t(Lx, Wt, D, D);  // Wt = C_xx^-1 C_xr, i.e. W = Wt'
+    } else {
+        // rank-deficient / indefinite C_xx: W' = pinv(C_xx) C_xr as the reference (gaussian_lkernel.py:64-75)
+        path = 1;
+        double* Afull = scratch + 3 * DD;
+        double* V = scratch + 4 * DD;
+        double* Pinv = scratch + 5 * DD;
+        for (int t = threadIdx.x; t < DD; t += blockDim.x) Afull[t] = cov(D + t / D, D + t % D);
+        __syncthreads();
+        pinv_sym_jacobi(Afull, V, Pinv, D);
+        for (int t = threadIdx.x; t < DD; t += blockDim.x) {
+            const int i = t / D, j = t % D;
+            double acc = 0.0;
+            for (int k = 0; k < D; ++k) acc += Pinv[i * D + k] * cov(D + k, j);
+            Wt[t] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) fail = 0;
+        __syncthreads();
+    }
     for (int t = threadIdx.x; t < DD; t += blockDim.x) {
         const int i = t / D, j = t % D;
         double s = cov(i, j);
@@ -281,11 +407,17 @@ __global__ void __launch_bounds__(256) gaussL_factor_kernel(const double* __rest
         if (j < i) S[t] = 0.5 * (S[t] + S[j * D + i]);
     }
     __syncthreads();
-    chol_inplace(S, D);
+    chol_inplace(S, D, 0.0, &fail);
+    __syncthreads();
     if (threadIdx.x == 0) {
         double ld = 0.0;
         for (int i = 0; i < D; ++i) ld += log(S[i * D + i]);
-        out_logdet[0] = 2.0 * ld;
+        out_logdet[0] = fail ? __longlong_as_double(0x7ff8000000000000LL) : 2.0 * ld;
+        out_logdet[1] = fail ? -1.0 : (double)path;   // 0: Cholesky of C_xx, 1: pseudo-inverse path, -1: S not positive definite
+    }
+    if (fail) {   // poison G so that the failure cannot pass silently as finite weights
+        for (int t = threadIdx.x; t < D * D2; t += blockDim.x) G[t] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
     }
     // G = L^-1 [I, -W]   (D x 2D)
     for (int t = threadIdx.x; t < D * D2; t += blockDim.x) {

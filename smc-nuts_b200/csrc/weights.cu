@@ -131,6 +131,44 @@ __global__ void std_normal_logpdf_kernel(const double* __restrict__ x, long long
     }
 }
 
+// Rows too wide for the shared-memory tile (D > 110): one warp per row, lanes stride over the coordinates.
+// mode 0: out = 0.5|row|^2;  1: out = -0.5|row|^2 - D/2 log 2pi;  2: out = aux - (-0.5|row|^2 - D/2 log 2pi)
+__global__ void __launch_bounds__(256) row_sqnorm_warp_kernel(const double* __restrict__ r, long long N, int D, int mode,
+                                                               const double* __restrict__ aux, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < N; i += nwarps) {
+        double s = 0.0;
+        for (int d = lane; d < D; d += 32) { const double v = r[i * D + d]; s += v * v; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const double h = 0.5 * s, lg = -h - 0.5 * D * kLog2Pi;
+            out[i] = mode == 0 ? h : mode == 1 ? lg : aux[i] - lg;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) reweight_forward_warp_kernel(const double* __restrict__ logw,
+                                                                     const double* __restrict__ lp_x,
+                                                                     const double* __restrict__ lp_xnew,
+                                                                     const double* __restrict__ r,
+                                                                     const double* __restrict__ r_new, long long N, int D,
+                                                                     double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const double c = 0.5 * D * kLog2Pi;
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < N; i += nwarps) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int d = lane; d < D; d += 32) {
+            const double a = r[i * D + d], b = r_new[i * D + d];
+            s0 += a * a; s1 += b * b;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+        if (lane == 0) out[i] = logw[i] + lp_xnew[i] - lp_x[i] + (-0.5 * s1 - c) - (-0.5 * s0 - c);
+    }
+}
+
 __global__ void uniform_logw_kernel(const double* __restrict__ logZ, double logN, long long N, double* __restrict__ out) {
     const double v = logZ[0] - logN;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) out[i] = v;
@@ -622,10 +660,15 @@ int smcb_uniforms(uint64_t seed, uint32_t iteration, uint32_t stream_id, uint64_
 }
 
 static size_t tile_smem(int D) { return sizeof(double) * (size_t)kRedThreads * (D + 1); }
+constexpr int kTileMaxD = 110;   // 256 rows x (D + 1) doubles must fit the 227 KB of shared memory; wider rows: one warp per row
 
 int smcb_row_half_sqnorm(const double* r, long long N, int D, double* out, void* stream) {
-    SMCB_REQUIRE(r && out && N >= 0 && D >= 1 && D <= 110, "bad argument (D <= 110)");
+    SMCB_REQUIRE(r && out && N >= 0 && D >= 1, "bad argument");
     if (N == 0) return 0;
+    if (D > kTileMaxD) {
+        row_sqnorm_warp_kernel<<<stride_grid(N * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(r, N, D, 0, nullptr, out);
+        return check_launch("row_sqnorm_warp_kernel");
+    }
     const size_t smem = tile_smem(D);
     if (smem > 48 * 1024)
         SMCB_CUDA(cudaFuncSetAttribute(row_half_sqnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -634,8 +677,12 @@ int smcb_row_half_sqnorm(const double* r, long long N, int D, double* out, void*
 }
 
 int smcb_std_normal_logpdf(const double* x, long long N, int D, double* out, void* stream) {
-    SMCB_REQUIRE(x && out && N >= 0 && D >= 1 && D <= 110, "bad argument (D <= 110)");
+    SMCB_REQUIRE(x && out && N >= 0 && D >= 1, "bad argument");
     if (N == 0) return 0;
+    if (D > kTileMaxD) {
+        row_sqnorm_warp_kernel<<<stride_grid(N * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, N, D, 1, nullptr, out);
+        return check_launch("row_sqnorm_warp_kernel");
+    }
     const size_t smem = tile_smem(D);
     if (smem > 48 * 1024)
         SMCB_CUDA(cudaFuncSetAttribute(std_normal_logpdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -658,8 +705,12 @@ int smcb_affine(const double* in, long long N, double a, double b, double* out, 
 }
 
 int smcb_init_logw(const double* lp, const double* x, long long N, int D, double* logw, void* stream) {
-    SMCB_REQUIRE(lp && x && logw && N >= 0 && D >= 1 && D <= 110, "bad argument (D <= 110)");
+    SMCB_REQUIRE(lp && x && logw && N >= 0 && D >= 1, "bad argument");
     if (N == 0) return 0;
+    if (D > kTileMaxD) {
+        row_sqnorm_warp_kernel<<<stride_grid(N * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, N, D, 2, lp, logw);
+        return check_launch("row_sqnorm_warp_kernel");
+    }
     const size_t smem = tile_smem(D);
     if (smem > 48 * 1024)
         SMCB_CUDA(cudaFuncSetAttribute(init_logw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -669,8 +720,13 @@ int smcb_init_logw(const double* lp, const double* x, long long N, int D, double
 
 int smcb_reweight_forward(const double* logw, const double* lp_x, const double* lp_xnew, const double* r,
                           const double* r_new, long long N, int D, double* out, void* stream) {
-    SMCB_REQUIRE(logw && lp_x && lp_xnew && r && r_new && out && N >= 0 && D >= 1 && D <= 110, "bad argument (D <= 110)");
+    SMCB_REQUIRE(logw && lp_x && lp_xnew && r && r_new && out && N >= 0 && D >= 1, "bad argument");
     if (N == 0) return 0;
+    if (D > kTileMaxD) {
+        reweight_forward_warp_kernel<<<stride_grid(N * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(logw, lp_x, lp_xnew, r,
+                                                                                                   r_new, N, D, out);
+        return check_launch("reweight_forward_warp_kernel");
+    }
     const bool aligned = (((uintptr_t)r | (uintptr_t)r_new) % 16) == 0;
     if (aligned && (D == 4 || D == 8 || D == 16 || D == 32 || D == 64)) {
         cudaStream_t st = (cudaStream_t)stream;

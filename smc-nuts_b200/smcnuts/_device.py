@@ -35,6 +35,13 @@ def to_device(a, dtype=F64):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device())
 
 
+def to_numpy(a):
+    """Any container (CUDA / CPU tensor, numpy, list) -> host numpy array."""
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
 def like_input(t, ref):
     """Return `t` in the container type of `ref` (numpy in -> numpy out)."""
     if is_host(ref):

@@ -14,4 +14,5 @@ class ForwardLKernel:
             out = dev.empty(rd.shape[0])
             _cabi.call("smcb_std_normal_logpdf", dev.ptr(rd), rd.shape[0], D, dev.ptr(out), dev.stream_ptr())
             return dev.like_input(out, r_new)
-        return self.momentum_proposal.logpdf(-1 * r_new)
+        # foreign momentum plugin (e.g. a scipy frozen distribution): it gets host NumPy, whatever container came in
+        return self.momentum_proposal.logpdf(-1 * dev.to_numpy(r_new))

@@ -15,6 +15,7 @@ class GaussianApproxLKernel:
         self.D = target.dim
         self.N = N            # GLOBAL particle count (np.cov ddof = 1 uses it)
         self.shard = shard or ShardContext()
+        self.last_status = None   # device tensor [logdet, path] of the last call: path 0 Cholesky, 1 pinv fallback, -1 failed
 
     def calculate_L(self, r_new, x_new):
         D = self.D
@@ -31,9 +32,10 @@ class GaussianApproxLKernel:
         gram = dev.zeros(2 * D, 2 * D)
         _cabi.call("smcb_gaussL_gram", dev.ptr(r), dev.ptr(x), n, D, dev.ptr(mean), dev.ptr(gram), st)
         self.shard.all_reduce_sum_(gram)
-        G, logdet, scratch = dev.empty(D, 2 * D), dev.empty(1), dev.empty(6 * D * D)
+        G, logdet, scratch = dev.empty(D, 2 * D), dev.empty(2), dev.empty(6 * D * D)
         _cabi.call("smcb_gaussL_factor", dev.ptr(gram), n_total, D, self.RIDGE, dev.ptr(G), dev.ptr(logdet),
                    dev.ptr(scratch), st)
+        self.last_status = logdet
         out = dev.empty(n)
         frag = dev.empty(2 * D * (D + 8) + 4096)
         _cabi.call("smcb_gaussL_logpdf", dev.ptr(r), dev.ptr(x), n, D, dev.ptr(mean), dev.ptr(G), dev.ptr(logdet),

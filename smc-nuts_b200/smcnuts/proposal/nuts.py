@@ -169,4 +169,5 @@ class NUTSProposal:
             _cabi.call("smcb_std_normal_logpdf", dev.ptr(rd), rd.shape[0], self.target.dim, dev.ptr(out),
                        dev.stream_ptr())
             return dev.like_input(out, r)
-        return self.momentum_proposal.logpdf(r)
+        # foreign momentum plugin (e.g. a scipy frozen distribution): it gets host NumPy, whatever container came in
+        return self.momentum_proposal.logpdf(dev.to_numpy(r))

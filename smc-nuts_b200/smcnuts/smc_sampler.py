@@ -78,6 +78,7 @@ class SMCSampler:
             self._logw_saved[0].copy_(self.samples.logw)
         else:
             self._x_saved = self._logw_saved = None
+        self._x_saved_host = self._logw_saved_host = None
 
         self._mean_dev = dev.zeros(self.K + 1, D)
         self._var_dev = dev.zeros(self.K + 1, D)
@@ -85,13 +86,31 @@ class SMCSampler:
         self.mean_estimate = np.zeros([self.K + 1, D])
         self.variance_estimate = np.zeros([self.K + 1, D])
 
-    # history is exposed with the reference's names; device tensors (use .cpu().numpy() for host copies)
+    # History under the reference's names (smc_sampler.py:73-74): host NumPy arrays [K+1, N, D] / [K+1, N], materialised
+    # lazily from the device-resident history on first access and cached (this rank's shard when particles are sharded).
+    # `x_saved_dev` / `logw_saved_dev` are the CUDA tensors themselves.
     @property
     def x_saved(self):
-        return self._x_saved
+        if self._x_saved is None:
+            return None
+        if self._x_saved_host is None:
+            self._x_saved_host = self._x_saved.cpu().numpy()
+        return self._x_saved_host
 
     @property
     def logw_saved(self):
+        if self._logw_saved is None:
+            return None
+        if self._logw_saved_host is None:
+            self._logw_saved_host = self._logw_saved.cpu().numpy()
+        return self._logw_saved_host
+
+    @property
+    def x_saved_dev(self):
+        return self._x_saved
+
+    @property
+    def logw_saved_dev(self):
         return self._logw_saved
 
     def update_sampler(self, k, mean_estimate, variance_estimate):
@@ -136,6 +155,7 @@ class SMCSampler:
         if self.save_history:
             self._x_saved[k + 1].copy_(s.x_new)
             self._logw_saved[k + 1].copy_(s.logw_new)
+            self._x_saved_host = self._logw_saved_host = None
 
     def finish(self):
         """Final estimates from the last proposal step (smc_sampler.py:143-155)."""
@@ -160,6 +180,9 @@ class SMCSampler:
 
         torch.cuda.synchronize()
         self.run_time = time() - self._start_time
+        s.resampler.close()           # peer-mapped migration buffers (sharded runs)
+        if hasattr(self.estimator, "resampler"):
+            self.estimator.resampler.close()
 
     def sample(self, show_progress=True):
         """Sample from the target distribution using an SMC sampler (smc_sampler.py:101-155)."""

@@ -317,6 +317,29 @@ def golden_lkernel_weights():
     print("lkernel_weights.npz", len(out))
 
 
+# ------------------------------------------------------------------ D2. Gaussian-approx L-kernel with a singular C_xx
+def golden_lkernel_degenerate():
+    """Cases where cov(x_new) is rank deficient, so that np.linalg.pinv (gaussian_lkernel.py:64-75) is not an inverse:
+    N <= D, and N > D with the particles collapsed onto few distinct rows (heavy duplication after resampling)."""
+    out = {}
+    gen = np.random.default_rng(17)
+    cases = {"n_le_d_4": (4, 4), "n_le_d_13": (13, 10), "dup_13": (13, 64), "dup_4": (4, 50)}
+    for tag, (D, N) in cases.items():
+        class T:  # noqa: N801
+            dim = D
+        if tag.startswith("dup"):
+            distinct = gen.normal(size=(3 if D == 4 else 6, D))
+            x_new = distinct[gen.integers(0, len(distinct), size=N)]
+        else:
+            x_new = gen.normal(size=(N, D))
+        r_new = gen.normal(size=(N, D))
+        with np.errstate(all="ignore"):
+            out[f"{tag}_L"] = GaussianApproxLKernel(T, N).calculate_L(r_new, x_new)
+        out[f"{tag}_r_new"], out[f"{tag}_x_new"] = r_new, x_new
+        print(f"degenerate {tag}: L in [{out[f'{tag}_L'].min():.6g}, {out[f'{tag}_L'].max():.6g}]")
+    np.savez_compressed(OUT / "lkernel_degenerate.npz", **out)
+
+
 # ------------------------------------------------------------------ E. tempering / bisect
 def golden_tempering():
     out = {}
@@ -386,6 +409,23 @@ def golden_runs():
     np.savez_compressed(OUT / "runs.npz", **out)
 
 
+# ------------------------------------------------------------------ G. experiments/plot_experiments.py::mse_mean_var
+def golden_mse():
+    """The reference's plot_experiments.py imports seaborn/matplotlib (absent here), so the function is lifted out of the
+    unmodified file by its AST and executed as is."""
+    import ast
+    src = Path("/root/reference/experiments/plot_experiments.py").read_text()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "mse_mean_var")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "plot_experiments.py", "exec"), ns)
+    gen = np.random.default_rng(4)
+    x = gen.normal(size=(7, 16, 4)) * 0.1 + np.array([0.0, 0.95, -0.03, 0.17])
+    truth = np.array([0.00678443, 0.95700831, -0.03407898, 0.16660982])
+    mean, var = ns["mse_mean_var"](x, truth)
+    np.savez_compressed(OUT / "mse.npz", x=x, truth=truth, mse_mean=mean, mse_var=var)
+    print("mse.npz", mean[:3], var[:3])
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["models", "nuts", "choice", "lkernel", "tempering", "runs"]
     if "models" in which:
@@ -402,3 +442,7 @@ if __name__ == "__main__":
         golden_tempering()
     if "runs" in which:
         golden_runs()
+    if "lkernel_degenerate" in which or not sys.argv[1:]:
+        golden_lkernel_degenerate()
+    if "mse" in which or not sys.argv[1:]:
+        golden_mse()

@@ -347,6 +347,26 @@ def test_gaussian_lkernel_matches_reference_golden(golden, D):
     np.testing.assert_allclose(L, g[f"gaussL_{D}_L"], rtol=1e-8 if D == 100 else 1e-9)
 
 
+@pytest.mark.parametrize("tag,D", [("n_le_d_4", 4), ("n_le_d_13", 13), ("dup_13", 13), ("dup_4", 4)])
+def test_gaussian_lkernel_singular_cxx_follows_the_reference_pinv(golden, tag, D):
+    """cov(x_new) rank deficient (N <= D, or particles collapsed onto a few distinct rows): the reference inverts it with
+    np.linalg.pinv (gaussian_lkernel.py:64-75) and stays finite; the device factorisation detects the unusable Cholesky
+    pivot and takes the pseudo-inverse path (one-CTA Jacobi, numpy's 1e-15 cutoff) instead of producing NaN."""
+    g = golden("lkernel_degenerate")
+    m, _ = _models(f"gauss{D}")
+    r_new, x_new = g[f"{tag}_r_new"], g[f"{tag}_x_new"]
+    lk = GaussianApproxLKernel(m, len(r_new))
+    L = lk.calculate_L(r_new, x_new)
+    assert np.all(np.isfinite(L))
+    assert lk.last_status.cpu().numpy()[1] == 1.0                    # pseudo-inverse path taken
+    np.testing.assert_allclose(L, g[f"{tag}_L"], rtol=1e-6, atol=1e-6)
+    # a well-conditioned case still takes the Cholesky path
+    g2 = golden("lkernel_weights")
+    lk2 = GaussianApproxLKernel(m, len(g2[f"gaussL_{D}_r_new"]))
+    lk2.calculate_L(g2[f"gaussL_{D}_r_new"], g2[f"gaussL_{D}_x_new"])
+    assert lk2.last_status.cpu().numpy()[1] == 0.0
+
+
 def test_gaussian_lkernel_large_n_matches_oracle():
     rng = np.random.default_rng(9)
     D, n = 6, 200_003

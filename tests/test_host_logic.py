@@ -358,3 +358,14 @@ def test_fast_exp_and_fast_log_tables_and_algorithms():
         ref = mp.log(mp.mpf(float(u)))
         worst = max(worst, float(abs(mp.mpf(flog(float(u))) - ref)) / max(1.0, abs(float(ref))))
     assert worst <= 2.5e-16, worst
+
+
+def test_mse_mean_var_matches_the_reference_function(golden):
+    """experiments/run_experiments.py::mse_mean_var against outputs of the unmodified plot_experiments.py:60-78."""
+    sys.path.insert(0, str(ROOT / "experiments"))
+    from run_experiments import mse_mean_var, mse_per_iteration
+    g = golden("mse")
+    mean, var = mse_mean_var(g["x"], g["truth"])
+    np.testing.assert_allclose(mean, g["mse_mean"], rtol=1e-13)
+    np.testing.assert_allclose(var, g["mse_var"], rtol=1e-12)
+    np.testing.assert_allclose(mse_per_iteration(g["x"], g["truth"]), g["mse_mean"], rtol=1e-13)

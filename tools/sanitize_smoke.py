@@ -13,7 +13,9 @@ for name, kw, eps, lk, temp, N, K, rs in (("arma", {}, 0.01, "forwardsLKernel", 
                                           ("PRMwCD", {}, 0.01, "asymptoticLKernel", True, 64, 2, "multinomial"),
                                           ("gauss", {"dim": 8}, 0.1, "GaussianApproxLKernel", False, 500, 2, "systematic"),
                                           ("gauss", {"dim": 100}, 0.1, "GaussianApproxLKernel", False, 400, 2, "systematic"),
-                                          ("gauss", {"dim": 110}, 0.1, "forwardsLKernel", False, 64, 1, "multinomial")):
+                                          ("gauss", {"dim": 110}, 0.1, "forwardsLKernel", False, 64, 1, "multinomial"),
+                                          ("gauss", {"dim": 128}, 0.1, "forwardsLKernel", False, 64, 2, "multinomial"),
+                                          ("gauss", {"dim": 120}, 0.1, "GaussianApproxLKernel", False, 300, 1, "systematic")):
     m = make_model(name, **kw)
     s = SMCSampler(K=K, N=N, target=m, step_size=eps, sample_proposal=StdNormal(m.dim), momentum_proposal=StdNormal(m.dim),
                    lkernel=lk, tempering=temp, rng=3, resampling=rs)
