@@ -125,20 +125,28 @@ class use_library:
 
     def __enter__(self):
         global _LIB, LIB_PATH
-        self._saved = (_LIB, LIB_PATH)
+        self._saved = (_LIB, LIB_PATH, dict(_FN))
         _LIB, LIB_PATH = None, self.path
+        _FN.clear()
         return lib()
 
     def __exit__(self, *exc):
         global _LIB, LIB_PATH
-        _LIB, LIB_PATH = self._saved
+        _LIB, LIB_PATH = self._saved[:2]
+        _FN.clear()
+        _FN.update(self._saved[2])
         return False
+
+
+_FN = {}
 
 
 def call(name, *args):
     """Invoke a status-returning entry point and raise SmcbError on failure."""
-    L = lib()
-    rc = getattr(L, name)(*args)
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(lib(), name)
+    rc = fn(*args)
     if rc != 0:
-        raise SmcbError(f"{name} failed ({rc}): {L.smcb_last_error().decode()}")
+        raise SmcbError(f"{name} failed ({rc}): {lib().smcb_last_error().decode()}")
     return rc

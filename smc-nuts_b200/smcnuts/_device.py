@@ -10,10 +10,22 @@ from . import _cabi
 F64 = torch.float64
 
 
+_CUDA_OK = None
+_DEVICES = {}
+
+
 def device():
-    if not torch.cuda.is_available():
+    """torch.device of the current CUDA device (cached objects: this is called for every allocation)."""
+    global _CUDA_OK
+    if _CUDA_OK is None:
+        _CUDA_OK = torch.cuda.is_available()
+    if not _CUDA_OK:
         raise _cabi.SmcbError("smcnuts device path needs a CUDA device (no CPU fallback exists)")
-    return torch.device("cuda", torch.cuda.current_device())
+    i = torch.cuda.current_device()
+    d = _DEVICES.get(i)
+    if d is None:
+        d = _DEVICES[i] = torch.device("cuda", i)
+    return d
 
 
 def stream_ptr():
@@ -127,8 +139,14 @@ def workspace(tag, nbytes):
     return buf
 
 
+_REDUCE_WS_BYTES = None
+
+
 def reduce_ws():
-    return workspace("reduce", _cabi.lib().smcb_reduce_workspace_bytes())
+    global _REDUCE_WS_BYTES
+    if _REDUCE_WS_BYTES is None:
+        _REDUCE_WS_BYTES = _cabi.lib().smcb_reduce_workspace_bytes()
+    return workspace("reduce", _REDUCE_WS_BYTES)
 
 
 def seed_from_rng(rng):

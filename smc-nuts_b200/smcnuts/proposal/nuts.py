@@ -5,6 +5,8 @@ Mirrors smcnuts/proposal/nuts.py of the reference: `NUTSProposal(target, momentu
 recursive build_tree (nuts.py:50-53,114-150) are one persistent CUDA kernel (csrc/nuts_kernel.cu).
 """
 
+import os
+
 import torch
 
 from .. import _cabi, _device as dev
@@ -41,6 +43,7 @@ class NUTSProposal:
         self.last = None          # per-particle by-products of the last transition (device tensors)
         self.record_events = False  # bench.py: CUDA events tightly around the kernel launch
         self.events = []
+        self._ws_bytes = {}
 
     # Host inputs of at least this many particles go through the pipelined path (copy/compute overlap)
     PIPELINE_MIN_PARTICLES = 1 << 16
@@ -118,6 +121,17 @@ class NUTSProposal:
         self.last = o
         return dev.host_result(xo_h, x_cond), dev.host_result(ro_h, r_cond)
 
+    def _workspace_bytes(self, N):
+        # the kernel variant (and its scratch) also depends on the A/B environment switches of csrc/nuts_kernel.cu
+        key = (N, self.max_tree_depth, _cabi.LIB_PATH, os.environ.get("SMCB_PRM_SCALAR"), os.environ.get("SMCB_GAUSS_SCALAR"),
+               os.environ.get("SMCB_NUTS_BLOCKS_PER_SM"))
+        b = self._ws_bytes.get(key)
+        if b is None:
+            nbytes = _cabi._ll()
+            _cabi.call("smcb_nuts_workspace_bytes", self.target.handle, N, self.max_tree_depth, nbytes)
+            b = self._ws_bytes[key] = nbytes.value
+        return b
+
     def _alloc_outputs(self, N, D, want_grad):
         o = dict(x_new=dev.empty(N, D), r_new=dev.empty(N, D), A_old=dev.empty(N), B_old=dev.empty(N),
                  A_new=dev.empty(N), B_new=dev.empty(N), ke_old=dev.empty(N), ke_new=dev.empty(N),
@@ -145,9 +159,7 @@ class NUTSProposal:
         model evaluation of every transition; want_grad=True also returns g_new for the next call."""
         N, D = x.shape
         it = self.iteration if iteration is None else iteration
-        nbytes = _cabi._ll()
-        _cabi.call("smcb_nuts_workspace_bytes", self.target.handle, N, self.max_tree_depth, nbytes)
-        ws = dev.workspace("nuts", nbytes.value)
+        ws = dev.workspace("nuts", self._workspace_bytes(N))
         if self.accept_reject:
             carry, want_grad = None, False
         o = self._alloc_outputs(N, D, want_grad)

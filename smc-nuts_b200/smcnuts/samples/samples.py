@@ -310,10 +310,21 @@ class Samples:
         self.logw = dev.empty(self.n_local)
         _cabi.call("smcb_uniform_logw", dev.ptr(self._stats), self.N, self.n_local, dev.ptr(self.logw), dev.stream_ptr())
 
+    def prefetch_momentum(self):
+        """Enqueue this iteration's momentum draw (samples.py:155) ahead of the host synchronisation on ESS: it depends
+        only on (seed, iteration), and having it queued shortens the GPU idle gap between the resampling decision and
+        the NUTS launch."""
+        self._r_ready = (self.iteration, self._draw_std_normal(self.forward_kernel.momentum_proposal,
+                                                               _cabi.STREAM_MOMENTUM, self.iteration))
+
     def propose_samples(self):
         """samples.py:149-158."""
         fk = self.forward_kernel
-        self.r = self._draw_std_normal(fk.momentum_proposal, _cabi.STREAM_MOMENTUM, self.iteration)
+        ready = getattr(self, "_r_ready", None)
+        if ready is not None and ready[0] == self.iteration:
+            self.r, self._r_ready = ready[1], None
+        else:
+            self.r = self._draw_std_normal(fk.momentum_proposal, _cabi.STREAM_MOMENTUM, self.iteration)
         if hasattr(fk, "transition"):
             fk.particle0 = self.offset
             # constant temperature and no MH epilogue: the evaluation at x_new is the next iteration's evaluation at x.

@@ -139,6 +139,7 @@ class SMCSampler:
         self.phi[k] = s.phi_new
         s.normalise_weights()
         mean_estimate, variance_estimate = self.estimator.return_estimate(s.x, s.wn)
+        s.prefetch_momentum()         # queued before the one host synchronisation of the iteration (ESS, below)
         s.calculate_ess()
         s.resample_if_required()
         self.resampled[k] = s.resampled_last

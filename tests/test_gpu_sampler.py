@@ -114,12 +114,16 @@ def test_prmwcd_config3_estimates_match_gold_standard_and_oracle_runs():
     dev_final = s.mean_estimate[K]
     err = np.abs(dev_final - PRM_TRUTH) / PRM_SD
     assert np.all(err < 0.15), (dev_final, err)
-    R = 8
-    orc = np.array([O.OracleSMC(15, 256, "PRMwCD", 0.01, "asymptoticLKernel", True, seed=10 * (i + 1), nthreads=8).run().mean_estimate[15]
+    # repeated small runs, the reference's recipe (N = 256, K = 15, seeds 10*(i+1)) on both sides: the two samplers are
+    # the same algorithm on different arithmetic, so their estimate distributions must agree within MC error
+    R, Ns, Ks = 16, 256, 15
+    orc = np.array([O.OracleSMC(Ks, Ns, "PRMwCD", 0.01, "asymptoticLKernel", True, seed=10 * (i + 1), nthreads=8).run().mean_estimate[Ks]
                     for i in range(R)])
-    se = orc.std(axis=0, ddof=1) / np.sqrt(R)
-    z = np.abs(dev_final - orc.mean(axis=0)) / se
-    assert np.all((z < 4.0) | (np.abs(dev_final - orc.mean(axis=0)) < 0.15 * PRM_SD)), (z, dev_final, orc.mean(axis=0))
+    dvc = np.array([_run("PRMwCD", {}, Ns, Ks, 0.01, "asymptoticLKernel", True, seed=10 * (i + 1)).mean_estimate[Ks]
+                    for i in range(R)])
+    se = np.sqrt(orc.var(axis=0, ddof=1) / R + dvc.var(axis=0, ddof=1) / R)
+    z = np.abs(dvc.mean(axis=0) - orc.mean(axis=0)) / se
+    assert np.all(z < 4.0), (z, dvc.mean(axis=0), orc.mean(axis=0))
     # the variance estimates are posterior variances: same order as the gold-standard column 3 squared
     assert np.all(s.variance_estimate[K] > 0.2 * PRM_SD ** 2) and np.all(s.variance_estimate[K] < 5.0 * PRM_SD ** 2)
 
