@@ -67,5 +67,15 @@ def _build_one(OUT, obj_dir, extra_flags, force, verbose):
     return OUT
 
 
+def build_variant(tag, flags):
+    """A/B experiments: another build of the same sources with extra -D flags -> _lib/libsmcnuts_b200_<tag>.so
+    (select it with SMCB_LIB_PATH; tools/ab_time.py)."""
+    return _build_one(OUT_DIR / f"libsmcnuts_b200_{tag}.so", HERE / f"build_{tag}", list(flags), False, False)
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

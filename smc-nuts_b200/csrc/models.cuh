@@ -53,6 +53,7 @@ struct ArmaModel {
     static constexpr int DMAX = 4;
     static constexpr int STATIC_D = 4;
     static constexpr int GROUP = 1, NLOC = 4, STATIC_NL = 4;   // one lane per particle, 4 coordinates per lane
+    static constexpr bool STAGE = false;                       // U-turn operands straight from the workspace (see nuts_lane.cuh)
     SMCB_HD constexpr int nloc() const { return 4; }
     const double* y;
     int T;
@@ -162,6 +163,7 @@ struct PrmModel {
     static constexpr int DMAX = 13;
     static constexpr int STATIC_D = 13;
     static constexpr int GROUP = 1, NLOC = 13, STATIC_NL = 13;
+    static constexpr bool STAGE = false;
     SMCB_HD constexpr int nloc() const { return 13; }
     static constexpr int M = 12, C = 11, ROW = 12, HDR = 16;
     const double* hdr;
@@ -278,6 +280,7 @@ struct PrmModelG {
     static constexpr int DMAX = 16;
     static constexpr int STATIC_D = 0;
     static constexpr int GROUP = 4, NLOC = 4, STATIC_NL = 4;
+    static constexpr bool STAGE = false;
     static constexpr int M = 12, HDRG = 32;
     static constexpr int PF1 = HDRG, PF2 = PF1 + NT * 3 * 32, YM = PF2 + NT * 4 * 32, TOTAL = YM + NT * 2 * 32;
     const double* blk;
@@ -433,6 +436,7 @@ struct GaussModel {
     static constexpr int DMAX = 128;
     static constexpr int STATIC_D = 0;  // runtime dimension
     static constexpr int GROUP = 1, NLOC = 128, STATIC_NL = 0;
+    static constexpr bool STAGE = false;
     SMCB_HD int nloc() const { return D; }
     const double* P;
     int D;
@@ -466,6 +470,13 @@ struct GaussModelG {
     static constexpr int DMAX = 8 * NT8;
     static constexpr int STATIC_D = 0;
     static constexpr int GROUP = 4, NLOC = 2 * NT8, STATIC_NL = 2 * NT8, KK = 2 * NT8;
+    // wide records (> 4 coordinates per lane): the stored edge of a U-turn test is staged in shared memory (cp.async /
+    // the previous leaf written directly) instead of being loaded into registers the kernel does not have
+#if defined(SMCB_NO_STAGE)   // A/B experiments only
+    static constexpr bool STAGE = false;
+#else
+    static constexpr bool STAGE = NLOC > 4;
+#endif
     const double* pfrag;  // [NT8][KK][32] doubles, shared memory
     int D;
     SMCB_HD explicit GaussModelG(const ModelDesc& d, const double* staged) : pfrag(staged), D(d.dim) {}

@@ -51,9 +51,12 @@ template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BL
 template <int T8> struct LaunchCfg<PrmModelG<T8>> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
 constexpr int kPrmTiles = 13;   // PrmModelG instantiation: 81..104 observations (the shipped PRMwCD has 100)
 
+// staged model data, then (M::STAGE) one staging row per thread for the stored edge of the U-turn tests
 template <class M>
 static size_t nuts_smem_bytes(const ModelDesc& d) {
-    return sizeof(double) * (size_t)M::staged_doubles(d);
+    size_t n = (size_t)M::staged_doubles(d);
+    if (M::STAGE) n += (size_t)LaunchCfg<M>::NT * nuts_stage_stride(M::STATIC_NL);
+    return sizeof(double) * n;
 }
 
 template <class M> struct StageOffset { static int of(const ModelDesc&) { return 0; } };
@@ -94,6 +97,7 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
     const unsigned lane_id = threadIdx.x & 31u;
     Lane<M> lane;
     lane.idle_init(model, (int)(lane_id % G));
+    lane.stg = M::STAGE ? smem + staged + (size_t)threadIdx.x * nuts_stage_stride(M::STATIC_NL) : nullptr;
     double* ws = a.ws + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * rec_doubles;
     constexpr unsigned kLeaders = G == 1 ? 0xffffffffu : 0x11111111u;   // first lane of every particle group
     const unsigned group_first = lane_id & ~(unsigned)(G - 1);

@@ -22,6 +22,14 @@
 //     sub-tree U-turn nuts.py:148) ends the transition at once, because the reference then never
 //     reads the sub-tree's candidate nor draws again from this particle's stream.
 //
+// Wide records (more than 4 coordinates per lane: the Gaussian tensor-core kernels, 26 per lane at D = 100) cannot
+// afford registers for the stored edge of a U-turn test -- with 255 registers in use the compiler chops its 52 loads
+// into short dependent batches, and the kernel spent 45 % of its warp time on their L2 round trips (ncu, round 2).
+// For those (M::STAGE) every lane owns a staging row in shared memory: the first leaf of a two-leaf sub-tree is copied
+// there when it is stored (the level-0 test at the next leaf, half of all tests, then never touches the workspace), and
+// deeper checkpoints / the other edge arrive by cp.async -- all 26 16-byte copies in flight at once, no registers --
+// issued before the Philox draw and the merge bookkeeping that precede the test.
+//
 // The selected sample: when a doubling is accepted and its candidate sits in a leaf slot, the lane only remembers the
 // slot (it stays allocated across doublings) and copies it into the caller's x_new/r_new row once, at the end of the
 // transition; a candidate that is the leaf in registers, and the start point, are written to the row at once.
@@ -72,15 +80,22 @@ struct alignas(16) D2 {
 
 // Workspace record of one LANE (global memory, 128-byte aligned; nlp = nl rounded up to even so that every vector is
 // 16-byte aligned):
+//   header[8]: A0 B0 ke0 | As Bs kes | 2 unused -- the split log densities and kinetic energies of the start point and of
+//              the selected sample: written once or twice per transition, read at its end, so they live here and not in
+//              registers that are precious across the model evaluation
 //   other edge: x[nlp] r[nlp] g[nlp] | 2L+3 leaf slots, each x[nlp] r[nlp] A B [g[nlp]]
 // A leaf state is stored at most ONCE: the first leaf of a sub-tree (U-turn checkpoint) and a pending candidate are
 // the same record when they are the same leaf (every odd leaf of a doubling is both); checkpoints and candidates
 // are slot references handed out from one free mask.  Candidates carry their gradient only when the caller asked
 // for g_new.
 SMCB_HD int nuts_nlp(int nl) { return (nl + 1) & ~1; }
+// doubles per lane of the shared-memory staging row (x[nlp] r[nlp] + 2 of padding: lanes then start 4 banks apart in
+// every quarter-warp phase of an LDS.128, i.e. conflict-free)
+SMCB_HD int nuts_stage_stride(int nl) { return 2 * nuts_nlp(nl) + 2; }
 SMCB_HD int nuts_slot_stride(int nl, bool carry) { return 2 * nuts_nlp(nl) + 2 + (carry ? nuts_nlp(nl) : 0); }
+constexpr int kNutsHdr = 8;
 SMCB_HD int nuts_ws_doubles(int nl, int L, bool carry = true) {
-    return ((3 * nuts_nlp(nl) + nuts_slot_stride(nl, carry) * (2 * L + 3)) + 15) & ~15;
+    return ((kNutsHdr + 3 * nuts_nlp(nl) + nuts_slot_stride(nl, carry) * (2 * L + 3)) + 15) & ~15;
 }
 
 enum LanePhase : int { kIdle = 0, kInit = 1, kLeaf = 2 };
@@ -93,10 +108,11 @@ struct Lane {
     static constexpr int G = M::GROUP;
     static constexpr int DM = M::NLOC;
     double xa[DM], ra[DM], ga[DM];  // active edge (this lane's coordinates)
-    double logu, A0, B0, As, Bs, ke0, kes;
+    double logu;
     long long pid;
     double* ws;       // per-lane record in global memory
-    int nlp, slot_stride;
+    double* stg;      // per-lane staging row in shared memory (M::STAGE only): x[nlp] r[nlp] of a stored edge
+    int nlp_, slot_stride;
     int phase, dir, depth, D, L, nl, sub;
     uint32_t leaf, n_tot, n_leapfrog;
     uint32_t ck_used, cand_used, ck_valid;   // slots referenced by live checkpoints / candidates; valid checkpoint ids
@@ -109,6 +125,21 @@ struct Lane {
 #define SMCB_PAIRS(i) for (int i = 0; i < (M::STATIC_NL ? M::STATIC_NL : nl); i += 2)
 
     SMCB_HD int gd(int i) const { return G == 1 ? i : sub + G * i; }   // global coordinate of local slot i
+    // ---- draws of this particle's NUTS stream, in the reference's order (nuts.py:69,91,99,142)
+    SMCB_HD uint64_t draw_bits(const NutsArgs& a) {
+        return rng.next_bits(a.seed, (a.iteration << 8) | (uint32_t)kStreamNuts, a.particle0 + (uint64_t)pid);
+    }
+    SMCB_HD double draw(const NutsArgs& a) { return (double)draw_bits(a) * 0x1.0p-53; }
+    // u < num/den for integers 0 <= num, 1 <= den < 2^11, decided in exact integer arithmetic: k * den < num * 2^53.
+    // The reference compares u with the ROUNDED quotient (nuts.py:142, :99); the two can only differ when u is the
+    // 2^-53-grid neighbour of num/den, i.e. with probability ~2^-53 per draw -- and no FP64 division is needed.
+    SMCB_HD bool draw_below_ratio(const NutsArgs& a, uint32_t num, uint32_t den) {
+        const uint64_t k = draw_bits(a);
+        return k * (uint64_t)den < ((uint64_t)num << 53);
+    }
+    // padded coordinates per lane: a compile-time constant for the static models (no register)
+    SMCB_HD int nlp_get() const { return M::STATIC_NL ? ((M::STATIC_NL + 1) & ~1) : nlp_; }
+#define nlp nlp_get()
     SMCB_HD double gsum(double v) const {
 #if defined(SMCB_WARP_CODE)
         if (G > 1) {
@@ -142,10 +173,10 @@ struct Lane {
     }
 
     // ---- record views
-    SMCB_HD double* other_x() const { return ws; }
-    SMCB_HD double* other_r() const { return ws + nlp; }
-    SMCB_HD double* other_g() const { return ws + 2 * nlp; }
-    SMCB_HD double* slotp(int slot) const { return ws + 3 * nlp + slot_stride * slot; }   // x[nlp] r[nlp] A B [g[nlp]]
+    SMCB_HD double* other_x() const { return ws + kNutsHdr; }
+    SMCB_HD double* other_r() const { return ws + kNutsHdr + nlp; }
+    SMCB_HD double* other_g() const { return ws + kNutsHdr + 2 * nlp; }
+    SMCB_HD double* slotp(int slot) const { return ws + kNutsHdr + 3 * nlp + slot_stride * slot; }   // x[nlp] r[nlp] A B [g[nlp]]
     SMCB_HD int alloc_slot() {
         const uint32_t free_ = ~(ck_used | cand_used | samp_used);
         return ctz32(free_);   // 2L+3 <= 23 slots: at most L checkpoints + L+1 candidates + the selected sample are live
@@ -179,12 +210,12 @@ struct Lane {
     }
 
     SMCB_HD void idle_init(const M& m, int sub_) {
-        phase = kIdle; sub = sub_; D = m.dim(); nl = m.nloc(); nlp = nuts_nlp(nl); pid = -1;
+        phase = kIdle; sub = sub_; D = m.dim(); nl = m.nloc(); nlp_ = nuts_nlp(nl); pid = -1;
         SMCB_LOCAL(i) { xa[i] = 0.0; ra[i] = 0.0; ga[i] = 0.0; }
     }
 
     SMCB_HD void begin(const NutsArgs& a, const M& m, long long p, double* ws_) {
-        pid = p; ws = ws_; D = m.dim(); nl = m.nloc(); nlp = nuts_nlp(nl); L = a.max_depth;
+        pid = p; ws = ws_; D = m.dim(); nl = m.nloc(); nlp_ = nuts_nlp(nl); L = a.max_depth;
         const int d_ = D;
 #pragma unroll
         SMCB_LOCAL(i) {
@@ -192,7 +223,7 @@ struct Lane {
             xa[i] = ok ? a.x[p * d_ + gd(i)] : 0.0;
             ra[i] = ok ? a.r[p * d_ + gd(i)] : 0.0;
         }
-        rng.reset(a.seed, a.iteration, kStreamNuts, a.particle0 + (uint64_t)p);
+        rng.reset();
         n_leapfrog = 0;
         slot_stride = nuts_slot_stride(nl, a.g_new != nullptr);
         phase = kInit;
@@ -214,8 +245,8 @@ struct Lane {
         }
     }
 
-    SMCB_HD void start_doubling(bool first) {
-        const int nd = (rng.next_bits() < (1ull << 52)) ? 1 : -1;  // u < 0.5, nuts.py:91
+    SMCB_HD void start_doubling(const NutsArgs& a, bool first) {
+        const int nd = (draw_bits(a) < (1ull << 52)) ? 1 : -1;  // u < 0.5, nuts.py:91
         if (!first && nd != dir) {                   // bring the other edge into registers
             double tx[DM], tr[DM], tg[DM];
             ldv(other_x(), tx); ldv(other_r(), tr); ldv(other_g(), tg);
@@ -229,14 +260,81 @@ struct Lane {
     }
 
     // start_doubling(false) when x and r of the other edge are already in registers (only its gradient is loaded)
-    SMCB_HD void start_doubling_with(const double (&xo)[DM], const double (&ro)[DM]) {
-        const int nd = (rng.next_bits() < (1ull << 52)) ? 1 : -1;  // u < 0.5, nuts.py:91
+    SMCB_HD void start_doubling_with(const NutsArgs& a, const double (&xo)[DM], const double (&ro)[DM]) {
+        const int nd = (draw_bits(a) < (1ull << 52)) ? 1 : -1;  // u < 0.5, nuts.py:91
         if (nd != dir) {
             double tg[DM];
             ldv(other_g(), tg);
             stv(other_x(), xa); stv(other_r(), ra); stv(other_g(), ga);
 #pragma unroll
             SMCB_LOCAL(i) { xa[i] = xo[i]; ra[i] = ro[i]; ga[i] = tg[i]; }
+        }
+        dir = nd;
+        leaf = 0; pend_n = 0; pend_ref = 0; ck_ref = 0;
+        ck_used = cand_used = ck_valid = 0;
+    }
+
+    // ---- shared-memory staging of a stored edge (M::STAGE)
+    static constexpr bool kStage = M::STAGE;
+    SMCB_HD void stage_from_regs() {   // the active edge (the leaf just stored) -> staging row
+        stv(stg, xa); stv(stg + nlp, ra);
+    }
+    // start copying x[nlp] r[nlp] at c (workspace, contiguous) into the staging row; nothing waits here
+    SMCB_HD void stage_issue(const double* c) {
+#if defined(__CUDA_ARCH__)
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(stg);
+#pragma unroll
+        for (int i = 0; i < 2 * DM; i += 2)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 8u * i), "l"(c + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+        for (int i = 0; i < 2 * nlp; ++i) stg[i] = c[i];
+#endif
+    }
+    SMCB_HD void stage_wait() const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+    }
+    // U-turn test of the staged edge against the active edge, operands read pair by pair from shared memory
+    SMCB_HD bool uturn_stage() const {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        SMCB_PAIRS(i) {
+            const D2 xc = *reinterpret_cast<const D2*>(stg + i);
+            const D2 rc = *reinterpret_cast<const D2*>(stg + nlp + i);
+            const double dx0 = xa[i] - xc.x;
+            s1 += dx0 * rc.x;
+            s2 += dx0 * ra[i];
+            if (i + 1 < DM) {
+                const double dx1 = xa[i + 1 < DM ? i + 1 : i] - xc.y;
+                s1 += dx1 * rc.y;
+                s2 += dx1 * ra[i + 1 < DM ? i + 1 : i];
+            }
+        }
+        s1 = gsum(s1); s2 = gsum(s2);
+        return (dir * s1 < 0) || (dir * s2 < 0);
+    }
+    // start_doubling(false) when x and r of the other edge sit in the staging row: exchange the edges pair by pair
+    SMCB_HD void start_doubling_from_stage(const NutsArgs& a) {
+        const int nd = (draw_bits(a) < (1ull << 52)) ? 1 : -1;  // u < 0.5, nuts.py:91
+        if (nd != dir) {
+            double* og = other_g();
+#pragma unroll
+            SMCB_PAIRS(i) {
+                const D2 tg = *reinterpret_cast<const D2*>(og + i);
+                const D2 tx = *reinterpret_cast<const D2*>(stg + i);
+                const D2 tr = *reinterpret_cast<const D2*>(stg + nlp + i);
+                D2 mx, mr, mg;
+                mx.x = xa[i]; mr.x = ra[i]; mg.x = ga[i];
+                const int j = i + 1 < DM ? i + 1 : i;
+                mx.y = xa[j]; mr.y = ra[j]; mg.y = ga[j];
+                *reinterpret_cast<D2*>(other_x() + i) = mx;
+                *reinterpret_cast<D2*>(other_r() + i) = mr;
+                *reinterpret_cast<D2*>(og + i) = mg;
+                xa[i] = tx.x; ra[i] = tr.x; ga[i] = tg.x;
+                if (i + 1 < DM) { xa[j] = tx.y; ra[j] = tr.y; ga[j] = tg.y; }
+            }
         }
         dir = nd;
         leaf = 0; pend_n = 0; pend_ref = 0; ck_ref = 0;
@@ -276,8 +374,10 @@ struct Lane {
         if (G == 1 && (d_ & 1) == 0) {
             stv(base + pid * d_, v);   // rows of an even number of doubles are 16-byte aligned (torch allocations are)
         } else {
+            double* row = base + pid * d_ + (G == 1 ? 0 : sub);
+            const int n_ok = G == 1 ? d_ : (d_ - sub + G - 1) / G;   // local slots that hold a real coordinate
 #pragma unroll
-            SMCB_LOCAL(i) if (gd(i) < d_) base[pid * d_ + gd(i)] = v[i];
+            SMCB_LOCAL(i) if (i < n_ok) row[G * i] = v[i];
         }
     }
 
@@ -285,24 +385,40 @@ struct Lane {
         write_row(a.x_new, xa);
         write_row(a.r_new, ra);
         if (a.g_new) write_row(a.g_new, ga);
-        As = A; Bs = B; kes = ke;
+        ws[3] = A; ws[4] = B; ws[5] = ke;   // every lane of a group keeps the (identical) scalars in its own record
         samp_ref = -1; samp_used = 0u;
     }
 
-    // the deferred copy of a sample that still sits in its leaf slot (see the header comment)
-    SMCB_HD void flush_sample(const NutsArgs& a) {
-        if (samp_ref < 0) return;
-        const double* c = slotp(samp_ref);
-        double t[DM];
-        ldv(c, t); write_row(a.x_new, t);
-        ldv(c + nlp, t); write_row(a.r_new, t);
-        double k2 = 0.0;
+    // The deferred copy of the selected sample into the caller's row; returns its (A, B, kinetic energy).
+    //   samp_ref >= 0: it sits in a leaf slot;  -1: it is already in the row (values in the header);
+    //   -2: it is still the start point -- the row is copied from the inputs here, once, instead of being written at the
+    //       start of every transition and usually overwritten
+    SMCB_HD void flush_sample(const NutsArgs& a, double& As, double& Bs, double& kes) {
+        const int d_ = D;
+        if (samp_ref == -2) {
+            const double* xin = a.x + pid * d_ + (G == 1 ? 0 : sub);
+            const double* rin = a.r + pid * d_ + (G == 1 ? 0 : sub);
+            double* xo = a.x_new + pid * d_ + (G == 1 ? 0 : sub);
+            double* ro = a.r_new + pid * d_ + (G == 1 ? 0 : sub);
+            const int n_ok = G == 1 ? d_ : (d_ - sub + G - 1) / G;
 #pragma unroll
-        SMCB_LOCAL(i) k2 += t[i] * t[i];
-        kes = 0.5 * gsum(k2);
-        const D2 ab = *reinterpret_cast<const D2*>(c + 2 * nlp);
-        As = ab.x; Bs = ab.y;
-        if (a.g_new) { ldv(c + 2 * nlp + 2, t); write_row(a.g_new, t); }
+            SMCB_LOCAL(i) if (i < n_ok) { xo[G * i] = xin[G * i]; ro[G * i] = rin[G * i]; }
+            As = ws[0]; Bs = ws[1]; kes = ws[2];
+        } else if (samp_ref < 0) {
+            As = ws[3]; Bs = ws[4]; kes = ws[5];
+        } else {
+            const double* c = slotp(samp_ref);
+            double t[DM];
+            ldv(c, t); write_row(a.x_new, t);
+            ldv(c + nlp, t); write_row(a.r_new, t);
+            double k2 = 0.0;
+#pragma unroll
+            SMCB_LOCAL(i) k2 += t[i] * t[i];
+            kes = 0.5 * gsum(k2);
+            const D2 ab = *reinterpret_cast<const D2*>(c + 2 * nlp);
+            As = ab.x; Bs = ab.y;
+            if (a.g_new) { ldv(c + 2 * nlp + 2, t); write_row(a.g_new, t); }
+        }
         samp_ref = -1; samp_used = 0u;
     }
 
@@ -313,18 +429,22 @@ struct Lane {
         double rr = 0.0;
 #pragma unroll
         SMCB_LOCAL(i) rr += ra[i] * ra[i];
-        ke0 = 0.5 * gsum(rr);
-        A0 = A; B0 = B;
+        const double ke0 = 0.5 * gsum(rr);
+        ws[0] = A; ws[1] = B; ws[2] = ke0;
         const double H0 = lp - ke0;
 #if SMCB_TABLE_MATH
-        logu = H0 + fast_log(1.0 - rng.next());      // 1 - u is exact; table-driven log (common.cuh), <= 2.2e-16 absolute
+        logu = H0 + fast_log(1.0 - draw(a));      // 1 - u is exact; table-driven log (common.cuh), <= 2.2e-16 absolute
 #else
-        logu = H0 - (-log1p(-rng.next()));
+        logu = H0 - (-log1p(-draw(a)));
 #endif
-        write_sample_from_active(a, A, B, ke0);
+        if (a.g_new) {   // gradient carry-over wants the start point's gradient in the row: write it now
+            write_sample_from_active(a, A, B, ke0);
+        } else {
+            samp_ref = -2; samp_used = 0u;
+        }
         stv(other_x(), xa); stv(other_r(), ra); stv(other_g(), ga);
         n_tot = 1; depth = 0;
-        start_doubling(true);
+        start_doubling(a, true);
         phase = kLeaf;
     }
 
@@ -373,16 +493,18 @@ struct Lane {
                 // the pending level-0 candidate
                 run_ref = store_leaf(a, A, B);
                 set_ck(popc32(i0), run_ref);
+                if constexpr (kStage) stage_from_regs();   // it is the level-0 checkpoint of the next leaf
             } else {
                 const int tz = ctz32(leaf);
                 for (int l = 0; l < tz; ++l) {  // nuts.py:136-148, second child = running node
                     const double* ck = slotp(get_ck(popc32(i0 - (2u << l) + 1u)));
                     double xc[kEarly ? DM : 1], rc[kEarly ? DM : 1];
                     if constexpr (kEarly) { ldv(ck, xc); ldv(ck + nlp, rc); }
+                    if constexpr (kStage) { if (l > 0) stage_issue(ck); }   // l == 0: staged when the previous leaf was stored
                     const uint32_t n1 = get_n(l);
                     const int ref1 = get_ref(l);
                     const uint32_t tot = n1 + run_n;
-                    if (rng.next_below_ratio(run_n, tot > 1u ? tot : 1u)) {   // u < n''/max(n'+n'', 1), nuts.py:142
+                    if (draw_below_ratio(a, run_n, tot > 1u ? tot : 1u)) {   // u < n''/max(n'+n'', 1), nuts.py:142
                         cand_used &= ~(1u << ref1);
                     } else {
                         if (run_ref >= 0) cand_used &= ~(1u << run_ref);
@@ -391,6 +513,7 @@ struct Lane {
                     run_n = tot;
                     bool stop;
                     if constexpr (kEarly) stop = uturn_regs(xc, rc);
+                    else if constexpr (kStage) { stage_wait(); stop = uturn_stage(); }
                     else stop = uturn(ck);
                     if (stop) { ++depth; return finish(a); }
                 }
@@ -399,8 +522,9 @@ struct Lane {
         if (leaf == nleaves) {  // doubling complete and not stopped: nuts.py:99-110
             double xo[kEarly ? DM : 1], ro[kEarly ? DM : 1];   // the other edge: needed by the trajectory U-turn test
             if constexpr (kEarly) { ldv(other_x(), xo); ldv(other_r(), ro); }   // and, on a direction flip, as the new active edge
+            if constexpr (kStage) stage_issue(other_x());
             // u < min(1, n'/n), nuts.py:99; u < 1 always, so only n' < n needs the comparison (the draw is consumed anyway)
-            const bool take = rng.next_below_ratio(run_n, n_tot) || run_n >= n_tot;
+            const bool take = draw_below_ratio(a, run_n, n_tot) || run_n >= n_tot;
             if (take) {
                 if (run_ref < 0) {
                     write_sample_from_active(a, A, B, 0.5 * rr);
@@ -411,11 +535,13 @@ struct Lane {
             n_tot += run_n;
             bool stop;
             if constexpr (kEarly) stop = uturn_regs(xo, ro);
+            else if constexpr (kStage) { stage_wait(); stop = uturn_stage(); }
             else stop = uturn(other_x());
             ++depth;
             if (stop || depth > L) return finish(a);
-            if constexpr (kEarly) start_doubling_with(xo, ro);
-            else start_doubling(false);
+            if constexpr (kEarly) start_doubling_with(a, xo, ro);
+            else if constexpr (kStage) start_doubling_from_stage(a);
+            else start_doubling(a, false);
             return false;
         }
         // park the running node as the pending first child of level ctz(leaf)
@@ -430,7 +556,9 @@ struct Lane {
     // End of transition: optional endpoint MH step (nuts_acc_rej.py:42-49, utils.py:22-34) and outputs.
     SMCB_HD bool finish(const NutsArgs& a) {
         const int d_ = D;
-        flush_sample(a);
+        double As, Bs, kes;
+        flush_sample(a, As, Bs, kes);
+        const double A0 = ws[0], B0 = ws[1], ke0 = ws[2];
         double ken = kes;
         int anyinf = 0;
         if (a.accrej) {   // np.any(np.isinf(x_prime)), utils.py:32
@@ -478,6 +606,7 @@ struct Lane {
     }
 #undef SMCB_LOCAL
 #undef SMCB_PAIRS
+#undef nlp
 };
 
 }  // namespace smcb

@@ -70,17 +70,16 @@ SMCB_HD double stream_uniform(uint64_t seed, uint32_t iter, uint32_t stream, uin
     return (draw & 1) ? u64_to_unit(b.w[2], b.w[3]) : u64_to_unit(b.w[0], b.w[1]);
 }
 
-// Sequential reader of one stream; caches the second half of each Philox block.
+// Sequential reader of one stream; caches the second half of each Philox block.  The stream identity (seed, iteration and
+// stream id, particle) is passed at every draw instead of being stored: in the NUTS kernels it comes from kernel
+// arguments (constant bank), and the reader then costs three registers instead of eight.
 struct StreamReader {
-    uint64_t seed, particle;
-    uint32_t iter_stream, pos;
+    uint32_t pos;
     uint32_t c_lo, c_hi;  // cached words 2,3 of the current block
 
-    SMCB_HD void reset(uint64_t seed_, uint32_t iter, uint32_t stream, uint64_t particle_) {
-        seed = seed_; particle = particle_; iter_stream = (iter << 8) | stream; pos = 0; c_lo = c_hi = 0;
-    }
+    SMCB_HD void reset() { pos = 0; c_lo = c_hi = 0; }
     // next draw as the 53-bit integer k; the uniform is u = k * 2^-53 (numpy's double construction)
-    SMCB_HD uint64_t next_bits() {
+    SMCB_HD uint64_t next_bits(uint64_t seed, uint32_t iter_stream, uint64_t particle) {
         uint64_t k;
         if ((pos & 1) == 0) {
             Philox4 b = philox4x32_10(pos >> 1, iter_stream, (uint32_t)particle, (uint32_t)(particle >> 32),
@@ -92,14 +91,6 @@ struct StreamReader {
         }
         ++pos;
         return k;
-    }
-    SMCB_HD double next() { return (double)next_bits() * 0x1.0p-53; }
-    // u < num/den for integers 0 <= num, 1 <= den < 2^11, decided in exact integer arithmetic: k * den < num * 2^53.
-    // The reference compares u with the ROUNDED quotient (nuts.py:142, :99); the two can only differ when u is the
-    // 2^-53-grid neighbour of num/den, i.e. with probability ~2^-53 per draw -- and no FP64 division is needed.
-    SMCB_HD bool next_below_ratio(uint32_t num, uint32_t den) {
-        const uint64_t k = next_bits();
-        return k * (uint64_t)den < ((uint64_t)num << 53);
     }
 };
 

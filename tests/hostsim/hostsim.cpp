@@ -16,7 +16,7 @@ static void run(NutsArgs a, int lanes) {
     std::vector<double> ws((size_t)lanes * rec, 0.0);
     std::vector<Lane<M>> L(lanes);
     M model(a.model, a.model.data);
-    for (auto& l : L) l.idle_init(model, 0);
+    for (auto& l : L) { l.idle_init(model, 0); l.stg = nullptr; }
     long long head = 0;
     for (;;) {
         bool any = false;

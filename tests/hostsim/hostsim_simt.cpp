@@ -15,11 +15,14 @@ static void run_warp_kernel(NutsArgs a, const double* staged) {
     constexpr int G = M::GROUP;
     const int rec = nuts_ws_doubles(M(a.model, staged).nloc(), a.max_depth, a.g_new != nullptr);
     std::vector<double> ws((size_t)simt_emu::kLanes * rec, 0.0);
+    const int stride = nuts_stage_stride(M(a.model, staged).nloc());
+    std::vector<double> stage((size_t)simt_emu::kLanes * stride, 0.0);   // the staging rows of the device kernel's shared memory
     unsigned long long head = 0;
     simt_emu::run_warp([&](int lane_id) {
         M model(a.model, staged);
         Lane<M> lane;
         lane.idle_init(model, lane_id % G);
+        lane.stg = stage.data() + (size_t)lane_id * stride;
         double* w = ws.data() + (size_t)lane_id * rec;
         constexpr unsigned kLeaders = G == 1 ? 0xffffffffu : 0x11111111u;
         const unsigned group_first = (unsigned)lane_id & ~(unsigned)(G - 1);
