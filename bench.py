@@ -193,9 +193,9 @@ def run_micro(args):
         _cabi.call("smcb_reweight_forward", dev.ptr(logw), dev.ptr(lp_x), dev.ptr(lp_xn), dev.ptr(r), dev.ptr(r_new), n, D,
                    dev.ptr(out), st)
         if ev: ev[1].record()
-        wn, stats, _ = normalise(out, sh)
+        wn, stats, _, scan = normalise(out, sh, scan=True)     # lse + normalise, with the tile sums of the scan fused in
         if ev: ev[2].record()
-        cdf = rs._cdf(wn)
+        cdf = rs._cdf(wn, scan)                                # second pass of the scan
         if ev: ev[3].record()
         rs_x = rs.resample_from_cdf(x, cdf, it)
         if ev: ev[4].record()

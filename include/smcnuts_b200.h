@@ -143,6 +143,15 @@ long long smcb_scan_workspace_bytes(long long N);
  * prefix before normalisation and total_in (nullable) replaces the local total: the multi-GPU global scan. */
 int smcb_cdf(const double* wn, long long N, const double* offset_in, const double* total_in, double* cdf,
              double* total_out, void* workspace, void* stream);
+/* The same scan in two halves, the first fused with the normalisation (samples.py:101-102): wn = exp(logw - logZ) is
+ * written and summed per 2048-element tile in ONE pass, the tile sums are scanned (local exclusive offsets and
+ * total_out[0] stay in `workspace`); smcb_cdf_from_tilesums then writes cdf = (offset + prefix) / total, with
+ * offset_total = NULL (single GPU: offset 0, local total) or a device pair (rank offset, global total) from
+ * smcb_rank_offsets.  lse + normalise + scan move 8 + 16 + 16 bytes per particle in total. */
+int smcb_normalise_tilesums(const double* logw, long long N, const double* logZ, double* wn, double* total_out,
+                            void* workspace, void* stream);
+int smcb_cdf_from_tilesums(const double* wn, long long N, const double* offset_total, double* cdf, void* workspace,
+                           void* stream);
 int smcb_ancestors_multinomial(const double* cdf, long long N, const double* u, long long M, int64_t* idx,
                                void* stream);
 /* systematic: positions (j0 + j + u0)/M_total, j = 0..M-1 (north_star; not in the reference) */

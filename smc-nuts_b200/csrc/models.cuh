@@ -502,12 +502,15 @@ struct GaussModelG {
                 dmma(c[2 * nt], c[2 * nt + 1], av, bp[(nt * KK + kk) * 32]);
             }
         }
-        double qf = 0.0;
+        double qf = 0.0, qf1 = 0.0;   // two partial sums: the NLOC-term chain of dependent DFMAs is pure latency
 #pragma unroll
-        for (int i = 0; i < NLOC; ++i) {
+        for (int i = 0; i < NLOC; i += 2) {
             g[i] = phi * (-c[i]);
             qf += x[i] * c[i];
+            g[i + 1] = phi * (-c[i + 1]);
+            qf1 += x[i + 1] * c[i + 1];
         }
+        qf += qf1;
         qf += __shfl_xor_sync(0xffffffffu, qf, 1);
         qf += __shfl_xor_sync(0xffffffffu, qf, 2);
         A = 0.0;

@@ -52,6 +52,21 @@ template <int T8> struct LaunchCfg<PrmModelG<T8>> { static constexpr int NT = 12
 constexpr int kPrmTiles = 13;   // PrmModelG instantiation: 81..104 observations (the shipped PRMwCD has 100)
 
 // staged model data, then (M::STAGE) one staging row per thread for the stored edge of the U-turn tests
+// Parity alignment of the refill.  A particle that starts at trip t0 stores a leaf (first leaf of a two-leaf sub-tree)
+// at trips t0+2, t0+4, ... and merges / ends doublings at the trips in between: every doubling after the first has an
+// even number of leaves.  When the particles of a warp start at trips of mixed parity, every trip executes BOTH
+// divergent paths of the lane bookkeeping; when new particles are only admitted at even trips, all particles of a warp
+// store on even trips and merge on odd ones, and a trip executes one path.  The price is one idle trip for half of
+// the refills (1 % of the work at 50 leapfrogs per particle); results do not depend on the lane assignment.
+#ifndef SMCB_ALIGN_PARITY
+#define SMCB_ALIGN_PARITY 0
+#endif
+template <class M> struct AlignCfg { static constexpr bool ON = (SMCB_ALIGN_PARITY != 0) && M::GROUP > 1; };
+#if SMCB_ALIGN_PARITY == 2   // A/B experiments: also for the one-lane-per-particle kernels
+template <> struct AlignCfg<ArmaModel> { static constexpr bool ON = true; };
+template <> struct AlignCfg<PrmModel> { static constexpr bool ON = true; };
+#endif
+
 template <class M>
 static size_t nuts_smem_bytes(const ModelDesc& d) {
     size_t n = (size_t)M::staged_doubles(d);
@@ -102,9 +117,12 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
     constexpr unsigned kLeaders = G == 1 ? 0xffffffffu : 0x11111111u;   // first lane of every particle group
     const unsigned group_first = lane_id & ~(unsigned)(G - 1);
     bool drained = false;
-    for (;;) {
+    // with gradient carry-over the tree starts in the trip a particle is admitted, one trip earlier than otherwise
+    const unsigned admit_parity = a.g_in ? 1u : 0u;
+    for (unsigned trip = 0;; ++trip) {
         // ---- refill finished particle groups from the work queue (warp-aggregated atomic)
-        const bool want = (lane.phase == kIdle) && !drained;
+        const bool admit = !AlignCfg<M>::ON || ((trip & 1u) == admit_parity);
+        const bool want = (lane.phase == kIdle) && !drained && admit;
         const unsigned m = __ballot_sync(0xffffffffu, want) & kLeaders;
         if (m) {
             const int leader = __ffs(m) - 1;
@@ -117,7 +135,10 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
                 else drained = true;
             }
         }
-        if (__all_sync(0xffffffffu, lane.phase == kIdle)) break;
+        if (__all_sync(0xffffffffu, lane.phase == kIdle)) {
+            if (!AlignCfg<M>::ON || __all_sync(0xffffffffu, drained)) break;
+            continue;   // nobody active at a non-admitting trip: the queue is asked again at the next one
+        }
         // ---- one model evaluation per particle per trip: the initial point or one leapfrog.  The evaluation is
         //      executed by every lane (idle ones carry zeros) so that warp-wide tensor-core instructions stay legal.
         if (lane.phase != kIdle) lane.pre_eval(a);

@@ -298,7 +298,8 @@ struct Lane {
     }
     // U-turn test of the staged edge against the active edge, operands read pair by pair from shared memory
     SMCB_HD bool uturn_stage() const {
-        double s1 = 0.0, s2 = 0.0;
+        // two partial sums per dot product: the 26-term chains of dependent DFMAs are latency, not throughput
+        double s1 = 0.0, s2 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll
         SMCB_PAIRS(i) {
             const D2 xc = *reinterpret_cast<const D2*>(stg + i);
@@ -308,12 +309,32 @@ struct Lane {
             s2 += dx0 * ra[i];
             if (i + 1 < DM) {
                 const double dx1 = xa[i + 1 < DM ? i + 1 : i] - xc.y;
-                s1 += dx1 * rc.y;
-                s2 += dx1 * ra[i + 1 < DM ? i + 1 : i];
+                t1 += dx1 * rc.y;
+                t2 += dx1 * ra[i + 1 < DM ? i + 1 : i];
             }
         }
-        s1 = gsum(s1); s2 = gsum(s2);
+        s1 = gsum(s1 + t1); s2 = gsum(s2 + t2);
         return (dir * s1 < 0) || (dir * s2 < 0);
+    }
+    // sum of squares of the active momentum: split into partial sums for wide records (a group kernel's summation order
+    // differs from the oracle's sequential one anyway; the one-lane kernels keep the oracle's order for bit-parity)
+    SMCB_HD double ra_sqnorm() const {
+        if constexpr (G > 1 && DM > 4) {
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < DM; i += 4) {
+                p0 += ra[i] * ra[i];
+                if (i + 1 < DM) p1 += ra[i + 1 < DM ? i + 1 : i] * ra[i + 1 < DM ? i + 1 : i];
+                if (i + 2 < DM) p2 += ra[i + 2 < DM ? i + 2 : i] * ra[i + 2 < DM ? i + 2 : i];
+                if (i + 3 < DM) p3 += ra[i + 3 < DM ? i + 3 : i] * ra[i + 3 < DM ? i + 3 : i];
+            }
+            return (p0 + p1) + (p2 + p3);
+        } else {
+            double rr = 0.0;
+#pragma unroll
+            SMCB_LOCAL(i) rr += ra[i] * ra[i];
+            return rr;
+        }
     }
     // start_doubling(false) when x and r of the other edge sit in the staging row: exchange the edges pair by pair
     SMCB_HD void start_doubling_from_stage(const NutsArgs& a) {
@@ -426,10 +447,7 @@ struct Lane {
     SMCB_HD void init_tree(const NutsArgs& a, double A, double B) {
         double lp = A + a.phi * B;
         if (!is_finite(lp)) lp = neg_inf();
-        double rr = 0.0;
-#pragma unroll
-        SMCB_LOCAL(i) rr += ra[i] * ra[i];
-        const double ke0 = 0.5 * gsum(rr);
+        const double ke0 = 0.5 * gsum(ra_sqnorm());
         ws[0] = A; ws[1] = B; ws[2] = ke0;
         const double H0 = lp - ke0;
 #if SMCB_TABLE_MATH
@@ -472,13 +490,9 @@ struct Lane {
 
         // ---- leaf: second half-kick, slice and divergence tests (nuts.py:121-125,173)
         const double half = dir * a.eps / 2;
-        double rr = 0.0;
 #pragma unroll
-        SMCB_LOCAL(i) {
-            ra[i] = ra[i] + half * ga[i];
-            rr += ra[i] * ra[i];
-        }
-        rr = gsum(rr);
+        SMCB_LOCAL(i) ra[i] = ra[i] + half * ga[i];
+        const double rr = gsum(ra_sqnorm());
         ++n_leapfrog;
         ++leaf;
         const double joint = lp - 0.5 * rr;

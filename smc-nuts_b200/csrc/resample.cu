@@ -93,13 +93,91 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(double* tile_su
     }
 }
 
+// phase 2, wide: ONE pass of a 1024-thread block over all tile sums (thread t owns a contiguous run of them: sequential
+// sum, block scan of the 1024 run totals, sequential write-back of the exclusive offsets).  Replaces the 256-wide chunked
+// loop above, whose ntiles/256 dependent round trips (64 at 2^25 particles) were a third of the whole scan.
+constexpr int kWideThreads = 1024;
+__global__ void __launch_bounds__(kWideThreads) tile_scan_wide_kernel(double* tile_sums, long long ntiles,
+                                                                       const double* __restrict__ offset_in,
+                                                                       const double* __restrict__ total_in,
+                                                                       double* total_out, double* norm_total) {
+    __shared__ double wsum[kWideThreads / 32];
+    __shared__ double btotal;
+    const long long ipt = (ntiles + kWideThreads - 1) / kWideThreads;
+    const long long lo = min(ntiles, (long long)threadIdx.x * ipt), hi = min(ntiles, lo + ipt);
+    double s = 0.0;
+    for (long long i = lo; i < hi; ++i) s += tile_sums[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double incl = warp_incl_scan(s);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const double w = wsum[lane];
+        const double wi = warp_incl_scan(w);
+        wsum[lane] = wi - w;
+        if (lane == 31) btotal = wi;
+    }
+    __syncthreads();
+    const double carry0 = offset_in ? *offset_in : 0.0;
+    double off = carry0 + (wsum[warp] + (incl - s));
+    for (long long i = lo; i < hi; ++i) {
+        const double v = tile_sums[i];
+        tile_sums[i] = off;
+        off += v;
+    }
+    if (threadIdx.x == 0) {
+        total_out[0] = btotal;                               // this rank's local weight total
+        norm_total[0] = total_in ? *total_in : carry0 + btotal;   // normaliser: global total when sharded
+    }
+}
+
+// samples.py:101-102 fused with phase 1 of the scan: wn = exp(logw - logZ) (0 where logw = -inf) is written AND summed
+// per tile in the same pass, so the weights are read from HBM once for normalisation and tile sums together
+// (lse + normalise + scan: 8 + 16 + 16 bytes per particle in total, the algorithmic figure).
+__global__ void __launch_bounds__(kScanThreads) normalise_tile_sum_kernel(const double* __restrict__ logw, long long N,
+                                                                           const double* __restrict__ logZ,
+                                                                           double* __restrict__ wn,
+                                                                           double* __restrict__ tile_sums,
+                                                                           long long ntiles) {
+    __shared__ double sm[kTile + kTile / 32];
+    const double z = *logZ;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * kTile;
+        double w[kScanItems];
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = k * kScanThreads + threadIdx.x;
+            const double x = (base + e < N) ? logw[base + e] : neg_inf();
+            w[k] = (x == neg_inf()) ? 0.0 : fast_exp(x - z);
+        }
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = k * kScanThreads + threadIdx.x;
+            if (base + e < N) wn[base + e] = w[k];
+            sm[e + e / 32] = w[k];
+        }
+        __syncthreads();
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = threadIdx.x * kScanItems + k;
+            s += sm[e + e / 32];
+        }
+        double total;
+        block_incl_scan(s, &total);
+        if (threadIdx.x == 0) tile_sums[tile] = total;
+    }
+}
+
 // phase 3: scan each tile, add its offset, normalise: cdf = prefix / total  (numpy: cdf /= cdf[-1])
 __global__ void __launch_bounds__(kScanThreads) tile_cdf_kernel(const double* __restrict__ w, long long N,
                                                                  const double* __restrict__ tile_offsets,
                                                                  const double* __restrict__ norm_total,
+                                                                 const double* __restrict__ extra_offset,
                                                                  double* __restrict__ cdf, long long ntiles) {
     __shared__ double sm[kTile + kTile / 32];
-    const double tot = *norm_total;
+    const double tot = extra_offset ? extra_offset[1] : *norm_total;   // (rank offset, global total) when sharded late
+    const double xoff = extra_offset ? extra_offset[0] : 0.0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long base = tile * kTile;
 #pragma unroll
@@ -117,7 +195,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_cdf_kernel(const double* __
         }
         double total;
         const double incl = block_incl_scan(s, &total);
-        const double off = tile_offsets[tile] + (incl - s);
+        const double off = (xoff + tile_offsets[tile]) + (incl - s);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
@@ -348,9 +426,36 @@ int smcb_cdf(const double* wn, long long N, const double* offset_in, const doubl
     const int grid = (int)(ntiles < cap ? ntiles : cap);
     tile_sum_kernel<<<grid, kScanThreads, 0, st>>>(wn, N, tile_sums, ntiles);
     if (check_launch("tile_sum_kernel")) return -1;
-    tile_scan_kernel<<<1, kScanThreads, 0, st>>>(tile_sums, ntiles, offset_in, total_in, total_out, norm_total);
-    if (check_launch("tile_scan_kernel")) return -1;
-    tile_cdf_kernel<<<grid, kScanThreads, 0, st>>>(wn, N, tile_sums, norm_total, cdf, ntiles);
+    tile_scan_wide_kernel<<<1, kWideThreads, 0, st>>>(tile_sums, ntiles, offset_in, total_in, total_out, norm_total);
+    if (check_launch("tile_scan_wide_kernel")) return -1;
+    tile_cdf_kernel<<<grid, kScanThreads, 0, st>>>(wn, N, tile_sums, norm_total, nullptr, cdf, ntiles);
+    return check_launch("tile_cdf_kernel");
+}
+
+int smcb_normalise_tilesums(const double* logw, long long N, const double* logZ, double* wn, double* total_out,
+                            void* workspace, void* stream) {
+    SMCB_REQUIRE(logw && logZ && wn && total_out && workspace && N >= 1, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ntiles = (N + kTile - 1) / kTile;
+    double* tile_sums = (double*)workspace;
+    double* norm_total = tile_sums + ntiles;
+    const long long cap = (long long)device_sm_count() * 8;
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    normalise_tile_sum_kernel<<<grid, kScanThreads, 0, st>>>(logw, N, logZ, wn, tile_sums, ntiles);
+    if (check_launch("normalise_tile_sum_kernel")) return -1;
+    tile_scan_wide_kernel<<<1, kWideThreads, 0, st>>>(tile_sums, ntiles, nullptr, nullptr, total_out, norm_total);
+    return check_launch("tile_scan_wide_kernel");
+}
+
+int smcb_cdf_from_tilesums(const double* wn, long long N, const double* offset_total, double* cdf, void* workspace,
+                           void* stream) {
+    SMCB_REQUIRE(wn && cdf && workspace && N >= 1, "bad argument");
+    const long long ntiles = (N + kTile - 1) / kTile;
+    double* tile_sums = (double*)workspace;
+    double* norm_total = tile_sums + ntiles;
+    const long long cap = (long long)device_sm_count() * 8;
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    tile_cdf_kernel<<<grid, kScanThreads, 0, (cudaStream_t)stream>>>(wn, N, tile_sums, norm_total, offset_total, cdf, ntiles);
     return check_launch("tile_cdf_kernel");
 }
 

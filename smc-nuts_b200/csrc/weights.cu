@@ -330,11 +330,47 @@ __device__ void lse_block_finish(Lse (&v)[NV], double* ws, double* out, int nv) 
     }
 }
 
+// Four elements at once: one running-max update (rare after the first few elements), then four independent exps --
+// no per-element branch on the running maximum, 16-byte loads.  Same semantics as lse_push element by element
+// (-inf dropped, NaN poisons, an element equal to the maximum counts exactly 1).
+__device__ __forceinline__ void lse_push4(Lse& a, double x0, double x1, double x2, double x3) {
+    double mn = a.m;
+    mn = (x0 > mn) ? x0 : mn; mn = (x1 > mn) ? x1 : mn; mn = (x2 > mn) ? x2 : mn; mn = (x3 > mn) ? x3 : mn;
+    if (mn > a.m) {
+        const double f = fast_exp(a.m - mn);   // exp(-inf) = 0 on the first finite element
+        a.s1 *= f; a.s2 *= f * f; a.m = mn;
+    }
+    const double ninf = neg_inf();
+    double e0, e1, e2, e3;
+    fast_exp_pair(x0 - mn, x1 - mn, e0, e1);
+    fast_exp_pair(x2 - mn, x3 - mn, e2, e3);
+    e0 = (x0 == mn) ? 1.0 : e0; e1 = (x1 == mn) ? 1.0 : e1; e2 = (x2 == mn) ? 1.0 : e2; e3 = (x3 == mn) ? 1.0 : e3;
+    e0 = (x0 == ninf) ? 0.0 : e0; e1 = (x1 == ninf) ? 0.0 : e1; e2 = (x2 == ninf) ? 0.0 : e2; e3 = (x3 == ninf) ? 0.0 : e3;
+    a.s1 += (e0 + e1) + (e2 + e3);
+    a.s2 += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+}
+
 __global__ void __launch_bounds__(kRedThreads) lse_partial_kernel(const double* __restrict__ logw, long long N,
                                                                    double* out3, double* ws) {
     Lse v[1] = {lse_empty()};
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
-        lse_push(v[0], logw[i]);
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(logw) & 15) == 0) {
+        const long long nq = N / 4;
+        const double2* p = reinterpret_cast<const double2*>(logw);
+        long long q = tid;
+        for (; q + nthr < nq; q += 2 * nthr) {   // two quads in flight per thread
+            const double2 a0 = p[2 * q], b0 = p[2 * q + 1], a1 = p[2 * (q + nthr)], b1 = p[2 * (q + nthr) + 1];
+            lse_push4(v[0], a0.x, a0.y, b0.x, b0.y);
+            lse_push4(v[0], a1.x, a1.y, b1.x, b1.y);
+        }
+        for (; q < nq; q += nthr) {
+            const double2 a0 = p[2 * q], b0 = p[2 * q + 1];
+            lse_push4(v[0], a0.x, a0.y, b0.x, b0.y);
+        }
+        for (long long i = 4 * nq + tid; i < N; i += nthr) lse_push(v[0], logw[i]);
+    } else {
+        for (long long i = tid; i < N; i += nthr) lse_push(v[0], logw[i]);
+    }
     lse_block_finish<1>(v, ws, out3, 1);
 }
 
@@ -778,7 +814,7 @@ int smcb_lse_partial(const double* logw, long long N, double* out3, void* worksp
     SMCB_REQUIRE(logw && out3 && workspace && N >= 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (reset_counter(workspace, st)) return -1;
-    lse_partial_kernel<<<stride_grid(N, kRedThreads * 4, 4), kRedThreads, 0, st>>>(logw, N, out3, (double*)workspace);
+    lse_partial_kernel<<<stride_grid(N, kRedThreads * 8, 4), kRedThreads, 0, st>>>(logw, N, out3, (double*)workspace);
     return check_launch("lse_partial_kernel");
 }
 

@@ -50,6 +50,8 @@ _SIGS = {
     "smcb_bisect_step": [_vp, _i, _vp, _vp],
     "smcb_bisect_read": [_vp, _vp, _vp],
     "smcb_cdf": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp],
+    "smcb_normalise_tilesums": [_vp, _ll, _vp, _vp, _vp, _vp, _vp],
+    "smcb_cdf_from_tilesums": [_vp, _ll, _vp, _vp, _vp, _vp],
     "smcb_ancestors_multinomial": [_vp, _ll, _vp, _ll, _vp, _vp],
     "smcb_ancestors_systematic": [_vp, _ll, _d, _ll, _ll, _ll, _vp, _vp],
     "smcb_resample_systematic": [_vp, _ll, _d, _vp, _ll, _ll, _ll, _vp, _i, _vp, _vp, _vp, _vp],

@@ -22,8 +22,8 @@ class EstimateFromTempered(Estimate):
         mean_e, var_e = np.zeros([self.K + 1, D]), np.zeros([self.K + 1, D])
         for k in range(self.K + 1):
             xk, lwk = dev.to_device(x_saved[k]), dev.to_device(logw_saved[k])
-            wn, _, _ = normalise(lwk, self.shard)
-            x = self.resampler.resample_rows(xk, wn, iteration=k)
+            wn, _, _, scan = normalise(lwk, self.shard, scan=True)
+            x = self.resampler.resample_rows(xk, wn, iteration=k, scan=scan)
             A, B = self.target.split(x)
             lw = dev.empty(x.shape[0])
             # logpdf(x, 1) - logpdf(x, phi_k)  (estimate_from_tempered.py:47)

@@ -16,8 +16,18 @@ from ..parallel import ShardContext, split_counts, systematic_slot_bounds
 from ..tempering.adaptive_tempering import ESSTempering
 
 
-def normalise(logw, shard):
-    """samples.py:91-113 -> (wn, stats) where stats is a device tensor [logZ, ESS] (global when sharded)."""
+class ScanState:
+    """First half of the cdf scan, produced together with the normalised weights (smcb_normalise_tilesums): the scanned
+    tile sums in `ws` and this rank's weight total.  Valid until the next normalisation."""
+
+    def __init__(self, ws, total):
+        self.ws, self.total = ws, total
+
+
+def normalise(logw, shard, scan=False):
+    """samples.py:91-113 -> (wn, stats, tris[, ScanState]) where stats is a device tensor [logZ, ESS] (global when
+    sharded).  scan=True fuses the first pass of the resampling scan into the normalisation (the weights are read once
+    for both)."""
     n = logw.shape[0]
     st = dev.stream_ptr()
     tri = dev.empty(3)
@@ -26,6 +36,11 @@ def normalise(logw, shard):
     stats = dev.empty(2)
     _cabi.call("smcb_lse_finalize", dev.ptr(tris), shard.world, dev.ptr(stats), st)
     wn = dev.empty(n)
+    if scan:
+        ws = dev.workspace("scan", _cabi.lib().smcb_scan_workspace_bytes(n))
+        total = dev.empty(1)
+        _cabi.call("smcb_normalise_tilesums", dev.ptr(logw), n, dev.ptr(stats), dev.ptr(wn), dev.ptr(total), dev.ptr(ws), st)
+        return wn, stats, tris, ScanState(ws, total)
     _cabi.call("smcb_normalise", dev.ptr(logw), n, dev.ptr(stats), dev.ptr(wn), st)
     return wn, stats, tris
 
@@ -50,8 +65,19 @@ class Resampler:
         self.last_idx = None          # ancestors of the last resample (global indices for this rank's slots)
         self._migrated = 0            # rows this rank received from other ranks in the last resample (diagnostic)
 
-    def _cdf(self, wn):
+    def _cdf(self, wn, scan=None):
         n, st, sh = wn.shape[0], dev.stream_ptr(), self.shard
+        if scan is not None:
+            # the tile sums were produced with the normalised weights: only the second pass of the scan is left
+            cdf = dev.empty(n)
+            off = 0
+            if sh.world > 1:
+                totals = sh.all_gather_vec(scan.total).view(-1).contiguous()
+                off_t = dev.empty(2)
+                _cabi.call("smcb_rank_offsets", dev.ptr(totals), sh.world, sh.rank, dev.ptr(off_t), st)
+                off = dev.ptr(off_t)
+            _cabi.call("smcb_cdf_from_tilesums", dev.ptr(wn), n, off, dev.ptr(cdf), dev.ptr(scan.ws), st)
+            return cdf
         ws = dev.workspace("scan", _cabi.lib().smcb_scan_workspace_bytes(n))
         cdf, total = dev.empty(n), dev.empty(1)
         if sh.world == 1:
@@ -67,9 +93,9 @@ class Resampler:
                    dev.ptr(ws), st)
         return cdf
 
-    def resample_rows(self, x, wn, iteration):
-        """Returns the resampled rows for this rank's output slots."""
-        return self.resample_from_cdf(x, self._cdf(wn), iteration)
+    def resample_rows(self, x, wn, iteration, scan=None):
+        """Returns the resampled rows for this rank's output slots.  scan: the ScanState that came with `wn`."""
+        return self.resample_from_cdf(x, self._cdf(wn, scan), iteration)
 
     def resample_from_cdf(self, x, cdf, iteration):
         sh, st = self.shard, dev.stream_ptr()
@@ -233,6 +259,7 @@ class Samples:
             self.phi_old = 1.0
             self.phi_new = 1.0
         self._stats = None
+        self._scan = None
         self._carry = None       # (A, B, grad) at the current x, handed back to the NUTS kernel (skips its initial evaluation)
         self.carry_gradients = False
         self._split_new = None   # (A, B) at x_new from the last transition
@@ -280,7 +307,7 @@ class Samples:
 
     def normalise_weights(self):
         """samples.py:91-105 (+ the sums calculate_ess needs, from the same pass)."""
-        self.wn, self._stats, _ = normalise(self.logw, self.shard)
+        self.wn, self._stats, _, self._scan = normalise(self.logw, self.shard, scan=True)
         self._stats_host = None
 
     def _host_stats(self):
@@ -305,7 +332,8 @@ class Samples:
 
     def _resample(self, x, wn, log_likelihood):
         """samples.py:125-146."""
-        self.x = self.resampler.resample_rows(x, wn, self.iteration)
+        scan = self._scan if wn is self.wn else None
+        self.x = self.resampler.resample_rows(x, wn, self.iteration, scan)
         self._carry = None   # the carried evaluation belongs to the pre-resampling rows
         self.logw = dev.empty(self.n_local)
         _cabi.call("smcb_uniform_logw", dev.ptr(self._stats), self.N, self.n_local, dev.ptr(self.logw), dev.stream_ptr())

@@ -471,6 +471,26 @@ def test_cdf_scan_and_systematic(n):
     assert np.all(np.abs(counts - n * wn) < 1.0 + 1e-6 * n)                      # systematic: |offspring - N w| < 1
 
 
+def test_fused_normalise_scan_equals_the_separate_passes():
+    """normalise(scan=True) (weights written and tile-summed in one pass) followed by the second scan pass gives the same
+    wn and, bit for bit, the same cdf as normalise + smcb_cdf; non-multiples of the tile size and -inf weights included."""
+    sh = ShardContext()
+    rng = np.random.default_rng(8)
+    for n in (1, 7, 2048, 2049, 300_001):
+        logw = rng.normal(size=n) * 4.0
+        if n > 4:
+            logw[rng.integers(0, n, n // 7)] = -np.inf
+        lw = dev.to_device(logw)
+        wn_a, stats_a, _ = normalise(lw, sh)
+        wn_b, stats_b, _, scan = normalise(lw, sh, scan=True)
+        assert torch.equal(wn_a, wn_b) and torch.equal(stats_a, stats_b)
+        cdf_a, _ = _cdf_dev(wn_a.cpu().numpy())
+        rs = Resampler(n, 1, sh)
+        cdf_b = rs._cdf(wn_b, scan)
+        assert torch.equal(cdf_a, cdf_b)
+        np.testing.assert_allclose(cdf_b.cpu().numpy(), O.cdf_of(wn_b.cpu().numpy()), rtol=1e-12, atol=1e-15)
+
+
 def test_gather_rows():
     rng = np.random.default_rng(0)
     for D, n in ((4, 1000), (13, 777), (16, 100_000), (100, 50)):
