@@ -64,9 +64,12 @@ int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long lon
 int smcb_nuts_transition(void* handle, const double* x, const double* r, long long N, double eps, double phi,
                          int max_depth, int accrej, uint64_t seed, uint32_t iteration, uint64_t particle0,
                          double* x_new, double* r_new, double* A_old, double* B_old, double* A_new, double* B_new,
-                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth,
+                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth, double* accept_stat,
                          const double* A_in, const double* B_in, const double* g_in, double* g_new, void* workspace,
                          long long workspace_bytes, void* stream);
+/* accept_stat (nullable): per particle, the mean over its leaves of min(1, exp(joint_leaf - joint_0)) -- the NUTS
+ * acceptance statistic used by dual-averaging step-size adaptation (README.md:66-67 "future updates"; off in the
+ * reference, whose step size is a run constant, nuts.py:31). */
 /* A_in/B_in/g_in (all or none, accrej == 0): the split log density and gradient at x handed back from the previous
  * transition's A_new/B_new/g_new at the same phi -- the initial evaluation (nuts.py:66,72) is then skipped.
  * g_new (nullable): gradient of A + phi*B at the returned x_new. */
@@ -217,6 +220,9 @@ int smcb_gaussL_logpdf(const double* r_new, const double* x_new, long long N, in
 
 /* out[0] (int64) = sum of an int32 array: the per-iteration leapfrog / grad-eval counter */
 int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, void* stream);
+/* out[0] = sum of a double array in fixed tile order: the summed NUTS acceptance statistic that drives the dual-averaging
+ * step-size adaptation (README.md:66-67 "future updates"; the reference's step size is a run constant, nuts.py:31) */
+int smcb_sum_f64(const double* v, long long N, double* out, void* workspace, void* stream);
 
 /* out[i] = exp(x[i]) with the library's in-kernel exp (test hook: accuracy of the hot-loop exp, <= 1.5 ulp) */
 int smcb_fast_exp(const double* x, long long N, double* out, void* stream);

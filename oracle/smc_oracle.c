@@ -255,6 +255,8 @@ typedef struct {
     uint64_t seed, particle, draw;
     uint32_t iter;
     long n_leapfrog;
+    double H0, accept_sum; /* NUTS acceptance statistic (step-size adaptation; not in the reference): sum over the
+                              leaves of min(1, exp(joint - joint_0)) */
 } Ctx;
 
 static double next_uniform(Ctx* c) { return stream_uniform(c->seed, c->iter, 0u, c->particle, c->draw++); }
@@ -293,6 +295,10 @@ static void build_tree(Ctx* c, const double* x, const double* r, const double* g
         for (int d = 0; d < D; ++d) rn[d] = rn[d] + half * gn[d];
         c->n_leapfrog++;
         double joint = lp - 0.5 * dot(rn, rn, D);
+        {
+            double dj = joint - c->H0;
+            c->accept_sum += (dj >= 0.0) ? 1.0 : ((dj == dj) ? m_exp(dj) : 0.0);
+        }
         t->n = (c->logu < joint);
         t->s = ((c->logu - 100.) >= joint);
         memcpy(t->xm, xn, sz); memcpy(t->xp, xn, sz); memcpy(t->xc, xn, sz);
@@ -330,6 +336,7 @@ static void nuts_one(Ctx* c, const double* x0, const double* r0, double* xo, dou
     double g0[MAXD];
     double logp = model_eval(c->m, x0, c->phi, g0);
     double H0 = logp - 0.5 * dot(r0, r0, D);
+    c->H0 = H0; c->accept_sum = 0.0;
     if (g_devmath) {
         c->logu = H0 + m_log_1mu(next_uniform(c));
     } else {
@@ -370,18 +377,32 @@ static void nuts_one(Ctx* c, const double* x0, const double* r0, double* xo, dou
     *lp0_out = logp; *lpsel_out = lpsel; *depth_out = depth;
 }
 
+void orc_nuts_batch_stat(void* h, const double* x, const double* r, long N, double eps, double phi, int max_depth,
+                         uint64_t seed, uint32_t iter, uint64_t particle0, int accrej, double* x_new, double* r_new,
+                         double* lp_old, double* lp_new, int* n_leapfrog, int* accepted, int* depth_out,
+                         double* accept_stat, int nthreads);
+
 /* NUTSProposal.rvs (nuts.py:34-56) and, when accrej != 0, NUTSProposalWithAccRej.rvs
  * (nuts_acc_rej.py:27-52) + hmc_accept_reject (utils.py:22-34).
  * lp_old = logp(x_cond, phi); lp_new = logp(returned x_prime, phi). */
 void orc_nuts_batch(void* h, const double* x, const double* r, long N, double eps, double phi, int max_depth,
                     uint64_t seed, uint32_t iter, uint64_t particle0, int accrej, double* x_new, double* r_new,
                     double* lp_old, double* lp_new, int* n_leapfrog, int* accepted, int* depth_out, int nthreads) {
+    orc_nuts_batch_stat(h, x, r, N, eps, phi, max_depth, seed, iter, particle0, accrej, x_new, r_new, lp_old, lp_new,
+                        n_leapfrog, accepted, depth_out, 0, nthreads);
+}
+
+/* same, also returning accept_stat[i] = accept_sum / n_leapfrog (nullable) */
+void orc_nuts_batch_stat(void* h, const double* x, const double* r, long N, double eps, double phi, int max_depth,
+                         uint64_t seed, uint32_t iter, uint64_t particle0, int accrej, double* x_new, double* r_new,
+                         double* lp_old, double* lp_new, int* n_leapfrog, int* accepted, int* depth_out,
+                         double* accept_stat, int nthreads) {
     const Model* m = (const Model*)h;
     const int D = m->dim;
     (void)nthreads;
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1)
     for (long i = 0; i < N; ++i) {
-        Ctx c = {m, D, max_depth, eps, phi, 0.0, seed, particle0 + (uint64_t)i, 0, iter, 0};
+        Ctx c = {m, D, max_depth, eps, phi, 0.0, seed, particle0 + (uint64_t)i, 0, iter, 0, 0.0, 0.0};
         double lp0, lps;
         int dep;
         nuts_one(&c, x + i * D, r + i * D, x_new + i * D, r_new + i * D, &lp0, &lps, &dep);
@@ -407,5 +428,6 @@ void orc_nuts_batch(void* h, const double* x, const double* r, long N, double ep
         if (n_leapfrog) n_leapfrog[i] = (int)c.n_leapfrog;
         if (accepted) accepted[i] = acc;
         if (depth_out) depth_out[i] = dep;
+        if (accept_stat) accept_stat[i] = c.n_leapfrog ? c.accept_sum / (double)c.n_leapfrog : 0.0;
     }
 }

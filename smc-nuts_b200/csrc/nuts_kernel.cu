@@ -369,7 +369,7 @@ int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long lon
 int smcb_nuts_transition(void* handle, const double* x, const double* r, long long N, double eps, double phi,
                          int max_depth, int accrej, uint64_t seed, uint32_t iteration, uint64_t particle0,
                          double* x_new, double* r_new, double* A_old, double* B_old, double* A_new, double* B_new,
-                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth,
+                         double* ke_old, double* ke_new, int* n_leapfrog, int* accepted, int* depth, double* accept_stat,
                          const double* A_in, const double* B_in, const double* g_in, double* g_new, void* workspace,
                          long long workspace_bytes, void* stream) {
     SMCB_REQUIRE(handle && x && r && x_new && r_new && workspace, "null argument");
@@ -387,6 +387,7 @@ int smcb_nuts_transition(void* handle, const double* x, const double* r, long lo
     a.seed = seed; a.iteration = iteration; a.particle0 = particle0;
     a.x_new = x_new; a.r_new = r_new; a.A_old = A_old; a.B_old = B_old; a.A_new = A_new; a.B_new = B_new;
     a.ke_old = ke_old; a.ke_new = ke_new; a.n_leapfrog = n_leapfrog; a.accepted = accepted; a.depth = depth;
+    a.accept_stat = accept_stat;
     a.A_in = A_in; a.B_in = B_in; a.g_in = g_in; a.g_new = g_new;
     a.ws = (double*)workspace;
     cudaStream_t st = (cudaStream_t)stream;

@@ -62,6 +62,8 @@ struct NutsArgs {
     int* n_leapfrog;      // [N] leapfrog steps = gradient evaluations excluding the initial one (nullable)
     int* accepted;        // [N] MH outcome (1 when accrej == 0)     (nullable)
     int* depth;           // [N] number of doublings                 (nullable)
+    double* accept_stat;  // [N] mean over the leaves of min(1, exp(joint_leaf - joint_0)): the NUTS acceptance statistic
+                          //     that drives dual-averaging step-size adaptation (nullable: not computed)
     // gradient carry-over (optional, accrej == 0 only): when the caller hands back the split log density and the
     // gradient of the current positions (outputs A_new, B_new, g_new of the previous transition at the same phi), the
     // initial evaluation of every transition (nuts.py:66,72) is skipped -- same numbers, one model evaluation less.
@@ -80,7 +82,7 @@ struct alignas(16) D2 {
 
 // Workspace record of one LANE (global memory, 128-byte aligned; nlp = nl rounded up to even so that every vector is
 // 16-byte aligned):
-//   header[8]: A0 B0 ke0 | As Bs kes | 2 unused -- the split log densities and kinetic energies of the start point and of
+//   header[8]: A0 B0 ke0 | As Bs kes | sum of leaf acceptance probabilities, joint_0 (only with accept_stat) -- the split log densities and kinetic energies of the start point and of
 //              the selected sample: written once or twice per transition, read at its end, so they live here and not in
 //              registers that are precious across the model evaluation
 //   other edge: x[nlp] r[nlp] g[nlp] | 2L+3 leaf slots, each x[nlp] r[nlp] A B [g[nlp]]
@@ -450,6 +452,7 @@ struct Lane {
         const double ke0 = 0.5 * gsum(ra_sqnorm());
         ws[0] = A; ws[1] = B; ws[2] = ke0;
         const double H0 = lp - ke0;
+        if (a.accept_stat) { ws[6] = 0.0; ws[7] = H0; }
 #if SMCB_TABLE_MATH
         logu = H0 + fast_log(1.0 - draw(a));      // 1 - u is exact; table-driven log (common.cuh), <= 2.2e-16 absolute
 #else
@@ -496,6 +499,10 @@ struct Lane {
         ++n_leapfrog;
         ++leaf;
         const double joint = lp - 0.5 * rr;
+        if (a.accept_stat) {   // min(1, exp(joint - joint_0)); a NaN or -inf joint counts 0
+            const double dj = joint - ws[7];
+            ws[6] += (dj >= 0.0) ? 1.0 : ((dj == dj) ? fast_exp(dj) : 0.0);
+        }
         if ((logu - 100.) >= joint) { ++depth; return finish(a); }
         uint32_t run_n = (logu < joint) ? 1u : 0u;
         int run_ref = -1;  // -1: the candidate is the leaf in registers
@@ -614,6 +621,7 @@ struct Lane {
             if (a.n_leapfrog) a.n_leapfrog[pid] = (int)n_leapfrog;
             if (a.accepted) a.accepted[pid] = acc;
             if (a.depth) a.depth[pid] = depth;
+            if (a.accept_stat) a.accept_stat[pid] = n_leapfrog ? ws[6] / (double)n_leapfrog : 0.0;
         }
         phase = kIdle;
         return true;

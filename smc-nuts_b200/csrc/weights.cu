@@ -570,20 +570,22 @@ __global__ void __launch_bounds__(kRedThreads) count_moved_kernel(const double* 
     }
 }
 
-// sum of an int32 array -> int64 (the grad-eval counter of the metric)
-__global__ void __launch_bounds__(kRedThreads) sum_int32_kernel(const int* __restrict__ v, long long N, long long* out,
-                                                                 double* ws) {
-    __shared__ long long sh[kRedThreads / 32];
+// sum of an array in a wider accumulator: int32 -> int64 (the grad-eval counter of the metric), double -> double (the
+// acceptance statistic of the step-size adaptation); fixed tile order, so the result does not depend on scheduling
+template <typename T, typename Acc>
+__global__ void __launch_bounds__(kRedThreads) sum_kernel(const T* __restrict__ v, long long N, Acc* out, double* ws) {
+    static_assert(sizeof(Acc) == sizeof(double), "partials share the reduction workspace");
+    __shared__ Acc sh[kRedThreads / 32];
     __shared__ bool is_last;
-    long long acc = 0;
+    Acc acc = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) acc += v[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
     __syncthreads();
-    long long* wsl = (long long*)ws;
+    Acc* wsl = (Acc*)ws;
     if (threadIdx.x == 0) {
-        long long s = 0;
+        Acc s = 0;
         for (int w = 0; w < kRedThreads / 32; ++w) s += sh[w];
         wsl[(size_t)blockIdx.x * kRedMaxVals] = s;
     }
@@ -594,15 +596,15 @@ __global__ void __launch_bounds__(kRedThreads) sum_int32_kernel(const int* __res
     __syncthreads();
     if (is_last) {
         __threadfence();
-        long long s = 0;
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += kRedThreads) s += ((const volatile long long*)wsl)[(size_t)b * kRedMaxVals];
+        Acc s = 0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kRedThreads) s += ((const volatile Acc*)wsl)[(size_t)b * kRedMaxVals];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         __syncthreads();
         if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
         __syncthreads();
         if (threadIdx.x == 0) {
-            long long t = 0;
+            Acc t = 0;
             for (int w = 0; w < kRedThreads / 32; ++w) t += sh[w];
             out[0] = t;
             *counter = 0;
@@ -910,8 +912,16 @@ int smcb_sum_int32(const int* v, long long N, long long* out, void* workspace, v
     SMCB_REQUIRE(v && out && workspace && N >= 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (reset_counter(workspace, st)) return -1;
-    sum_int32_kernel<<<stride_grid(N, kRedThreads * 4, 4), kRedThreads, 0, st>>>(v, N, out, (double*)workspace);
-    return check_launch("sum_int32_kernel");
+    sum_kernel<int, long long><<<stride_grid(N, kRedThreads * 4, 4), kRedThreads, 0, st>>>(v, N, out, (double*)workspace);
+    return check_launch("sum_kernel<int>");
+}
+
+int smcb_sum_f64(const double* v, long long N, double* out, void* workspace, void* stream) {
+    SMCB_REQUIRE(v && out && workspace && N >= 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (reset_counter(workspace, st)) return -1;
+    sum_kernel<double, double><<<stride_grid(N, kRedThreads * 4, 4), kRedThreads, 0, st>>>(v, N, out, (double*)workspace);
+    return check_launch("sum_kernel<double>");
 }
 
 int smcb_fast_log(const double* x, long long N, double* out, void* stream) {

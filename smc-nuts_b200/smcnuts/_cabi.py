@@ -25,7 +25,7 @@ _SIGS = {
     "smcb_logp_grad": [_vp, _vp, _ll, _d, _vp, _vp, _vp, _vp],
     "smcb_combine_logp": [_vp, _vp, _d, _ll, _vp, _vp],
     "smcb_nuts_workspace_bytes": [_vp, _ll, _i, ctypes.POINTER(_ll)],
-    "smcb_nuts_transition": [_vp, _vp, _vp, _ll, _d, _d, _i, _i, _u64, _u32, _u64] + [_vp] * 15 + [_vp, _ll, _vp],
+    "smcb_nuts_transition": [_vp, _vp, _vp, _ll, _d, _d, _i, _i, _u64, _u32, _u64] + [_vp] * 16 + [_vp, _ll, _vp],
     "smcb_normals": [_u64, _u32, _u32, _u64, _ll, _i, _vp, _vp],
     "smcb_uniforms": [_u64, _u32, _u32, _u64, _ll, _u32, _vp, _vp],
     "smcb_row_half_sqnorm": [_vp, _ll, _i, _vp, _vp],
@@ -71,6 +71,7 @@ _SIGS = {
     "smcb_gaussL_factor": [_vp, _ll, _i, _d, _vp, _vp, _vp, _vp],
     "smcb_gaussL_logpdf": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "smcb_sum_int32": [_vp, _ll, _vp, _vp, _vp],
+    "smcb_sum_f64": [_vp, _ll, _vp, _vp, _vp],
     "smcb_fast_exp": [_vp, _ll, _vp, _vp],
     "smcb_fast_log": [_vp, _ll, _vp, _vp],
     "smcb_probe_fp64": [_i, _i, _i, _vp, _vp],

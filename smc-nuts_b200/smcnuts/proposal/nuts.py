@@ -44,6 +44,7 @@ class NUTSProposal:
         self.record_events = False  # bench.py: CUDA events tightly around the kernel launch
         self.events = []
         self._ws_bytes = {}
+        self.want_accept_stat = False   # also emit the per-particle NUTS acceptance statistic (step-size adaptation)
 
     # Host inputs of at least this many particles go through the pipelined path (copy/compute overlap)
     PIPELINE_MIN_PARTICLES = 1 << 16
@@ -139,6 +140,8 @@ class NUTSProposal:
                  depth=dev.empty(N, dtype=torch.int32))
         if want_grad:
             o["g_new"] = dev.empty(N, D)
+        if self.want_accept_stat:
+            o["accept_stat"] = dev.empty(N)
         return o
 
     def _launch(self, x, r, o, lo, hi, phi, it, carry, ws, stream):
@@ -149,7 +152,7 @@ class NUTSProposal:
                    self.max_tree_depth, int(self.accept_reject), self.seed, it, self.particle0 + lo,
                    sl(o["x_new"]), sl(o["r_new"]), sl(o["A_old"]), sl(o["B_old"]), sl(o["A_new"]), sl(o["B_new"]),
                    sl(o["ke_old"]), sl(o["ke_new"]), sl(o["n_leapfrog"]), sl(o["accepted"]), sl(o["depth"]),
-                   sl(cA), sl(cB), sl(cg), sl(o.get("g_new")), dev.ptr(ws), ws.numel(), stream)
+                   sl(o.get("accept_stat")), sl(cA), sl(cB), sl(cg), sl(o.get("g_new")), dev.ptr(ws), ws.numel(), stream)
 
     def transition(self, x, r, phi=1.0, iteration=None, carry=None, want_grad=False):
         """Device entry point: returns dict of device tensors (x_new, r_new, A_old, B_old, A_new, B_new,

@@ -18,13 +18,15 @@ from .estimate.estimate_from_tempered import EstimateFromTempered
 from .parallel import ShardContext
 from .proposal.nuts import NUTSProposal
 from .proposal.nuts_acc_rej import NUTSProposalWithAccRej
+from .proposal.step_size import DualAveragingStepSize
 from .samples.samples import Samples
 
 
 class SMCSampler:
     def __init__(self, K: int, N: int, target, step_size=None, sample_proposal=None, momentum_proposal=None,
                  lkernel="forwardsLKernel", tempering=False, rng=None, forward_kernel=None, verbose=False,
-                 resampling="multinomial", save_history=None, history_budget_bytes=48 << 30, shard=None):
+                 resampling="multinomial", save_history=None, history_budget_bytes=48 << 30, shard=None,
+                 adapt_step_size=0, target_accept=0.8):
         self.K = K  # Number of iterations
         self.N = N  # Number of particles (global)
         self.target = target
@@ -41,6 +43,19 @@ class SMCSampler:
             cls = NUTSProposalWithAccRej if lkernel == "asymptoticLKernel" else NUTSProposal  # smc_sampler.py:45-60
             forward_kernel = cls(target=self.target, momentum_proposal=momentum_proposal, step_size=step_size, rng=rng)
         self.forward_kernel = forward_kernel
+
+        # Step-size adaptation (README.md:66-67 "future updates"; off by default = the reference's constant step size,
+        # nuts.py:31): dual averaging on the NUTS acceptance statistic during the first `adapt_step_size` iterations.
+        self.adapt_iters = (K // 2 if adapt_step_size is True else int(adapt_step_size or 0))
+        self.adapt_iters = max(0, min(self.adapt_iters, K))
+        self.step_size_adapter = None
+        if self.adapt_iters:
+            if not hasattr(forward_kernel, "want_accept_stat"):
+                raise TypeError("adapt_step_size needs the device NUTS proposal (it emits the acceptance statistic)")
+            forward_kernel.want_accept_stat = True
+            self.step_size_adapter = DualAveragingStepSize(forward_kernel.step_size, target_accept)
+        self.step_sizes = np.full(K, float(getattr(forward_kernel, "step_size", np.nan)))   # step size used at iteration k
+        self.accept_stat = np.full(K, np.nan)   # mean NUTS acceptance statistic of iteration k (adaptation iterations only)
         seed = getattr(forward_kernel, "seed", None)
         if seed is None:
             seed = dev.seed_from_rng(rng)
@@ -131,7 +146,21 @@ class SMCSampler:
         self._ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(self.K)]
         self._ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(self.K)]
         self._lf = dev.zeros(self.K, dtype=torch.int64)
+        self._acc_sum = dev.zeros(max(self.adapt_iters, 1))
         self._start_time = time()
+
+    def _adapt_step_size(self, k):
+        """Feed iteration k-1's mean acceptance statistic to the dual averaging and set the step size of iteration k;
+        the averaged step size is frozen from iteration `adapt_iters` on."""
+        if self.adapt_iters and 1 <= k <= self.adapt_iters:
+            self.accept_stat[k - 1] = float(self._acc_sum[k - 1].item()) / self.N
+            eps = self.step_size_adapter.update(self.accept_stat[k - 1])
+            if k == self.adapt_iters:
+                eps = self.step_size_adapter.averaged()
+                self.forward_kernel.want_accept_stat = False
+            self.forward_kernel.step_size = eps
+        if k < self.K:
+            self.step_sizes[k] = self.forward_kernel.step_size
 
     def iterate(self, k):
         """One SMC iteration, in the reference's order of operations (smc_sampler.py:109-140)."""
@@ -141,11 +170,16 @@ class SMCSampler:
         mean_estimate, variance_estimate = self.estimator.return_estimate(s.x, s.wn)
         s.prefetch_momentum()         # queued before the one host synchronisation of the iteration (ESS, below)
         s.calculate_ess()
+        self._adapt_step_size(k)      # after the host synchronisation above: the previous iteration's statistic is ready
         s.resample_if_required()
         self.resampled[k] = s.resampled_last
         self._ev0[k].record()
         s.propose_samples()
         self._ev1[k].record()
+        if k < self.adapt_iters:      # summed acceptance statistic of this iteration's N trees (read at iteration k + 1)
+            _cabi.call("smcb_sum_f64", dev.ptr(self.forward_kernel.last["accept_stat"]), s.n_local,
+                       dev.ptr(self._acc_sum[k:k + 1]), dev.ptr(dev.reduce_ws()), dev.stream_ptr())
+            self.shard.all_reduce_sum_(self._acc_sum[k:k + 1])
         if getattr(s, "n_leapfrog", None) is not None:
             _cabi.call("smcb_sum_int32", dev.ptr(s.n_leapfrog), s.n_local, dev.ptr(self._lf[k:k + 1]),
                        dev.ptr(dev.reduce_ws()), dev.stream_ptr())
