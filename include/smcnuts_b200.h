@@ -46,6 +46,10 @@ long long smcb_launch_count(void);
 
 /* ---- model (replaces StanModel.__init__, bridgestan.py:13-26; phi is an argument, not a reload :122-146) */
 int smcb_model_create(int kind, const double* host_data, long long n, int dim, void** handle);
+/* A model that lives in its own shared object (csrc/nuts_plugin.cuh: a generated model struct compiled with the NUTS / logp
+ * kernel templates).  Replaces the generic half of bridgestan.py:13-26 (any Stan program handed to BridgeStan):
+ * smcnuts/model/stan_codegen.py translates a Stan program into the struct.  host_data[n] is the plug-in's data blob. */
+int smcb_model_create_plugin(const char* so_path, const double* host_data, long long n, void** handle);
 int smcb_model_destroy(void* handle);
 int smcb_model_dim(void* handle);
 /* Host-only test hook (no GPU work): the tensor-core fragment packing of the PRMwCD NUTS kernel (csrc/models.cuh,
@@ -191,6 +195,11 @@ int smcb_peer_close(void* ptr);
 int smcb_peer_free(void* ptr);
 /* out[j, :] = x[idx[j], :]  (samples.py:140) */
 int smcb_gather_rows(const double* x, const int64_t* idx, long long M, int D, double* out, void* stream);
+
+/* out[i][d] = Stan's constraining transform of x[i][d] (bridgestan.py:93-120 calls param_constrain per particle).
+ * table (device, 3*D doubles): per coordinate kind (0 identity, 1 lower: lo + exp u, 2 upper: hi - exp u, 3 both:
+ * lo + (hi - lo) inv_logit u), lo, hi.  Used for generated models; the built-in ones fuse exp-on-last into the moments. */
+int smcb_constrain_rows(const double* x, long long N, int D, const double* table, double* out, void* stream);
 
 /* ---- estimators (estimate.py:79-95 with constrain fused, bridgestan.py:93-120) */
 /* out[d] = sum_i wn_i * (c(x_i)_d - center_d)^power ; center may be NULL (0), power in {1, 2} */

@@ -12,8 +12,17 @@
 
 namespace smcb {
 
+#if defined(SMCB_PLUGIN_TU)
+// a generated model plug-in (nuts_plugin.cuh) is its own shared object: it keeps private copies of the small state below
+inline std::string& last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+inline std::atomic<long long> g_launches{0};
+#else
 std::string& last_error_ref();
 extern std::atomic<long long> g_launches;
+#endif
 
 inline int fail(const char* where, const char* what) {
     last_error_ref() = std::string(where) + ": " + what;
@@ -35,12 +44,39 @@ inline int check_launch(const char* where) {
         if (!(cond)) return ::smcb::fail(__func__, msg); \
     } while (0)
 
+// Entry points of a generated model plug-in (nuts_plugin.cuh), resolved by smcb_model_create_plugin
+struct NutsArgs;
+struct PluginVT {
+    void* dl;
+    int (*abi)(void);
+    int (*dim)(void);
+    int (*ndata)(void);
+    const char* (*last_error)(void);
+    long long (*nuts_workspace_bytes)(const ModelDesc*, long long, int);
+    int (*nuts_transition)(const ModelDesc*, const NutsArgs*, long long, void*);
+    int (*logp_grad)(const ModelDesc*, const double*, long long, double, double*, double*, double*, void*);
+};
+
 struct Model {
     ModelDesc desc;
     double* d_data;
+    PluginVT* vt = nullptr;   // non-null: a generated model living in its own shared object
 };
 
+#if defined(SMCB_PLUGIN_TU)
+inline int device_sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+#else
 int device_sm_count();
+#endif
 
 // grid for a grid-stride elementwise / reduction kernel: a multiple of the SM count
 inline int stride_grid(long long n, int threads, int per_sm) {

@@ -269,6 +269,6 @@ SMCB_HD double ref_log1p(double q) {
 }
 
 // model kinds of the C-ABI (include/smcnuts_b200.h)
-enum ModelKind : int { kArma = 0, kPRMwCD = 1, kGauss = 2 };
+enum ModelKind : int { kArma = 0, kPRMwCD = 1, kGauss = 2, kPlugin = 100 };
 
 }  // namespace smcb

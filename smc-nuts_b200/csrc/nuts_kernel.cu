@@ -5,12 +5,13 @@
 // owns one particle at a time and pulls the next index from a global atomic queue (warp-aggregated)
 // when its tree ends, which absorbs the 1..2047-leapfrog raggedness of NUTS trees
 // (/root/reference/smcnuts/proposal/nuts.py:50-53 loops particles serially instead).
+#include <dlfcn.h>
+
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
-#include "capi.cuh"
-#include "nuts_lane.cuh"
+#include "nuts_launch.cuh"
 
 namespace smcb {
 
@@ -31,19 +32,6 @@ int device_sm_count() {
     return n;
 }
 
-// Tuning knob for experiments (tools/quick_time.py): cap on resident CTAs per SM of the NUTS kernel.
-static int blocks_per_sm_cap() {
-    const char* e = getenv("SMCB_NUTS_BLOCKS_PER_SM");
-    const int v = e ? atoi(e) : 0;
-    return v > 0 ? v : 1 << 20;
-}
-
-// NT threads per CTA, MIN_BLOCKS resident CTAs/SM (register budget).
-// MEASURED (round 1, profiles/README.md): more resident warps do not help arma (94 registers / 5 CTAs: same time,
-// 64 registers / 8 CTAs: 12 % slower), and keeping the low slots of the per-lane tree workspace in shared memory made
-// the kernel 37 % SLOWER -- the carve-out leaves almost no L1, and the L1 already serves the workspace and
-// particle-row traffic.  The per-lane records therefore stay in global memory (L1/L2 resident).
-template <class M> struct LaunchCfg { static constexpr int NT = 256, MIN_BLOCKS = 1; };   // GaussModelG: one CTA/SM, one copy of the B fragments
 template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
 template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2; };
 template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1; };
@@ -51,30 +39,11 @@ template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BL
 template <int T8> struct LaunchCfg<PrmModelG<T8>> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
 constexpr int kPrmTiles = 13;   // PrmModelG instantiation: 81..104 observations (the shipped PRMwCD has 100)
 
-// staged model data, then (M::STAGE) one staging row per thread for the stored edge of the U-turn tests
-// Parity alignment of the refill.  A particle that starts at trip t0 stores a leaf (first leaf of a two-leaf sub-tree)
-// at trips t0+2, t0+4, ... and merges / ends doublings at the trips in between: every doubling after the first has an
-// even number of leaves.  When the particles of a warp start at trips of mixed parity, every trip executes BOTH
-// divergent paths of the lane bookkeeping; when new particles are only admitted at even trips, all particles of a warp
-// store on even trips and merge on odd ones, and a trip executes one path.  The price is one idle trip for half of
-// the refills (1 % of the work at 50 leapfrogs per particle); results do not depend on the lane assignment.
-#ifndef SMCB_ALIGN_PARITY
-#define SMCB_ALIGN_PARITY 0
-#endif
-template <class M> struct AlignCfg { static constexpr bool ON = (SMCB_ALIGN_PARITY != 0) && M::GROUP > 1; };
 #if SMCB_ALIGN_PARITY == 2   // A/B experiments: also for the one-lane-per-particle kernels
 template <> struct AlignCfg<ArmaModel> { static constexpr bool ON = true; };
 template <> struct AlignCfg<PrmModel> { static constexpr bool ON = true; };
 #endif
 
-template <class M>
-static size_t nuts_smem_bytes(const ModelDesc& d) {
-    size_t n = (size_t)M::staged_doubles(d);
-    if (M::STAGE) n += (size_t)LaunchCfg<M>::NT * nuts_stage_stride(M::STATIC_NL);
-    return sizeof(double) * n;
-}
-
-template <class M> struct StageOffset { static int of(const ModelDesc&) { return 0; } };
 template <int NT8> struct StageOffset<GaussModelG<NT8>> { static int of(const ModelDesc& d) { return d.dim * d.dim; } };
 template <int T8> struct StageOffset<PrmModelG<T8>> { static int of(const ModelDesc& d) { return PrmModel::HDR + d.T * PrmModel::ROW; } };
 
@@ -89,143 +58,6 @@ static bool prm_use_group(const ModelDesc& d, long long N) {
     return PrmModelG<kPrmTiles>::fits(d) && !(e && atoi(e) != 0);
 }
 
-// Model data (y[200]; the PRMwCD table or its tensor-core fragments; the Gaussian B-fragments) is staged once per CTA into shared memory,
-// where every lane reads the same address each step (broadcast / conflict-free).  The plain Gaussian precision
-// matrix of the one-lane-per-particle fallback stays in L1/L2.
-template <class M>
-__device__ __forceinline__ const double* stage_model(const ModelDesc& d, double* smem, int staged, int offset) {
-    if constexpr (M::STATIC_NL != 0) {
-        for (int i = threadIdx.x; i < staged; i += blockDim.x) smem[i] = d.data[offset + i];
-        __syncthreads();
-        return smem;
-    } else {
-        return d.data;
-    }
-}
-
-template <class M>
-__global__ void __launch_bounds__(LaunchCfg<M>::NT, LaunchCfg<M>::MIN_BLOCKS)
-nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles) {
-    extern __shared__ double smem[];
-    constexpr int G = M::GROUP;
-    M model(a.model, stage_model<M>(a.model, smem, staged, stage_offset));
-    const unsigned lane_id = threadIdx.x & 31u;
-    Lane<M> lane;
-    lane.idle_init(model, (int)(lane_id % G));
-    lane.stg = M::STAGE ? smem + staged + (size_t)threadIdx.x * nuts_stage_stride(M::STATIC_NL) : nullptr;
-    double* ws = a.ws + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * rec_doubles;
-    constexpr unsigned kLeaders = G == 1 ? 0xffffffffu : 0x11111111u;   // first lane of every particle group
-    const unsigned group_first = lane_id & ~(unsigned)(G - 1);
-    bool drained = false;
-    // with gradient carry-over the tree starts in the trip a particle is admitted, one trip earlier than otherwise
-    const unsigned admit_parity = a.g_in ? 1u : 0u;
-    for (unsigned trip = 0;; ++trip) {
-        // ---- refill finished particle groups from the work queue (warp-aggregated atomic)
-        const bool admit = !AlignCfg<M>::ON || ((trip & 1u) == admit_parity);
-        const bool want = (lane.phase == kIdle) && !drained && admit;
-        const unsigned m = __ballot_sync(0xffffffffu, want) & kLeaders;
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if ((int)lane_id == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (want) {
-                const long long p = (long long)base + __popc(m & ((1u << group_first) - 1u));
-                if (p < a.N) lane.begin(a, model, p, ws);
-                else drained = true;
-            }
-        }
-        if (__all_sync(0xffffffffu, lane.phase == kIdle)) {
-            if (!AlignCfg<M>::ON || __all_sync(0xffffffffu, drained)) break;
-            continue;   // nobody active at a non-admitting trip: the queue is asked again at the next one
-        }
-        // ---- one model evaluation per particle per trip: the initial point or one leapfrog.  The evaluation is
-        //      executed by every lane (idle ones carry zeros) so that warp-wide tensor-core instructions stay legal.
-        if (lane.phase != kIdle) lane.pre_eval(a);
-        double A, B, g[M::NLOC];
-        if constexpr (G > 1) __syncwarp();   // the group models issue warp-wide mma.sync.aligned: reconverge explicitly
-        model.eval(lane.xa, a.phi, A, B, g);
-        lane.take_grad(g);
-        if (lane.phase != kIdle) lane.post_eval(a, A, B);
-    }
-}
-
-// Batched value + gradient (one thread per particle).
-template <class M>
-__global__ void __launch_bounds__(128) logp_grad_kernel(ModelDesc md, const double* __restrict__ x, long long N,
-                                                        double phi, double* __restrict__ Aout,
-                                                        double* __restrict__ Bout, double* __restrict__ grad,
-                                                        int staged) {
-    extern __shared__ double smem[];
-    M model(md, stage_model<M>(md, smem, staged, 0));
-    const int D = M::STATIC_D ? M::STATIC_D : model.dim();
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-        double xv[M::DMAX], g[M::DMAX], A, B;
-#pragma unroll
-        for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : D); ++d) xv[d] = x[i * D + d];
-        model.eval(xv, phi, A, B, g);
-        if (Aout) Aout[i] = A;
-        if (Bout) Bout[i] = B;
-        if (grad) {
-            const bool bad = !is_finite(A + phi * B);
-#pragma unroll
-            for (int d = 0; d < (M::STATIC_D ? M::STATIC_D : D); ++d) grad[i * D + d] = bad ? neg_inf() : g[d];
-        }
-    }
-}
-
-__global__ void combine_logp_kernel(const double* __restrict__ A, const double* __restrict__ B, double phi,
-                                    long long N, double* __restrict__ out) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-        const double lp = A[i] + phi * B[i];
-        out[i] = is_finite(lp) ? lp : neg_inf();
-    }
-}
-
-template <class M>
-static long long nuts_blocks(const Model* mdl, long long N, size_t smem, int* occ_out) {
-    const int NT = LaunchCfg<M>::NT;
-    auto kern = nuts_transition_kernel<M>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) return -1;
-    if (occ > blocks_per_sm_cap()) occ = blocks_per_sm_cap();
-    long long blocks = (long long)device_sm_count() * occ;
-    const long long need = (N * M::GROUP + NT - 1) / NT;
-    if (blocks > need) blocks = need;
-    if (blocks < 1) blocks = 1;
-    if (occ_out) *occ_out = occ;
-    (void)mdl;
-    return blocks;
-}
-
-template <class M>
-static long long nuts_ws_bytes(const Model* mdl, long long N, int max_depth) {
-    const size_t smem = nuts_smem_bytes<M>(mdl->desc);
-    const long long blocks = nuts_blocks<M>(mdl, N, smem, nullptr);
-    if (blocks < 0) return -1;
-    M probe(mdl->desc, nullptr);
-    return (long long)sizeof(double) * nuts_ws_doubles(probe.nloc(), max_depth) * blocks * LaunchCfg<M>::NT + 256;
-}
-
-template <class M>
-static int launch_nuts(const Model* mdl, NutsArgs a, long long ws_bytes, cudaStream_t st) {
-    const int NT = LaunchCfg<M>::NT;
-    const int staged = M::staged_doubles(mdl->desc);
-    const size_t smem = nuts_smem_bytes<M>(mdl->desc);
-    const long long blocks = nuts_blocks<M>(mdl, a.N, smem, nullptr);
-    if (blocks < 0) return fail("smcb_nuts_transition", "kernel does not fit on an SM");
-    M probe(mdl->desc, nullptr);
-    const int rec = nuts_ws_doubles(probe.nloc(), a.max_depth, a.g_new != nullptr);
-    const long long ws_need = (long long)sizeof(double) * rec * blocks * NT + 256;
-    if (ws_bytes < ws_need) return fail("smcb_nuts_transition", "workspace too small (see smcb_nuts_workspace_bytes)");
-    // queue head lives in the last 256 bytes of the workspace
-    a.queue = (unsigned long long*)((char*)a.ws + (ws_need - 256));
-    SMCB_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), st));
-    nuts_transition_kernel<M><<<(int)blocks, NT, smem, st>>>(a, staged, StageOffset<M>::of(mdl->desc), rec);
-    return check_launch("nuts_transition_kernel");
-}
-
 // Gaussian: tensor-core group kernel for D <= 104, one-lane-per-particle fallback above (SMCB_GAUSS_SCALAR=1 forces the
 // fallback: parity test of the two)
 static bool gauss_force_scalar() {
@@ -234,16 +66,6 @@ static bool gauss_force_scalar() {
 }
 #define SMCB_GAUSS_DISPATCH(D, CALL_G, CALL_PLAIN) \
     (gauss_force_scalar() ? CALL_PLAIN : (D) <= 8 ? CALL_G(1) : (D) <= 16 ? CALL_G(2) : (D) <= 32 ? CALL_G(4) : (D) <= 64 ? CALL_G(8) : (D) <= 104 ? CALL_G(13) : CALL_PLAIN)
-
-template <class M>
-static int launch_logp(const Model* mdl, const double* x, long long N, double phi, double* A, double* B, double* g,
-                       cudaStream_t st) {
-    const int staged = M::staged_doubles(mdl->desc);
-    const size_t smem = sizeof(double) * (size_t)staged;
-    const int grid = stride_grid(N, 128, 8);
-    logp_grad_kernel<M><<<grid, 128, smem, st>>>(mdl->desc, x, N, phi, A, B, g, staged);
-    return check_launch("logp_grad_kernel");
-}
 
 }  // namespace smcb
 
@@ -307,9 +129,52 @@ int smcb_model_create(int kind, const double* host_data, long long n, int dim, v
     return 0;
 }
 
+int smcb_model_create_plugin(const char* so_path, const double* host_data, long long n, void** handle) {
+    SMCB_REQUIRE(so_path && handle && n >= 0 && (host_data || n == 0), "null argument");
+    void* dl = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+    if (!dl) return fail("smcb_model_create_plugin", dlerror());
+    PluginVT* vt = new PluginVT{};
+    vt->dl = dl;
+    bool ok = true;
+    auto sym = [&](const char* name) { void* p = dlsym(dl, name); ok = ok && p; return p; };
+    vt->abi = (int (*)(void))sym("smcb_plugin_abi");
+    vt->dim = (int (*)(void))sym("smcb_plugin_dim");
+    vt->ndata = (int (*)(void))sym("smcb_plugin_ndata");
+    vt->last_error = (const char* (*)(void))sym("smcb_plugin_last_error");
+    vt->nuts_workspace_bytes = (long long (*)(const ModelDesc*, long long, int))sym("smcb_plugin_nuts_workspace_bytes");
+    vt->nuts_transition = (int (*)(const ModelDesc*, const NutsArgs*, long long, void*))sym("smcb_plugin_nuts_transition");
+    vt->logp_grad = (int (*)(const ModelDesc*, const double*, long long, double, double*, double*, double*, void*))sym("smcb_plugin_logp_grad");
+    auto bail = [&](const char* what) { dlclose(dl); delete vt; return fail("smcb_model_create_plugin", what); };
+    if (!ok) return bail("not a model plug-in: an smcb_plugin_* entry point is missing (csrc/nuts_plugin.cuh)");
+    if (vt->abi() != 1) return bail("plug-in ABI version mismatch: rebuild it against this library's csrc/");
+    if (vt->ndata() != n) return bail("data blob length differs from the one the plug-in was generated for");
+    ModelDesc d{};
+    d.kind = kPlugin;
+    d.dim = vt->dim();
+    d.n_data = (int)n;
+    Model* m = new Model{d, nullptr};
+    m->vt = vt;
+    if (cudaMalloc(&m->d_data, sizeof(double) * (size_t)(n > 0 ? n : 1)) != cudaSuccess) {
+        delete m;
+        return bail("cudaMalloc failed (is a CUDA device present?)");
+    }
+    if (n > 0 && cudaMemcpy(m->d_data, host_data, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(m->d_data);
+        delete m;
+        return bail("cudaMemcpy of the data blob failed");
+    }
+    m->desc.data = m->d_data;
+    *handle = m;
+    return 0;
+}
+
 int smcb_model_destroy(void* handle) {
     if (!handle) return 0;
     Model* m = (Model*)handle;
+    if (m->vt) {
+        dlclose(m->vt->dl);
+        delete m->vt;
+    }
     cudaFree(m->d_data);
     delete m;
     return 0;
@@ -330,6 +195,11 @@ int smcb_logp_grad(void* handle, const double* x, long long N, double phi, doubl
     if (N == 0) return 0;
     const Model* m = (const Model*)handle;
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->vt) {
+        if (m->vt->logp_grad(&m->desc, x, N, phi, A, B, grad, stream)) return fail("smcb_logp_grad (plug-in)", m->vt->last_error());
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     switch (m->desc.kind) {
         case kArma: return launch_logp<ArmaModel>(m, x, N, phi, A, B, grad, st);
         case kPRMwCD: return launch_logp<PrmModel>(m, x, N, phi, A, B, grad, st);
@@ -349,6 +219,12 @@ int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long lon
     SMCB_REQUIRE(max_depth >= 1 && max_depth <= 10, "max_depth must be in [1, 10] (reference: MAX_TREE_DEPTH = 10)");
     const Model* m = (const Model*)handle;
     long long b;
+    if (m->vt) {
+        b = m->vt->nuts_workspace_bytes(&m->desc, N, max_depth);
+        if (b < 0) return fail("smcb_nuts_workspace_bytes (plug-in)", "occupancy query failed");
+        *bytes = b;
+        return 0;
+    }
     switch (m->desc.kind) {
         case kArma: b = nuts_ws_bytes<ArmaModel>(m, N, max_depth); break;
         case kPRMwCD:
@@ -391,6 +267,11 @@ int smcb_nuts_transition(void* handle, const double* x, const double* r, long lo
     a.A_in = A_in; a.B_in = B_in; a.g_in = g_in; a.g_new = g_new;
     a.ws = (double*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->vt) {
+        if (m->vt->nuts_transition(&m->desc, &a, workspace_bytes, stream)) return fail("smcb_nuts_transition (plug-in)", m->vt->last_error());
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     switch (m->desc.kind) {
         case kArma: return launch_nuts<ArmaModel>(m, a, workspace_bytes, st);
         case kPRMwCD:

@@ -73,6 +73,7 @@ struct NutsArgs {
     double* g_new;        // [N, D]   gradient at the returned x_new (nullable)
     double* ws;           // workspace: lanes * ws_doubles(D, max_depth)
     unsigned long long* queue;  // work-queue head, zeroed before launch
+    void* exchange;             // tail compaction: one Lane<M> per thread of the grid (nuts_launch.cuh)
 };
 
 // 16-byte pair, the unit of every access to the per-lane workspace record (LDG.128 / STG.128)

@@ -612,6 +612,22 @@ __global__ void __launch_bounds__(kRedThreads) sum_kernel(const T* __restrict__ 
     }
 }
 
+// Stan's constraining transforms, coordinate by coordinate (generated models: smcnuts/model/stan_codegen.py).
+// table[3 * D]: kind (0 identity, 1 lower, 2 upper, 3 lower and upper), lo, hi per coordinate.
+__global__ void constrain_rows_kernel(const double* __restrict__ x, long long n_elem, int D, const double* __restrict__ table,
+                                      double* __restrict__ out) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_elem; e += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(e % D);
+        const int kind = (int)table[3 * col];
+        const double lo = table[3 * col + 1], hi = table[3 * col + 2], u = x[e];
+        double v = u;
+        if (kind == 1) v = lo + exp(u);
+        else if (kind == 2) v = hi - exp(u);
+        else if (kind == 3) v = lo + (hi - lo) * (u >= 0.0 ? 1.0 / (1.0 + exp(-u)) : exp(u) / (1.0 + exp(u)));
+        out[e] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ FP64 probe
 __global__ void probe_fp64_kernel(int iters, double* sink) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -897,6 +913,13 @@ int smcb_weighted_moment(const double* x, const double* wn, long long N, int D, 
     weighted_moment_kernel<<<stride_grid(N * D, kRedThreads * 4, 4), kRedThreads, 0, st>>>(x, wn, N, D, constrain, center,
                                                                                         power, out, (double*)workspace, used);
     return check_launch("weighted_moment_kernel");
+}
+
+int smcb_constrain_rows(const double* x, long long N, int D, const double* table, double* out, void* stream) {
+    SMCB_REQUIRE(x && table && out && N >= 0 && D >= 1, "bad argument");
+    if (N == 0) return 0;
+    constrain_rows_kernel<<<stride_grid(N * D, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, N * D, D, table, out);
+    return check_launch("constrain_rows_kernel");
 }
 
 int smcb_count_moved(const double* x, const double* x_new, long long N, int D, double* out_count, void* workspace,

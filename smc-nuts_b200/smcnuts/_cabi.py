@@ -12,6 +12,7 @@ HEADER = _PKG.parents[1] / "include" / "smcnuts_b200.h"
 MODEL_KINDS = {"arma": 0, "PRMwCD": 1, "gauss": 2}
 STREAM_NUTS, STREAM_MOMENTUM, STREAM_ACCREJ, STREAM_RESAMPLE, STREAM_INIT, STREAM_ESTIMATE = range(6)
 CONSTRAIN_NONE, CONSTRAIN_EXP_LAST = 0, 1
+CONSTRAIN_TABLE = 2   # host side only: constrain with smcb_constrain_rows first, then unconstrained moments
 
 _vp, _ll, _i, _d = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_double
 _u64, _u32 = ctypes.c_uint64, ctypes.c_uint32
@@ -19,6 +20,7 @@ _u64, _u32 = ctypes.c_uint64, ctypes.c_uint32
 # name -> argtypes (restype is int unless listed in _RESTYPES); pointers are passed as integers (void*)
 _SIGS = {
     "smcb_model_create": [_i, _vp, _ll, _i, ctypes.POINTER(_vp)],
+    "smcb_model_create_plugin": [ctypes.c_char_p, _vp, _ll, ctypes.POINTER(_vp)],
     "smcb_model_destroy": [_vp],
     "smcb_model_dim": [_vp],
     "smcb_debug_pack_prm": [_vp, _i, _i, _vp, _ll],
@@ -72,6 +74,7 @@ _SIGS = {
     "smcb_gaussL_logpdf": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "smcb_sum_int32": [_vp, _ll, _vp, _vp, _vp],
     "smcb_sum_f64": [_vp, _ll, _vp, _vp, _vp],
+    "smcb_constrain_rows": [_vp, _ll, _i, _vp, _vp, _vp],
     "smcb_fast_exp": [_vp, _ll, _vp, _vp],
     "smcb_fast_log": [_vp, _ll, _vp, _vp],
     "smcb_probe_fp64": [_i, _i, _i, _vp, _vp],

@@ -26,6 +26,8 @@ class Estimate:
     def _estimate(self, x, wn, constrain=_cabi.CONSTRAIN_NONE):
         xd, wd = dev.to_device(x), dev.to_device(wn)
         N, D = xd.shape
+        if constrain == _cabi.CONSTRAIN_TABLE:     # generated models: Stan's transforms coordinate by coordinate
+            xd, constrain = self.target.constrain(xd), _cabi.CONSTRAIN_NONE
         mean, var = dev.empty(D), dev.empty(D)
         ws, st = dev.reduce_ws(), dev.stream_ptr()
         _cabi.call("smcb_weighted_moment", dev.ptr(xd), dev.ptr(wd), N, D, constrain, 0, 1, dev.ptr(mean),

@@ -1,7 +1,8 @@
 """`StanModel(model_name, model_path, data_path)` with the reference's constructor
-(smcnuts/model/bridgestan.py:13 in the reference), resolved to the fused CUDA device function of the
-same name.  BridgeStan itself is not used: the device path has no CPU fallback, and only the shipped
-Stan programs (arma, PRMwCD) have device functions."""
+(smcnuts/model/bridgestan.py:13 in the reference).  The two shipped programs (arma, PRMwCD) resolve to their
+hand-tuned fused CUDA device functions; any other Stan program of the supported subset is translated and compiled
+into a device model by smcnuts/model/generated.py (`use_builtin=False` forces that path for the shipped ones too).
+BridgeStan itself is not used: the device path has no CPU fallback."""
 import json
 from pathlib import Path
 
@@ -9,7 +10,7 @@ from .device_model import DeviceModel, arma_model, prmwcd_model
 
 
 class StanModel(DeviceModel):
-    def __init__(self, model_name, model_path=None, data_path=None):
+    def __init__(self, model_name, model_path=None, data_path=None, use_builtin=True):
         self.model_name, self.model_path, self.data_path = model_name, model_path, data_path
         data = None
         if data_path and str(data_path) != "None" and Path(data_path).exists():
@@ -18,15 +19,25 @@ class StanModel(DeviceModel):
                 data = json.loads(raw)
             except json.JSONDecodeError:
                 data = json.loads(raw + " 1.0}")  # the shipped PRMwCD.json is truncated after `"phi": `
-        if model_name == "arma":
+        if model_name == "arma" and use_builtin:
             m = arma_model(None if data is None else data["y"])
-        elif model_name == "PRMwCD":
+        elif model_name == "PRMwCD" and use_builtin:
             m = prmwcd_model(data)
         else:
-            raise NotImplementedError(f"no device function for Stan model {model_name!r}; available: arma, PRMwCD")
+            if not model_path or not Path(model_path).exists():
+                raise FileNotFoundError(f"Stan program {model_path!r} of model {model_name!r} not found")
+            from .generated import GeneratedModel
+            m = GeneratedModel(Path(model_path).read_text(), data or {}, model_name)
+        self._generated = not isinstance(m, DeviceModel) or type(m) is not DeviceModel
         self.__dict__.update(m.__dict__)
         m._h = None  # ownership of the handle moved to self
         self.last_phi = 1.0
+
+    def constrain(self, x, include_tparams=True, include_gqs=True):
+        if self._generated:
+            from .generated import GeneratedModel
+            return GeneratedModel.constrain(self, x, include_tparams, include_gqs)
+        return DeviceModel.constrain(self, x, include_tparams, include_gqs)
 
     def _update_phi(self, phi):
         """Kept for API compatibility (bridgestan.py:122-146): phi is a kernel argument here, nothing to reload."""

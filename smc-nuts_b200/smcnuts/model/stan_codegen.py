@@ -1,0 +1,1046 @@
+"""Stan-subset front end: a Stan program + its data -> a fused value-and-gradient device function.
+
+The reference hands ANY Stan program to BridgeStan (smcnuts/model/bridgestan.py:13-26: `StanModel(model_name,
+model_path, data_path)` compiles it with stanc + Stan Math and evaluates log_density / log_density_gradient through
+ctypes, one call per particle).  Here the program is translated into the C++ body of a model struct with the interface
+of csrc/models.cuh (`eval(x, phi, A, B, g)`), which csrc/nuts_plugin.cuh instantiates into the same persistent NUTS
+kernel and batched logp/grad kernel as the built-in models.  The same generated text also
+compiles with plain g++ -- that is how the `not gpu` tests check it against the oracle densities.
+
+What is generated
+  * parameters on the unconstrained scale, Stan's transforms and log-Jacobians (lower -> lo + exp(u), upper,
+    lower+upper -> scaled inverse logit), declaration order = BridgeStan's unconstrained order;
+  * the split  logp(x, phi) = A(x) + phi * B(x): the data variable named `phi` is the tempering parameter
+    (bridgestan.py:122-146 rewrites it in the data JSON); `target += phi * e` accumulates into B, everything else into A;
+    all normalising constants of `target +=` statements are kept, `~` statements drop parameter-free terms (Stan's
+    propto semantics under BridgeStan's defaults);
+  * the gradient by statement-level forward-mode differentiation: every assignment's right-hand side is differentiated
+    in reverse over its (small) expression DAG, and the adjoints of its leaves are pushed onto the sensitivities of the
+    assigned variable -- only over the coordinates that variable can depend on;  loop-carried recurrences (arma's
+    err[t-1]) therefore work, and loops stay loops (bounds are literals: scalar data is folded at generation time).
+
+Supported subset (anything else raises StanSubsetError with the offending line):
+  blocks data / parameters / model;  int, real, vector, row_vector, array[..] (and the pre-2.33 `real y[N]` form);
+  lower/upper bounds on real parameters;  local declarations, =, +=, -=, *=, /=, `target +=`, `~`, for loops, blocks;
+  + - * / ^, unary minus, indexing, exp log log1p sqrt fabs abs square inv inv_logit log1p_exp log_sum_exp(a, b) pow
+  tanh sin cos lgamma(data only) dot_product-free scalar code;  normal, cauchy, student_t, double_exponential,
+  lognormal, exponential, gamma, inv_gamma, beta, uniform densities; poisson, poisson_log, bernoulli, bernoulli_logit,
+  binomial_logit mass functions -- scalar or vectorised over array arguments.
+"""
+import json
+import math
+import re
+from pathlib import Path
+
+
+class StanSubsetError(NotImplementedError):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------ tokenizer
+_TOKEN = re.compile(r"""
+    (?P<ws>\s+|//[^\n]*|\#[^\n]*|/\*.*?\*/)
+  | (?P<num>(\d+\.\d*|\.\d+|\d+)([eE][+-]?\d+)?)
+  | (?P<id>[A-Za-z_][A-Za-z_0-9]*)
+  | (?P<op>\+=|-=|\*=|/=|<=|>=|==|!=|&&|\|\||[-+*/^()\[\]{},;:|<>=~'!])
+""", re.X | re.S)
+
+
+def _tokenize(text):
+    toks, pos, line = [], 0, 1
+    while pos < len(text):
+        m = _TOKEN.match(text, pos)
+        if not m:
+            raise StanSubsetError(f"line {line}: cannot tokenize {text[pos:pos + 20]!r}")
+        kind = m.lastgroup
+        if kind != "ws":
+            toks.append((kind, m.group(), line))
+        line += m.group().count("\n")
+        pos = m.end()
+    toks.append(("eof", "", line))
+    return toks
+
+
+# ------------------------------------------------------------------------------------------------ parser (AST = tuples)
+class _Parser:
+    def __init__(self, text):
+        self.t = _tokenize(text)
+        self.i = 0
+
+    def peek(self, k=0):
+        return self.t[self.i + k]
+
+    def next(self):
+        tok = self.t[self.i]
+        self.i += 1
+        return tok
+
+    def accept(self, val):
+        if self.peek()[1] == val:
+            return self.next()
+        return None
+
+    def expect(self, val):
+        tok = self.next()
+        if tok[1] != val:
+            raise StanSubsetError(f"line {tok[2]}: expected {val!r}, found {tok[1]!r}")
+        return tok
+
+    def err(self, msg):
+        raise StanSubsetError(f"line {self.peek()[2]}: {msg}")
+
+    # ---- program
+    def program(self):
+        blocks = {}
+        while self.peek()[0] != "eof":
+            name = self.next()[1]
+            if name in ("transformed", "generated"):
+                name += " " + self.next()[1]
+            self.expect("{")
+            if name in ("data", "parameters"):
+                blocks[name] = self.decls()
+            elif name == "model":
+                blocks[name] = self.stmts()
+            else:
+                depth, empty = 1, True     # other blocks are accepted only when empty
+                while depth:
+                    tok = self.next()
+                    depth += (tok[1] == "{") - (tok[1] == "}")
+                    empty = empty and tok[1] == "}"
+                    if tok[0] == "eof":
+                        self.err("unterminated block")
+                if not empty:
+                    raise StanSubsetError(f"block {name!r} is outside the supported subset (data / parameters / model)")
+                continue
+            self.expect("}")
+        for need in ("parameters", "model"):
+            if need not in blocks:
+                raise StanSubsetError(f"missing block {need!r}")
+        blocks.setdefault("data", [])
+        return blocks
+
+    # ---- declarations: (name, base, shape[list of expr], lower, upper, init)
+    _TYPES = ("int", "real", "vector", "row_vector", "array", "matrix")
+
+    def is_decl(self):
+        return self.peek()[1] in self._TYPES
+
+    def bounds(self):
+        lo = hi = None
+        if self.accept("<"):
+            while True:
+                key = self.next()[1]
+                self.expect("=")
+                val = self.expr(no_gt=True)
+                if key == "lower":
+                    lo = val
+                elif key == "upper":
+                    hi = val
+                else:
+                    self.err(f"unsupported constraint {key!r}")
+                if not self.accept(","):
+                    break
+            self.expect(">")
+        return lo, hi
+
+    def dims(self):
+        out = []
+        if self.accept("["):
+            out.append(self.expr())
+            while self.accept(","):
+                out.append(self.expr())
+            self.expect("]")
+        return out
+
+    def decl(self):
+        line = self.peek()[2]
+        shape = []
+        base = self.next()[1]
+        if base == "array":
+            shape += self.dims()
+            base = self.next()[1]
+        if base == "matrix":
+            raise StanSubsetError(f"line {line}: matrix types are outside the supported subset (use flat arrays)")
+        lo, hi = self.bounds()
+        if base in ("vector", "row_vector"):
+            shape += self.dims()
+            base = "real"
+        name = self.next()
+        if name[0] != "id":
+            raise StanSubsetError(f"line {line}: expected a variable name, found {name[1]!r}")
+        shape += self.dims()          # pre-2.33 array syntax: real y[N]
+        init = self.expr() if self.accept("=") else None
+        self.expect(";")
+        return (name[1], base, shape, lo, hi, init, line)
+
+    def decls(self):
+        out = []
+        while self.peek()[1] != "}":
+            out.append(self.decl())
+        return out
+
+    # ---- statements
+    def stmts(self):
+        out = []
+        while self.peek()[1] != "}":
+            out.append(self.stmt())
+        return out
+
+    def stmt(self):
+        line = self.peek()[2]
+        if self.is_decl():
+            return ("decl", self.decl(), line)
+        if self.accept("{"):
+            body = self.stmts()
+            self.expect("}")
+            return ("block", body, line)
+        if self.accept("for"):
+            self.expect("(")
+            var = self.next()[1]
+            self.expect("in")
+            lo = self.expr(no_colon=True)
+            self.expect(":")
+            hi = self.expr()
+            self.expect(")")
+            return ("for", var, lo, hi, [self.stmt()], line)
+        if self.peek()[1] in ("if", "while", "print", "reject", "return"):
+            raise StanSubsetError(f"line {line}: statement {self.peek()[1]!r} is outside the supported subset")
+        if self.peek()[1] == "target" and self.peek(1)[1] == "+=":
+            self.next(); self.next()
+            e = self.expr()
+            self.expect(";")
+            return ("target", e, line)
+        lhs = self.expr()
+        if self.accept("~"):
+            dist = self.next()[1]
+            self.expect("(")
+            args = [] if self.peek()[1] == ")" else [self.expr()]
+            while self.accept(","):
+                args.append(self.expr())
+            self.expect(")")
+            if self.peek()[1] == "T":
+                raise StanSubsetError(f"line {line}: truncation T[,] is outside the supported subset")
+            self.expect(";")
+            return ("tilde", lhs, dist, args, line)
+        op = self.next()[1]
+        if op not in ("=", "+=", "-=", "*=", "/="):
+            raise StanSubsetError(f"line {line}: expected an assignment, found {op!r}")
+        rhs = self.expr()
+        self.expect(";")
+        return ("assign", lhs, op, rhs, line)
+
+    # ---- expressions
+    def expr(self, no_gt=False, no_colon=False):
+        return self.additive(no_gt)
+
+    def additive(self, no_gt):
+        a = self.multiplicative(no_gt)
+        while self.peek()[1] in ("+", "-"):
+            op = self.next()[1]
+            a = ("bin", op, a, self.multiplicative(no_gt))
+        return a
+
+    def multiplicative(self, no_gt):
+        a = self.unary(no_gt)
+        while self.peek()[1] in ("*", "/"):
+            op = self.next()[1]
+            a = ("bin", op, a, self.unary(no_gt))
+        return a
+
+    def unary(self, no_gt):
+        if self.accept("-"):
+            return ("neg", self.unary(no_gt))
+        if self.accept("+"):
+            return self.unary(no_gt)
+        return self.power(no_gt)
+
+    def power(self, no_gt):
+        a = self.postfix()
+        if self.accept("^"):
+            return ("bin", "^", a, self.unary(no_gt))     # right associative, binds tighter than unary minus on its left
+        return a
+
+    def postfix(self):
+        a = self.primary()
+        while True:
+            if self.peek()[1] == "[":
+                a = ("idx", a, self.dims())
+            elif self.peek()[1] == "'":
+                self.err("transposition is outside the supported subset")
+            else:
+                return a
+
+    def primary(self):
+        tok = self.next()
+        if tok[0] == "num":
+            return ("num", float(tok[1]), "." not in tok[1] and "e" not in tok[1].lower())
+        if tok[1] == "(":
+            e = self.expr()
+            self.expect(")")
+            return e
+        if tok[0] == "id":
+            if self.peek()[1] == "(":
+                self.next()
+                args = []
+                if self.peek()[1] != ")":
+                    args.append(self.expr())
+                    while self.accept(",") or self.accept("|"):
+                        args.append(self.expr())
+                self.expect(")")
+                return ("call", tok[1], args, tok[2])
+            return ("var", tok[1], tok[2])
+        raise StanSubsetError(f"line {tok[2]}: unexpected {tok[1]!r}")
+
+
+# ------------------------------------------------------------------------------------------------ expression DAG
+class Node:
+    """Real-valued expression node.  kind: const | param | local | data | ivar | un | bin.
+    deps = frozenset of unconstrained coordinates the value can depend on."""
+    __slots__ = ("kind", "op", "args", "val", "deps", "name", "idx")
+
+    def __init__(self, kind, op=None, args=(), val=None, deps=frozenset(), name=None, idx=None):
+        self.kind, self.op, self.args, self.val, self.deps, self.name, self.idx = kind, op, args, val, deps, name, idx
+
+
+def _const(v):
+    return Node("const", val=float(v))
+
+
+def _is_const(n, v=None):
+    return n.kind == "const" and (v is None or n.val == v)
+
+
+def _un(op, a):
+    if a.kind == "const":
+        f = {"neg": lambda z: -z, "exp": math.exp, "log": lambda z: math.log(z) if z > 0 else (-math.inf if z == 0 else math.nan),
+             "log1p": math.log1p, "sqrt": math.sqrt, "fabs": abs, "lgamma": math.lgamma, "tanh": math.tanh,
+             "sin": math.sin, "cos": math.cos, "inv_logit": lambda z: 1.0 / (1.0 + math.exp(-z)),
+             "log1p_exp": lambda z: max(z, 0.0) + math.log1p(math.exp(-abs(z)))}[op]
+        return _const(f(a.val))
+    return Node("un", op=op, args=(a,), deps=a.deps)
+
+
+def _fold(op, x, y):
+    try:
+        if op == "+":
+            return x + y
+        if op == "-":
+            return x - y
+        if op == "*":
+            return x * y
+        if op == "/":
+            return x / y if y != 0 else (math.nan if x == 0 else math.copysign(math.inf, x))
+        r = x ** y
+        return r if isinstance(r, float) else math.nan
+    except (OverflowError, ZeroDivisionError, ValueError):
+        return math.nan
+
+
+def _bin(op, a, b):
+    if a.kind == "const" and b.kind == "const":
+        return _const(_fold(op, a.val, b.val))
+    if op == "+" and _is_const(a, 0.0):
+        return b
+    if op in "+-" and _is_const(b, 0.0):
+        return a
+    if op == "*" and (_is_const(a, 1.0)):
+        return b
+    if op in "*/" and _is_const(b, 1.0):
+        return a
+    if op == "^" and _is_const(b, 2.0):
+        return Node("bin", op="*", args=(a, a), deps=a.deps)
+    if op == "^" and _is_const(b, 1.0):
+        return a
+    return Node("bin", op=op, args=(a, b), deps=a.deps | b.deps)
+
+
+def _add(*terms):
+    out = terms[0]
+    for t in terms[1:]:
+        out = _bin("+", out, t)
+    return out
+
+
+def _sub(a, b):
+    return _bin("-", a, b)
+
+
+def _mul(a, b):
+    return _bin("*", a, b)
+
+
+def _div(a, b):
+    return _bin("/", a, b)
+
+
+def _log(a):
+    return _un("log", a)
+
+
+_LOG_2PI, _LOG_PI = math.log(2.0 * math.pi), math.log(math.pi)
+
+# log densities as sums of terms (each a Node): Stan's definitions with every normalising constant
+_DENSITIES = {
+    "normal": lambda y, m, s: [_const(-0.5 * _LOG_2PI), _un("neg", _log(s)), _mul(_const(-0.5), _bin("^", _div(_sub(y, m), s), _const(2.0)))],
+    "cauchy": lambda y, m, s: [_const(-_LOG_PI), _un("neg", _log(s)), _un("neg", _un("log1p", _bin("^", _div(_sub(y, m), s), _const(2.0))))],
+    "double_exponential": lambda y, m, s: [_const(-math.log(2.0)), _un("neg", _log(s)), _un("neg", _div(_un("fabs", _sub(y, m)), s))],
+    "lognormal": lambda y, m, s: [_const(-0.5 * _LOG_2PI), _un("neg", _log(s)), _un("neg", _log(y)),
+                                  _mul(_const(-0.5), _bin("^", _div(_sub(_log(y), m), s), _const(2.0)))],
+    "student_t": lambda y, nu, m, s: [_sub(_un("lgamma", _mul(_const(0.5), _add(nu, _const(1.0)))), _un("lgamma", _mul(_const(0.5), nu))),
+                                      _mul(_const(-0.5), _log(_mul(nu, _const(math.pi)))), _un("neg", _log(s)),
+                                      _un("neg", _mul(_mul(_const(0.5), _add(nu, _const(1.0))),
+                                                      _un("log1p", _div(_bin("^", _div(_sub(y, m), s), _const(2.0)), nu))))],
+    "exponential": lambda y, b: [_log(b), _un("neg", _mul(b, y))],
+    "gamma": lambda y, a, b: [_mul(a, _log(b)), _un("neg", _un("lgamma", a)), _mul(_sub(a, _const(1.0)), _log(y)), _un("neg", _mul(b, y))],
+    "inv_gamma": lambda y, a, b: [_mul(a, _log(b)), _un("neg", _un("lgamma", a)), _un("neg", _mul(_add(a, _const(1.0)), _log(y))),
+                                  _un("neg", _div(b, y))],
+    "beta": lambda y, a, b: [_sub(_un("lgamma", _add(a, b)), _add(_un("lgamma", a), _un("lgamma", b))),
+                             _mul(_sub(a, _const(1.0)), _log(y)), _mul(_sub(b, _const(1.0)), _un("log1p", _un("neg", y)))],
+    "uniform": lambda y, a, b: [_un("neg", _log(_sub(b, a)))],
+    "poisson": lambda k, lam: [_mul(k, _log(lam)), _un("neg", lam), _un("neg", _un("lgamma", _add(k, _const(1.0))))],
+    "poisson_log": lambda k, eta: [_mul(k, eta), _un("neg", _un("exp", eta)), _un("neg", _un("lgamma", _add(k, _const(1.0))))],
+    "bernoulli": lambda k, p: [_mul(k, _log(p)), _mul(_sub(_const(1.0), k), _un("log1p", _un("neg", p)))],
+    "bernoulli_logit": lambda k, eta: [_mul(k, eta), _un("neg", _un("log1p_exp", eta))],
+    "binomial_logit": lambda k, n, eta: [_sub(_un("lgamma", _add(n, _const(1.0))),
+                                              _add(_un("lgamma", _add(k, _const(1.0))), _un("lgamma", _add(_sub(n, k), _const(1.0))))),
+                                         _mul(k, eta), _un("neg", _mul(n, _un("log1p_exp", eta)))],
+}
+_UNARY_FUNCS = {"exp": "exp", "log": "log", "log1p": "log1p", "sqrt": "sqrt", "fabs": "fabs", "abs": "fabs", "lgamma": "lgamma",
+                "tanh": "tanh", "sin": "sin", "cos": "cos", "inv_logit": "inv_logit", "log1p_exp": "log1p_exp"}
+
+
+# ------------------------------------------------------------------------------------------------ lowering + emission
+class _Var:
+    """A data array, parameter or model-block local."""
+
+    def __init__(self, name, kind, shape, base="real", offset=0, lower=None, upper=None, value=None):
+        self.name, self.kind, self.shape, self.base, self.offset = name, kind, shape, base, offset
+        self.lower, self.upper, self.value = lower, upper, value
+        self.size = 1
+        for s in shape:
+            self.size *= s
+        self.deps = frozenset()      # locals: coordinates the variable can depend on (fixpoint of the activity analysis)
+
+
+class GeneratedSource:
+    """Result of `generate`: C++ text of the model struct and what the host side needs to know about it."""
+
+    def __init__(self, struct_name, text, dim, blob, param_names, transforms, digest):
+        self.struct_name, self.text, self.dim, self.blob = struct_name, text, dim, blob
+        self.param_names, self.transforms, self.digest = param_names, transforms, digest
+
+
+class _Gen:
+    MAX_DIM = 64
+
+    def __init__(self, blocks, data, struct_name):
+        self.blocks, self.struct_name = blocks, struct_name
+        self.data_in = dict(data)
+        self.vars = {}          # name -> _Var
+        self.loop_vars = []     # stack of (name, c_name)
+        self.blob = []
+        self.lines = []
+        self.indent = 2
+        self.tmp = 0
+        self.derived = {}       # (data array, shift) -> blob offset of its tabulated lgamma
+        self.transforms = []    # per unconstrained coordinate: (kind, lo, hi) with kind in none/lower/upper/both
+        self.param_names = []
+
+    # ---- integer expressions (indices, bounds, sizes): folded to Python ints when no loop variable is involved
+    def int_expr(self, e):
+        """-> (int value or None, C text)"""
+        k = e[0]
+        if k == "num":
+            if not e[2]:
+                raise StanSubsetError(f"real literal {e[1]} where an integer is required")
+            return int(e[1]), str(int(e[1]))
+        if k == "var":
+            for name, cname in reversed(self.loop_vars):
+                if name == e[1]:
+                    return None, cname
+            v = self.vars.get(e[1])
+            if v is not None and v.kind == "data" and v.base == "int" and not v.shape:
+                return int(v.value), str(int(v.value))
+            raise StanSubsetError(f"line {e[2]}: {e[1]!r} is not an integer constant or loop variable")
+        if k == "neg":
+            v, c = self.int_expr(e[1])
+            return (None if v is None else -v), f"(-{c})"
+        if k == "bin" and e[1] in "+-*/":
+            (va, ca), (vb, cb) = self.int_expr(e[2]), self.int_expr(e[3])
+            if va is not None and vb is not None:
+                r = {"+": va + vb, "-": va - vb, "*": va * vb, "/": int(va / vb) if vb else 0}[e[1]]
+                return r, str(r)
+            return None, f"({ca} {e[1]} {cb})"
+        if k == "idx":     # integer data array element used as an index is not supported (no use in the target programs)
+            raise StanSubsetError("integer array elements as indices are outside the supported subset")
+        raise StanSubsetError(f"unsupported integer expression {e!r}")
+
+    def is_int_expr(self, e):
+        try:
+            self.int_expr(e)
+            return True
+        except StanSubsetError:
+            return False
+
+    # ---- flat 0-based element index of var[idx...] -> (int or None, C text)
+    def flat_index(self, v, idx_exprs, line=0):
+        if len(idx_exprs) != len(v.shape):
+            raise StanSubsetError(f"line {line}: {v.name} has {len(v.shape)} dimension(s), indexed with {len(idx_exprs)}")
+        val, text = 0, "0"
+        for e, n in zip(idx_exprs, v.shape):
+            iv, ic = self.int_expr(e)
+            if iv is not None and not (1 <= iv <= n):
+                raise StanSubsetError(f"line {line}: index {iv} of {v.name} is out of range 1..{n}")
+            if val is not None and iv is not None:
+                val = val * n + (iv - 1)
+                text = str(val)
+            else:
+                text = f"(({text}) * {n} + ({ic}) - 1)"
+                val = None
+        return val, text
+
+    # ---- real expressions -> Node
+    def real(self, e):
+        k = e[0]
+        if k == "num":
+            return _const(e[1])
+        if k == "neg":
+            return _un("neg", self.real(e[1]))
+        if k == "bin":
+            a, b = self.real(e[2]), self.real(e[3])
+            return _bin(e[1], a, b)
+        if k == "var" or k == "idx":
+            base, idx = (e, []) if k == "var" else (e[1], e[2])
+            if base[0] != "var":
+                raise StanSubsetError("only named variables can be indexed")
+            name = base[1]
+            for lv, cname in reversed(self.loop_vars):
+                if lv == name:
+                    return Node("ivar", name=cname)
+            v = self.vars.get(name)
+            if v is None:
+                raise StanSubsetError(f"line {base[2]}: unknown variable {name!r}")
+            if name == "phi" and v.kind == "data":
+                raise StanSubsetError(f"line {base[2]}: the tempering variable phi may only multiply a whole `target +=` term")
+            if len(idx) < len(v.shape):
+                raise StanSubsetError(f"line {base[2]}: whole-array use of {name!r} is only supported as a density argument")
+            iv, ic = self.flat_index(v, idx, base[2])
+            if v.kind == "data":
+                if iv is not None:
+                    return _const(v.value[iv] if v.shape else v.value)
+                return Node("data", name=name, idx=f"{v.offset} + {ic}")
+            if v.kind == "param":
+                if iv is not None:
+                    return Node("param", idx=str(v.offset + iv), val=v.offset + iv, deps=frozenset([v.offset + iv]))
+                return Node("param", idx=f"{v.offset} + {ic}", val=None, deps=frozenset(range(v.offset, v.offset + v.size)))
+            return Node("local", name=name, idx=(ic if v.shape else None), deps=v.deps)
+        if k == "call":
+            return self.call(e)
+        raise StanSubsetError(f"unsupported expression {e!r}")
+
+    def call(self, e):
+        name, args, line = e[1], e[2], e[3]
+        m = re.fullmatch(r"(\w+?)_(lpdf|lpmf|log)", name)
+        if m and m.group(1) in _DENSITIES:
+            return _add(*self.density_terms(m.group(1), args, line, vectorised=False))
+        if name in _UNARY_FUNCS and len(args) == 1:
+            return _un(_UNARY_FUNCS[name], self.real(args[0]))
+        if name == "square" and len(args) == 1:
+            return _bin("^", self.real(args[0]), _const(2.0))
+        if name == "inv" and len(args) == 1:
+            return _div(_const(1.0), self.real(args[0]))
+        if name == "pow" and len(args) == 2:
+            return _bin("^", self.real(args[0]), self.real(args[1]))
+        if name == "log_sum_exp" and len(args) == 2:
+            a, b = self.real(args[0]), self.real(args[1])
+            return _add(a, _un("log1p_exp", _sub(b, a)))
+        raise StanSubsetError(f"line {line}: function {name!r} is outside the supported subset")
+
+    def density_terms(self, dist, args, line, vectorised=True):
+        fn = _DENSITIES[dist]
+        if len(args) != fn.__code__.co_argcount:
+            raise StanSubsetError(f"line {line}: {dist} takes {fn.__code__.co_argcount} arguments")
+        return [self.hoist_lgamma(t) for t in fn(*[self.real(a) for a in args])]
+
+    def hoist_lgamma(self, n):
+        """lgamma(data[i] + c) is tabulated at generation time as one more data array (the log-factorials of a count
+        likelihood would otherwise be a run-time lgamma per observation and evaluation)."""
+        if n.kind not in ("un", "bin") or n.deps:
+            if n.kind in ("un", "bin"):
+                args = tuple(self.hoist_lgamma(a) for a in n.args)
+                if any(x is not y for x, y in zip(args, n.args)):
+                    return Node(n.kind, op=n.op, args=args, deps=n.deps)
+            return n
+        if n.kind == "un" and n.op == "lgamma":
+            a, shift = n.args[0], 0.0
+            if a.kind == "bin" and a.op in "+-" and a.args[0].kind == "data" and a.args[1].kind == "const":
+                a, shift = a.args[0], (a.args[1].val if a.op == "+" else -a.args[1].val)
+            if a.kind == "data":
+                key = (a.name, shift)
+                if key not in self.derived:
+                    src = self.vars[a.name]
+                    self.derived[key] = len(self.blob)
+                    self.blob += [math.lgamma(z + shift) if z + shift > 0 else math.inf for z in src.value]
+                off = self.derived[key] - self.vars[a.name].offset
+                return Node("data", name=a.name, idx=f"{off} + {a.idx}")
+            return n
+        args = tuple(self.hoist_lgamma(a) for a in n.args)
+        if any(x is not y for x, y in zip(args, n.args)):
+            return Node(n.kind, op=n.op, args=args, deps=n.deps)
+        return n
+
+    # ---- whole-array arguments of a density: length of the broadcast, or None when every argument is scalar
+    def vector_length(self, args):
+        n = None
+        for a in args:
+            if a[0] == "var":
+                v = self.vars.get(a[1])
+                if v is not None and v.shape and not any(a[1] == lv for lv, _ in self.loop_vars):
+                    if len(v.shape) != 1:
+                        raise StanSubsetError(f"whole-array density argument {a[1]!r} must be one-dimensional")
+                    if n is not None and n != v.shape[0]:
+                        raise StanSubsetError(f"density arguments of different lengths ({n} and {v.shape[0]})")
+                    n = v.shape[0]
+        return n
+
+    # ---- emission helpers
+    def emit(self, text):
+        self.lines.append("    " * self.indent + text)
+
+    def new_tmp(self, prefix="t"):
+        self.tmp += 1
+        return f"{prefix}{self.tmp}"
+
+    @staticmethod
+    def lit(v):
+        if v != v:
+            return "NAN"
+        if v in (math.inf, -math.inf):
+            return "INFINITY" if v > 0 else "(-INFINITY)"
+        r = repr(float(v))
+        return f"({r})" if r.startswith("-") else r
+
+    def topo(self, root):
+        order, seen = [], set()
+
+        def visit(n):
+            if id(n) in seen:
+                return
+            seen.add(id(n))
+            for a in n.args:
+                visit(a)
+            order.append(n)
+        visit(root)
+        return order
+
+    def emit_value_and_adjoints(self, root):
+        """Straight-line code for the value of `root` and the adjoints of its differentiable leaves.
+        -> (value C name, [(leaf node, adjoint C text)])"""
+        order = self.topo(root)
+        name = {}
+        for n in order:
+            if n.kind == "const":
+                name[id(n)] = self.lit(n.val)
+            elif n.kind == "param":
+                name[id(n)] = f"c[{n.idx}]"
+            elif n.kind == "local":
+                name[id(n)] = f"v_{n.name}" + (f"[{n.idx}]" if n.idx is not None else "")
+            elif n.kind == "data":
+                name[id(n)] = f"data[{n.idx}]"
+            elif n.kind == "ivar":
+                name[id(n)] = f"(double){n.name}"
+            else:
+                a = [name[id(x)] for x in n.args]
+                if n.kind == "un":
+                    text = {"neg": f"-{a[0]}", "inv_logit": f"smcgen_inv_logit({a[0]})", "log1p_exp": f"smcgen_log1p_exp({a[0]})"}.get(
+                        n.op, f"{n.op}({a[0]})")
+                    if n.op == "lgamma" and n.deps:
+                        raise StanSubsetError("lgamma of a parameter-dependent argument is outside the supported subset (no digamma)")
+                elif n.op == "^":
+                    text = f"sqrt({a[0]})" if _is_const(n.args[1], 0.5) else f"pow({a[0]}, {a[1]})"
+                else:
+                    text = f"{a[0]} {n.op} {a[1]}"
+                t = self.new_tmp()
+                self.emit(f"const double {t} = {text};")
+                name[id(n)] = t
+        # reverse sweep over the nodes that depend on parameters
+        adj = {id(root): ["1.0"]}
+        leaves = []
+        for n in reversed(order):
+            if not n.deps or id(n) not in adj:
+                continue
+            terms = adj[id(n)]
+            a_text = terms[0] if len(terms) == 1 else "(" + " + ".join(terms) + ")"
+            if n.kind in ("param", "local"):
+                leaves.append((n, a_text))
+                continue
+            if len(terms) > 1 or len(a_text) > 24:
+                t = self.new_tmp("a")
+                self.emit(f"const double {t} = {a_text};")
+                a_text = t
+            v = name[id(n)]
+            xs = [name[id(x)] for x in n.args]
+
+            def push(child, factor):
+                if child.deps:
+                    term = a_text if factor is None else factor if a_text == "1.0" else f"{a_text} * {factor}"
+                    adj.setdefault(id(child), []).append(term)
+            if n.kind == "un":
+                x = xs[0]
+                push(n.args[0], {"neg": "(-1.0)", "exp": v, "log": f"(1.0 / {x})", "log1p": f"(1.0 / (1.0 + {x}))",
+                                 "sqrt": f"(0.5 / {v})", "fabs": f"copysign(1.0, {x})", "tanh": f"(1.0 - {v} * {v})",
+                                 "sin": f"cos({x})", "cos": f"(-sin({x}))", "inv_logit": f"({v} * (1.0 - {v}))",
+                                 "log1p_exp": f"smcgen_inv_logit({x})"}[n.op])
+            elif n.op == "+":
+                push(n.args[0], None); push(n.args[1], None)
+            elif n.op == "-":
+                push(n.args[0], None); push(n.args[1], "(-1.0)")
+            elif n.op == "*":
+                push(n.args[0], xs[1]); push(n.args[1], xs[0])
+            elif n.op == "/":
+                push(n.args[0], f"(1.0 / {xs[1]})"); push(n.args[1], f"(-{v} / {xs[1]})")
+            elif n.op == "^":
+                if _is_const(n.args[1], 0.5):
+                    push(n.args[0], f"(0.5 / {v})")
+                else:
+                    push(n.args[0], f"({xs[1]} * pow({xs[0]}, {xs[1]} - 1.0))")
+                    push(n.args[1], f"({v} * log({xs[0]}))")
+        return name[id(root)], leaves
+
+    def emit_sensitivities(self, target_of, leaves, deps, accumulate):
+        """d_target[k] (+)= sum over the leaves of adjoint * d leaf / d x_k, coordinate by coordinate.
+        target_of(k) -> C lvalue of coordinate k;  param leaves with a run-time index scatter through `dyn`."""
+        per_k = {k: [] for k in sorted(deps)}
+        dynamic = []
+        for n, a in leaves:
+            if n.kind == "param":
+                if n.val is not None:
+                    per_k[n.val].append(f"{a} * dc[{n.val}]")
+                else:
+                    dynamic.append((n, a))
+            else:
+                vd = f"d_{n.name}" + (f"[{n.idx}]" if n.idx is not None else "")
+                for k in sorted(n.deps):
+                    per_k[k].append(f"{a} * {vd}[{k}]")
+        for k in sorted(deps):
+            terms = per_k[k]
+            if accumulate:
+                if terms:
+                    self.emit(f"{target_of(k)} += {' + '.join(terms)};")
+            else:
+                self.emit(f"{target_of(k)} = {' + '.join(terms) if terms else '0.0'};")
+        for n, a in dynamic:
+            self.emit(f"{target_of(n.idx)} += {a} * dc[{n.idx}];")
+
+    # ---- statements
+    def scale_split(self, e):
+        """`phi * E` (phi anywhere among the top-level factors) -> (True, E); otherwise (False, e)."""
+        def strip(x):
+            if x[0] == "var" and x[1] == "phi" and self.vars.get("phi") is not None and self.vars["phi"].kind == "data":
+                return True, None
+            if x[0] == "bin" and x[1] == "*":
+                fa, ra = strip(x[2])
+                if fa:
+                    return True, x[3] if ra is None else ("bin", "*", ra, x[3])
+                fb, rb = strip(x[3])
+                if fb:
+                    return True, x[2] if rb is None else ("bin", "*", x[2], rb)
+            return False, x
+        found, rest = strip(e)
+        if found and rest is None:
+            rest = ("num", 1.0, True)
+        return found, rest
+
+    def target_terms(self, e, line, drop_constant_terms):
+        """Emit `target += e` (possibly a vectorised density) into the A or B accumulators."""
+        tempered, e = self.scale_split(e)
+        acc = "B" if tempered else "A"
+        vec_n, m = None, None
+        if e[0] == "call":
+            m = re.fullmatch(r"(\w+?)_(lpdf|lpmf|log)", e[1])
+            m = m if (m and m.group(1) in _DENSITIES) else None
+            if m:
+                vec_n = self.vector_length(e[2])
+        if vec_n is not None:     # vectorised density: an element loop with scalar arguments broadcast
+            cname = self.new_tmp("i")
+            if vec_n <= 16:
+                self.emit("#pragma unroll")
+            self.emit(f"for (int {cname} = 1; {cname} <= {vec_n}; ++{cname}) {{")
+            self.indent += 1
+            self.loop_vars.append((cname, cname))
+            args = [("idx", a, [("var", cname, line)]) if (a[0] == "var" and self.vars.get(a[1]) is not None and self.vars[a[1]].shape
+                                                          and not any(a[1] == lv for lv, _ in self.loop_vars[:-1])) else a for a in e[2]]
+            self.add_to_target(_add(*self.filter_terms(self.density_terms(m.group(1), args, line), drop_constant_terms)), acc)
+            self.loop_vars.pop()
+            self.indent -= 1
+            self.emit("}")
+            return
+        node = _add(*self.filter_terms(self.density_terms(m.group(1), e[2], line), drop_constant_terms)) if m else self.real(e)
+        if drop_constant_terms and not node.deps:
+            return
+        self.add_to_target(node, acc)
+
+    @staticmethod
+    def filter_terms(terms, drop_constant_terms):
+        kept = [t for t in terms if t.deps] if drop_constant_terms else list(terms)
+        return kept or [_const(0.0)]
+
+    def add_to_target(self, node, acc):
+        self.emit("{")
+        self.indent += 1
+        val, leaves = self.emit_value_and_adjoints(node)
+        self.emit(f"{acc} += {val};")
+        self.emit_sensitivities(lambda k: f"g{acc}[{k}]", leaves, node.deps, accumulate=True)
+        self.indent -= 1
+        self.emit("}")
+
+    def assign(self, lhs, op, rhs_node, line):
+        base, idx = (lhs, []) if lhs[0] == "var" else (lhs[1], lhs[2])
+        if lhs[0] not in ("var", "idx") or base[0] != "var" or base[1] not in self.vars or self.vars[base[1]].kind != "local":
+            raise StanSubsetError(f"line {line}: only model-block locals can be assigned")
+        v = self.vars[base[1]]
+        _, ic = self.flat_index(v, idx, line)
+        cell = f"v_{v.name}" + (f"[{ic}]" if v.shape else "")
+        dcell = f"d_{v.name}" + (f"[{ic}]" if v.shape else "")
+        self_node = Node("local", name=v.name, idx=(ic if v.shape else None), deps=v.deps)
+        if op in ("*=", "/="):
+            rhs_node, op = _bin(op[0], self_node, rhs_node), "="
+        self.emit("{")
+        self.indent += 1
+        val, leaves = self.emit_value_and_adjoints(rhs_node)
+        if op == "=":
+            reads_self = any(n.kind == "local" and n.name == v.name for n, _ in leaves)
+            if reads_self and v.deps:        # the old sensitivities are inputs: build the new ones aside
+                self.emit(f"double nd[{max(v.deps) + 1}];")
+                self.emit_sensitivities(lambda k: f"nd[{k}]", leaves, v.deps, accumulate=False)
+                for k in sorted(v.deps):
+                    self.emit(f"{dcell}[{k}] = nd[{k}];")
+            else:
+                self.emit_sensitivities(lambda k: f"{dcell}[{k}]", leaves, v.deps, accumulate=False)
+            self.emit(f"{cell} = {val};")
+        else:
+            sign = "" if op == "+=" else "-"
+            if sign:
+                leaves = [(n, f"(-({a}))") for n, a in leaves]
+            self.emit_sensitivities(lambda k: f"{dcell}[{k}]", leaves, rhs_node.deps, accumulate=True)
+            self.emit(f"{cell} {op} {val};")
+        self.indent -= 1
+        self.emit("}")
+
+    def statements(self, stmts, emit=True):
+        for s in stmts:
+            kind, line = s[0], s[-1]
+            if kind == "decl":
+                name, base, shape, lo, hi, init, _ = s[1]
+                if name in self.vars and self.vars[name].kind != "local":
+                    raise StanSubsetError(f"line {line}: {name!r} shadows a data variable or parameter")
+                dims = []
+                for d in shape:
+                    dv, _ = self.int_expr(d)
+                    if dv is None:
+                        raise StanSubsetError(f"line {line}: local array sizes must be constants")
+                    dims.append(dv)
+                if name not in self.vars:
+                    self.vars[name] = _Var(name, "local", dims, base)
+                if init is not None:
+                    self.statements([("assign", ("var", name, line), "=", init, line)], emit)
+            elif kind == "block":
+                self.statements(s[1], emit)
+            elif kind == "for":
+                _, var, lo, hi, body, _ = s
+                (lov, loc), (hiv, hic) = self.int_expr(lo), self.int_expr(hi)
+                cname = f"{var}_{len(self.loop_vars)}"
+                if emit:
+                    trip = (hiv - lov + 1) if (lov is not None and hiv is not None) else None
+                    if trip is not None and trip <= 16:
+                        self.emit("#pragma unroll")
+                    self.emit(f"for (int {cname} = {loc}; {cname} <= {hic}; ++{cname}) {{")
+                    self.indent += 1
+                self.loop_vars.append((var, cname))
+                self.statements(body, emit)
+                self.loop_vars.pop()
+                if emit:
+                    self.indent -= 1
+                    self.emit("}")
+            elif kind == "target":
+                if emit:
+                    self.target_terms(s[1], line, drop_constant_terms=False)
+            elif kind == "tilde":
+                if emit:
+                    _, lhs, dist, args, _ = s
+                    if dist not in _DENSITIES:
+                        raise StanSubsetError(f"line {line}: distribution {dist!r} is outside the supported subset")
+                    self.target_terms(("call", dist + "_lpdf", [lhs] + args, line), line, drop_constant_terms=True)
+            elif kind == "assign":
+                _, lhs, op, rhs, _ = s
+                node = self.real(rhs)
+                if emit:
+                    self.assign(lhs, op, node, line)
+                else:      # activity analysis: the assigned local inherits the dependencies of its right-hand side
+                    base = lhs if lhs[0] == "var" else lhs[1]
+                    v = self.vars.get(base[1]) if base[0] == "var" else None
+                    if v is None or v.kind != "local":
+                        raise StanSubsetError(f"line {line}: only model-block locals can be assigned")
+                    new = v.deps | node.deps
+                    if new != v.deps:
+                        v.deps = new
+                        self.changed = True
+
+    # ---- driver
+    def run(self):
+        # data block
+        for name, base, shape, lo, hi, init, line in self.blocks["data"]:
+            dims = [self.int_expr(d)[0] for d in shape]
+            if name == "phi" and name not in self.data_in:
+                self.data_in[name] = 1.0
+            if name not in self.data_in:
+                raise StanSubsetError(f"line {line}: data variable {name!r} is missing from the data")
+            val = self.data_in[name]
+            if dims:
+                flat = [float(z) for z in _flatten(val)]
+                n = 1
+                for d in dims:
+                    n *= d
+                if len(flat) != n:
+                    raise StanSubsetError(f"data {name!r}: expected {n} values, found {len(flat)}")
+                v = _Var(name, "data", dims, base, offset=len(self.blob), value=flat)
+                self.blob += flat
+            else:
+                v = _Var(name, "data", [], base, value=(int(val) if base == "int" else float(val)))
+            self.vars[name] = v
+        # parameters block
+        off = 0
+        for name, base, shape, lo, hi, init, line in self.blocks["parameters"]:
+            if base != "real":
+                raise StanSubsetError(f"line {line}: parameters must be real")
+            dims = [self.int_expr(d)[0] for d in shape]
+            lov = None if lo is None else self._const_value(lo, line)
+            hiv = None if hi is None else self._const_value(hi, line)
+            v = _Var(name, "param", dims, "real", offset=off, lower=lov, upper=hiv)
+            self.vars[name] = v
+            kind = "none" if (lov is None and hiv is None) else "both" if (lov is not None and hiv is not None) else \
+                "lower" if lov is not None else "upper"
+            for j in range(v.size):
+                self.transforms.append((kind, lov, hiv))
+                self.param_names.append(name if not dims else f"{name}.{'.'.join(str(i + 1) for i in _unravel(j, dims))}")
+            off += v.size
+        self.dim = off
+        if not (1 <= self.dim <= self.MAX_DIM):
+            raise StanSubsetError(f"{self.dim} unconstrained parameters; the generated kernels support 1..{self.MAX_DIM}")
+        # activity analysis (which coordinates can each local depend on): fixpoint over the statement list
+        for _ in range(64):
+            self.changed = False
+            self.loop_vars = []
+            self.statements(self.blocks["model"], emit=False)
+            if not self.changed:
+                break
+        # emission
+        self.loop_vars = []
+        body_start = len(self.lines)
+        for v in self.vars.values():
+            if v.kind == "local":
+                dims = "".join(f"[{n}]" for n in ([v.size] if v.shape else []))
+                self.emit(f"double v_{v.name}{dims}{' = {0.0}' if v.shape else ' = 0.0'};")
+                if v.deps:
+                    self.emit(f"double d_{v.name}{dims}[{max(v.deps) + 1}]{' = {{0.0}}' if v.shape else ' = {0.0}'};")
+        self.statements(self.blocks["model"], emit=True)
+        body = "\n".join(self.lines[body_start:])
+        return self.wrap(body)
+
+    def _const_value(self, e, line):
+        n = self.real(e)
+        if n.kind != "const":
+            raise StanSubsetError(f"line {line}: parameter bounds must be constants")
+        return n.val
+
+    def wrap(self, body):
+        D = self.dim
+        pro = []
+        for k, (kind, lo, hi) in enumerate(self.transforms):
+            if kind == "none":
+                pro.append(f"c[{k}] = x[{k}]; dc[{k}] = 1.0;")
+            elif kind == "lower":
+                pro.append(f"{{ const double e = exp(x[{k}]); c[{k}] = {self.lit(lo)} + e; dc[{k}] = e; A += x[{k}]; gA[{k}] += 1.0; "
+                           f"ok = ok && e > 0.0 && e < INFINITY; }}")
+            elif kind == "upper":
+                pro.append(f"{{ const double e = exp(x[{k}]); c[{k}] = {self.lit(hi)} - e; dc[{k}] = -e; A += x[{k}]; gA[{k}] += 1.0; "
+                           f"ok = ok && e > 0.0 && e < INFINITY; }}")
+            else:
+                w = self.lit(hi - lo)
+                pro.append(f"{{ const double s = smcgen_inv_logit(x[{k}]); c[{k}] = {self.lit(lo)} + {w} * s; dc[{k}] = {w} * s * (1.0 - s); "
+                           f"A += log({w}) + log(s) + log1p(-s); gA[{k}] += 1.0 - 2.0 * s; ok = ok && s > 0.0 && s < 1.0; }}")
+        staged = len(self.blob) if len(self.blob) <= 4096 else 0
+        text = f"""// GENERATED by smcnuts/model/stan_codegen.py -- do not edit.  Model struct with the interface of csrc/models.cuh.
+#pragma once
+#include <cmath>
+#ifndef SMCGEN_HELPERS
+#define SMCGEN_HELPERS
+SMCB_HD double smcgen_inv_logit(double z) {{ return z >= 0.0 ? 1.0 / (1.0 + exp(-z)) : exp(z) / (1.0 + exp(z)); }}
+SMCB_HD double smcgen_log1p_exp(double z) {{ return (z > 0.0 ? z : 0.0) + log1p(exp(-fabs(z))); }}
+#endif
+struct {self.struct_name} {{
+    static constexpr int DMAX = {D}, STATIC_D = {D};
+    static constexpr int GROUP = 1, NLOC = {D}, STATIC_NL = {D};
+    static constexpr bool STAGE = false;
+    static constexpr int NDATA = {len(self.blob)}, NSTAGED = {staged};
+    const double* data;
+    SMCB_HD explicit {self.struct_name}(const smcb::ModelDesc& d, const double* staged) : data(NSTAGED ? staged : d.data) {{}}
+    SMCB_HD static constexpr int dim_of(const smcb::ModelDesc&) {{ return {D}; }}
+    SMCB_HD constexpr int dim() const {{ return {D}; }}
+    SMCB_HD constexpr int nloc() const {{ return {D}; }}
+    static int staged_doubles(const smcb::ModelDesc&) {{ return NSTAGED; }}
+
+    // A = log prior + log Jacobian (everything not multiplied by phi), B = the phi-scaled part, g = grad A + phi * grad B
+    SMCB_HD void eval(const double (&x)[DMAX], double phi, double& A_out, double& B_out, double (&g)[DMAX]) const {{
+        double A = 0.0, B = 0.0, gA[{D}] = {{0.0}}, gB[{D}] = {{0.0}}, c[{D}], dc[{D}];
+        bool ok = true;
+        {(chr(10) + '        ').join(pro)}
+{body}
+        if (!ok) A = -INFINITY;      // a constrained value under- or overflowed: Stan throws, the reference maps it to -inf
+        A_out = A; B_out = B;
+#pragma unroll
+        for (int k = 0; k < {D}; ++k) g[k] = gA[k] + phi * gB[k];
+    }}
+}};
+"""
+        return text
+
+
+def _flatten(v):
+    if isinstance(v, (list, tuple)):
+        for z in v:
+            yield from _flatten(z)
+    elif hasattr(v, "tolist") and not isinstance(v, (int, float)):
+        yield from _flatten(v.tolist())
+    else:
+        yield v
+
+
+def _unravel(j, dims):
+    out = []
+    for n in reversed(dims):
+        out.append(j % n)
+        j //= n
+    return list(reversed(out))
+
+
+def load_data(data_path):
+    """Read a Stan data JSON (the shipped PRMwCD.json is truncated after `"phi": `: repaired as the reference's _update_phi
+    would rewrite it, with phi = 1)."""
+    if data_path is None or str(data_path) == "None":
+        return {}
+    raw = Path(data_path).read_text()
+    try:
+        return json.loads(raw)
+    except json.JSONDecodeError:
+        return json.loads(raw + " 1.0}")
+
+
+def generate(stan_text, data, struct_name="GenModel"):
+    """Stan program text + data dict -> GeneratedSource."""
+    import hashlib
+    blocks = _Parser(stan_text).program()
+    g = _Gen(blocks, data, struct_name)
+    text = g.run()
+    digest = hashlib.sha256((text + repr(g.blob)).encode()).hexdigest()[:16]
+    return GeneratedSource(struct_name, text, g.dim, g.blob, g.param_names, g.transforms, digest)

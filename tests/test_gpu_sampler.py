@@ -78,8 +78,12 @@ def test_stanmodel_constructor_and_readme_signature(tmp_path):
     assert np.all(np.isfinite(s.mean_estimate)) and s.leapfrogs.sum() > 0
     with pytest.raises(Exception, match="Unknown L-kernel"):
         SMCSampler(2, 64, m, 0.01, StdNormal(4), StdNormal(4), "nope")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError):       # any other program goes to the Stan-subset code generator: it must exist
         StanModel("eight_schools", "x.stan", None)
+    bad = tmp_path / "bad.stan"
+    bad.write_text("parameters { real a; } model { a ~ wishart(1, 2); }")
+    with pytest.raises(NotImplementedError, match="wishart"):   # outside the subset: refused loudly, no fallback
+        StanModel("bad", str(bad), None)
 
 
 @pytest.mark.parametrize("lk,temp", [("forwardsLKernel", False), ("GaussianApproxLKernel", False), ("asymptoticLKernel", True)])

@@ -1,0 +1,222 @@
+"""Generic Stan-model ingestion (reference: smcnuts/model/bridgestan.py:13-26 hands any Stan
+program to BridgeStan).  CPU: the generated model struct is compiled with g++ and checked against the oracle densities,
+an independent scipy.stats restatement and finite differences.  GPU: the generated model runs through the NUTS / SMC
+kernels as a plug-in and is compared with the hand-written arma device function."""
+import ctypes
+import importlib.util
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import smc_oracle as O
+
+ROOT = Path(__file__).resolve().parents[1]
+STAN = ROOT / "tests" / "stan"
+CSRC = ROOT / "smc-nuts_b200" / "csrc"
+REF_MODELS = Path("/root/reference/stan_models")
+
+
+def _codegen():
+    spec = importlib.util.spec_from_file_location("smcb_stan_codegen", ROOT / "smc-nuts_b200/smcnuts/model/stan_codegen.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+SC = _codegen()
+HOST_HARNESS = r'''
+#include "common.cuh"
+#include "models.cuh"
+#include "model_gen.h"
+extern "C" void gen_logp(const double* x, long N, double phi, const double* blob, double* A, double* B, double* g) {
+    smcb::ModelDesc d{}; d.data = blob; d.dim = GenModel::DMAX;
+    GenModel m(d, blob);
+    for (long i = 0; i < N; ++i) {
+        double xv[GenModel::DMAX], gv[GenModel::DMAX];
+        for (int k = 0; k < GenModel::DMAX; ++k) xv[k] = x[i * GenModel::DMAX + k];
+        m.eval(xv, phi, A[i], B[i], gv);
+        for (int k = 0; k < GenModel::DMAX; ++k) g[i * GenModel::DMAX + k] = gv[k];
+    }
+}
+'''
+
+
+class HostModel:
+    """The generated struct compiled for the host (the same text nvcc compiles for the device)."""
+
+    def __init__(self, src, tmp_path):
+        (tmp_path / "model_gen.h").write_text(src.text)
+        (tmp_path / "host.cpp").write_text(HOST_HARNESS)
+        so = tmp_path / "libgen.so"
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", f"-I{CSRC}", f"-I{tmp_path}",
+                        str(tmp_path / "host.cpp"), "-o", str(so)], check=True, capture_output=True)
+        self.lib = ctypes.CDLL(str(so))
+        self.lib.gen_logp.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_double] + [ctypes.c_void_p] * 4
+        self.blob = np.array(src.blob if src.blob else [0.0])
+        self.dim = src.dim
+
+    def split(self, x, phi=1.0):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = len(x)
+        A, B, g = np.empty(n), np.empty(n), np.empty((n, self.dim))
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+        self.lib.gen_logp(p(x), n, float(phi), p(self.blob), p(A), p(B), p(g))
+        return A, B, g
+
+
+def _arma_data():
+    return {"T": 200, "y": json.loads((ROOT / "smc-nuts_b200/smcnuts/data/arma/arma.json").read_text())["y"]}
+
+
+def test_generated_arma_matches_oracle(tmp_path):
+    src = SC.generate((STAN / "arma11.stan").read_text(), _arma_data())
+    assert src.dim == 4 and src.param_names == ["mu", "beta", "theta", "sigma"]
+    assert [t[0] for t in src.transforms] == ["none", "none", "none", "lower"]
+    h = HostModel(src, tmp_path)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(300, 4)) * 0.5
+    t = O.COracleTarget("arma")
+    A, B, g = h.split(x, 0.6)
+    Ao, Bo, _, _ = t.split(x, grads=False)
+    np.testing.assert_allclose(A, Ao, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(B, Bo, rtol=1e-12)
+    np.testing.assert_allclose(g, t.logpdfgrad(x, 0.6), rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.skipif(not REF_MODELS.exists(), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("name", ["arma", "PRMwCD"])
+def test_reference_stan_programs_translate_to_the_oracle_densities(tmp_path, name):
+    """The mechanical translation of the reference's own .stan text agrees with the hand restatement of the oracle:
+    an independent pin of the model arithmetic (BridgeStan itself is not installable offline)."""
+    src = SC.generate((REF_MODELS / name / f"{name}.stan").read_text(), SC.load_data(REF_MODELS / name / f"{name}.json"))
+    h = HostModel(src, tmp_path)
+    t = O.COracleTarget(name)
+    assert src.dim == t.dim
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(400, src.dim)) * 0.7
+    for phi in (0.0, 0.37, 1.0):
+        A, B, g = h.split(x, phi)
+        Ao, Bo, _, _ = t.split(x, grads=False)
+        np.testing.assert_allclose(A, Ao, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(B, Bo, rtol=1e-12, atol=1e-10)
+        np.testing.assert_allclose(g, t.logpdfgrad(x, phi), rtol=1e-9, atol=1e-8)
+
+
+def _logistic_data(rng):
+    return {"N": 30, "K": 3, "y": rng.integers(0, 2, 30).tolist(), "X": rng.normal(size=90).tolist()}
+
+
+def test_generated_logistic_matches_scipy_restatement_and_finite_differences(tmp_path):
+    from scipy import stats
+    from scipy.special import expit
+    rng = np.random.default_rng(2)
+    data = _logistic_data(rng)
+    src = SC.generate((STAN / "logistic.stan").read_text(), data)
+    assert src.dim == 6 and src.param_names == ["alpha", "w.1", "w.2", "w.3", "tau", "rho"]
+    assert [t[0] for t in src.transforms] == ["none"] * 4 + ["lower", "both"]
+    h = HostModel(src, tmp_path)
+    X, y = np.array(data["X"]).reshape(30, 3), np.array(data["y"])
+    x = rng.normal(size=(50, 6)) * 0.8
+
+    def restated(u):
+        alpha, w, tau, s = u[0], u[1:4], np.exp(u[4]), expit(u[5])
+        rho = -1.0 + 3.0 * s
+        # `~` statements: Stan drops the parameter-free terms (here: the exponential's log rate, the Student-t's
+        # normaliser, the N(0, tau) 2 pi constants and the whole constant uniform density); Jacobians are kept
+        prior = -1.5 * tau + (stats.t.logpdf(alpha, 4, 0, 2.5) - stats.t.logpdf(0.0, 4, 0, 2.5)) \
+            + np.sum(-np.log(tau) - 0.5 * (w / tau) ** 2)
+        jac = u[4] + np.log(3.0) + np.log(s) + np.log1p(-s)
+        eta = alpha + rho + X @ w
+        return prior + jac, np.sum(stats.bernoulli.logpmf(y, expit(eta)))
+
+    A, B, g = h.split(x, 0.7)
+    ref = np.array([restated(u) for u in x])
+    np.testing.assert_allclose(A, ref[:, 0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(B, ref[:, 1], rtol=1e-12, atol=1e-12)
+    eps = 1e-6
+    for k in range(6):
+        xp, xm = x.copy(), x.copy()
+        xp[:, k] += eps; xm[:, k] -= eps
+        Ap, Bp, _ = h.split(xp, 0.7)
+        Am, Bm, _ = h.split(xm, 0.7)
+        fd = ((Ap + 0.7 * Bp) - (Am + 0.7 * Bm)) / (2 * eps)
+        np.testing.assert_allclose(g[:, k], fd, rtol=2e-6, atol=2e-6)
+
+
+def test_unsupported_constructs_fail_loudly_with_the_line():
+    ok = "data { int N; } parameters { real a; } model { a ~ normal(0, 1); }"
+    assert SC.generate(ok, {"N": 3}).dim == 1
+    for bad, what in [
+        ("parameters { real a; } model { if (a > 0) a ~ normal(0, 1); }", "if"),
+        ("parameters { real a; } model { a ~ wishart(1, 2); }", "wishart"),
+        ("parameters { matrix[2, 2] a; } model { }", "matrix"),
+        ("parameters { real a; } transformed parameters { real b; b = a; } model { }", "transformed parameters"),
+        ("data { int N; } parameters { real a; } model { a ~ normal(0, 1); }", "missing from the data"),
+        ("parameters { real a; } model { target += lgamma(a); }", "lgamma"),
+        ("data { real phi; } parameters { real a; } model { target += exp(phi * a); }", "phi"),
+    ]:
+        with pytest.raises(SC.StanSubsetError, match=what):
+            SC.generate(bad, {})
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_generated_model_runs_the_nuts_and_smc_kernels_like_the_builtin_one():
+    from smcnuts.distributions import StdNormal
+    from smcnuts.model.bridgestan import StanModel
+    from smcnuts.model.device_model import make_model
+    from smcnuts.model.generated import GeneratedModel
+    from smcnuts.proposal.nuts import NUTSProposal
+    from smcnuts.smc_sampler import SMCSampler
+    gen = GeneratedModel((STAN / "arma11.stan").read_text(), _arma_data(), "arma11")
+    ref = make_model("arma")
+    rng = np.random.default_rng(3)
+    N = 4096
+    x = rng.normal(size=(N, 4)) * 0.05 + np.array([0.0, 0.9, 0.0, -1.7])
+    r = rng.normal(size=(N, 4))
+    for phi in (0.3, 1.0):
+        np.testing.assert_allclose(gen.logpdf(x, phi), ref.logpdf(x, phi), rtol=1e-11)
+        np.testing.assert_allclose(gen.logpdfgrad(x, phi), ref.logpdfgrad(x, phi), rtol=1e-9, atol=1e-8)
+    kg, kr = NUTSProposal(gen, StdNormal(4), 0.01, rng=10), NUTSProposal(ref, StdNormal(4), 0.01, rng=10)
+    xg, _ = kg.rvs(x, r, 1.0)
+    xr, _ = kr.rvs(x, r, 1.0)
+    same = (kg.last["n_leapfrog"] == kr.last["n_leapfrog"]).cpu().numpy()
+    assert same.mean() > 0.99, same.mean()          # same trees up to the rounding of two formulations of one density
+    np.testing.assert_allclose(xg[same], xr[same], rtol=1e-6, atol=1e-8)
+    assert gen.constrain_kind == ref.constrain_kind
+    np.testing.assert_allclose(gen.constrain(x), ref.constrain(x), rtol=1e-15)
+    # whole SMC run through the reference-facing constructor, model resolved by StanModel(name, model_path, data_path)
+    data_path = ROOT / "smc-nuts_b200/smcnuts/data/arma/arma.json"
+    sm = StanModel("arma11", str(STAN / "arma11.stan"), str(data_path))
+    out = []
+    for target in (sm, ref):
+        s = SMCSampler(K=6, N=2048, target=target, step_size=0.01, sample_proposal=StdNormal(4), momentum_proposal=StdNormal(4),
+                       lkernel="forwardsLKernel", tempering=False, rng=10)
+        s.sample(show_progress=False)
+        out.append(s)
+    np.testing.assert_allclose(out[0].mean_estimate[-1], out[1].mean_estimate[-1], rtol=0.05, atol=0.02)
+    assert abs(out[0].leapfrogs.sum() / out[1].leapfrogs.sum() - 1.0) < 0.02
+
+
+@pytest.mark.gpu
+def test_generated_logistic_model_with_bounded_parameters_samples_and_constrains():
+    from scipy.special import expit
+    from smcnuts.distributions import StdNormal
+    from smcnuts.model.generated import GeneratedModel
+    from smcnuts.smc_sampler import SMCSampler
+    rng = np.random.default_rng(2)
+    m = GeneratedModel((STAN / "logistic.stan").read_text(), _logistic_data(rng), "logistic")
+    x = rng.normal(size=(64, 6))
+    c = m.constrain(x)
+    np.testing.assert_allclose(c[:, :4], x[:, :4])
+    np.testing.assert_allclose(c[:, 4], np.exp(x[:, 4]), rtol=1e-15)
+    np.testing.assert_allclose(c[:, 5], -1.0 + 3.0 * expit(x[:, 5]), rtol=1e-13, atol=1e-15)
+    s = SMCSampler(K=8, N=4096, target=m, step_size=0.05, sample_proposal=StdNormal(6), momentum_proposal=StdNormal(6),
+                   lkernel="forwardsLKernel", tempering=False, rng=3)
+    s.sample(show_progress=False)
+    est = s.mean_estimate[-1]
+    assert np.all(np.isfinite(est)) and est[4] > 0 and -1 < est[5] < 2 and s.leapfrogs.sum() > 0
