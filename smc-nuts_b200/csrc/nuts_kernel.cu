@@ -32,7 +32,10 @@ int device_sm_count() {
     return n;
 }
 
-template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
+#ifndef SMCB_ARMA_MIN_BLOCKS
+#define SMCB_ARMA_MIN_BLOCKS 4
+#endif
+template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = SMCB_ARMA_MIN_BLOCKS; };
 template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2; };
 template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1; };
 // PrmModelG, MEASURED (N = 2^20): 4 CTAs/SM at 118 registers 130.5 ms; 3 CTAs/SM 140+ ms; 5 CTAs/SM (96 registers, spills) 132-152 ms

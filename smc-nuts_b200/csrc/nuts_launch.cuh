@@ -59,6 +59,15 @@ __device__ __forceinline__ const double* stage_model(const ModelDesc& d, double*
     }
 }
 
+// REJECTED (measured on B200, round 2, gpurun_out/r2j, r2k): a per-warp reserve of claimed queue indices topped up by an
+// atomic whose result is read one trip later, plus an L2 prefetch of the claimed rows (meant to take the atomic round trip
+// and the DRAM latency of a new particle's rows out of every trip).  arma N = 2^20: 2.86 ms on demand, 4.08 / 3.60 / 3.31 ms
+// with chunks of 2 / 4 / 8; the prefetch was neutral.  A lane that finds the reserve empty idles a whole trip, and the
+// kernel is not latency- but issue-bound at 4 warps per scheduler (a DFMA occupies the dispatch port for two cycles:
+// 0.52 instructions per cycle issued + 0.69 x 0.5 for the FP64 second cycles = 86 % of the port), so hiding the
+// refill latency buys nothing there.  Occupancy sweep of the same kernel (1 / 2 / 3 / 4 CTAs per SM): 5.19 / 3.49 /
+// 3.02 / 2.90 ms; at 80 registers, 4 / 5 / 6 CTAs: 4.05 / 3.81 / 3.65 ms (spills cost more than the extra warps give).
+//
 // Tail compaction.  Once the work queue is empty the lanes of a warp finish one after the other, but the warp keeps
 // paying full price for every trip until its longest tree ends (an evaluation costs the FP64 pipe the same with 1 or
 // 32 live lanes): at N = 2^20 arma particles ~9 % of all evaluated lanes were idle, and the last ~0.5 ms of a 2.9 ms
@@ -88,7 +97,7 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
     extern __shared__ double smem[];
     constexpr int G = M::GROUP;
     constexpr int NW = LaunchCfg<M>::NT / 32;
-    __shared__ int s_tail;            // some warp of this CTA has found the queue empty
+    __shared__ int s_tail;            // number of warps of this CTA that have found the queue empty
     __shared__ int s_cnt[2][NW];      // tail mode: live particles per warp (double-buffered by trip parity)
     if (threadIdx.x == 0) s_tail = 0;
     M model(a.model, stage_model<M>(a.model, smem, staged, stage_offset));
@@ -103,9 +112,11 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
     bool drained = false;
     // with gradient carry-over the tree starts in the trip a particle is admitted, one trip earlier than otherwise
     const unsigned admit_parity = a.g_in ? 1u : 0u;
+    bool reported = false;                       // this warp is counted in s_tail
     for (unsigned trip = 0;; ++trip) {
         if constexpr (TailCfg<M>::ON) {
-            if (*(volatile int*)&s_tail) break;   // warp-uniform: one shared load for the whole warp
+            // tail mode starts once EVERY warp of the CTA has found the queue empty (warp-uniform test: one shared load)
+            if (*(volatile int*)&s_tail == NW) break;
         }
         // ---- refill finished particle groups from the work queue (warp-aggregated atomic)
         const bool admit = !AlignCfg<M>::ON || ((trip & 1u) == admit_parity);
@@ -122,7 +133,10 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
                 else drained = true;
             }
             if constexpr (TailCfg<M>::ON) {
-                if (__any_sync(0xffffffffu, drained)) *(volatile int*)&s_tail = 1;
+                if (!reported && __any_sync(0xffffffffu, drained)) {
+                    if (lane_id == 0) atomicAdd(&s_tail, 1);
+                    reported = true;
+                }
             }
         }
         if (__all_sync(0xffffffffu, lane.phase == kIdle)) {
