@@ -141,14 +141,35 @@ __global__ void __launch_bounds__(kScanThreads) normalise_tile_sum_kernel(const 
                                                                            long long ntiles) {
     __shared__ double sm[kTile + kTile / 32];
     const double z = *logZ;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long base = tile * kTile;
-        double w[kScanItems];
+    // software-pipelined over tiles: the next tile's weights are loaded before this tile's exps, stores and block scan
+    double xn[kScanItems];
+    long long tile = blockIdx.x;
+    if (tile < ntiles) {
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
-            const int e = k * kScanThreads + threadIdx.x;
-            const double x = (base + e < N) ? logw[base + e] : neg_inf();
-            w[k] = (x == neg_inf()) ? 0.0 : fast_exp(x - z);
+            const long long i = tile * kTile + k * kScanThreads + threadIdx.x;
+            xn[k] = (i < N) ? logw[i] : neg_inf();
+        }
+    }
+    for (; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * kTile;
+        double x[kScanItems], w[kScanItems];
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) x[k] = xn[k];
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) {
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) {
+                const long long i = next * kTile + k * kScanThreads + threadIdx.x;
+                xn[k] = (i < N) ? logw[i] : neg_inf();
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kScanItems; k += 2) {   // exps in interleaved pairs (two short dependency chains each)
+            double e0, e1;
+            fast_exp_pair(x[k] - z, x[k + 1] - z, e0, e1);
+            w[k] = (x[k] == neg_inf()) ? 0.0 : e0;
+            w[k + 1] = (x[k + 1] == neg_inf()) ? 0.0 : e1;
         }
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
