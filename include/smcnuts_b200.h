@@ -65,6 +65,10 @@ int smcb_combine_logp(const double* A, const double* B, double phi, long long N,
 
 /* ---- NUTS proposal (NUTSProposal.rvs nuts.py:34-175; accrej != 0: NUTSProposalWithAccRej.rvs nuts_acc_rej.py:27-52) */
 int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long long* bytes);
+/* Cap on the resident CTAs per SM of the following smcb_nuts_transition launches of the calling thread (0 = as many as
+ * fit, the default).  The chunked host path of NUTSProposal.rvs (nuts.py:34-56 with host arrays) runs the launches of
+ * several chunks side by side, each on a share of every SM, so that one chunk's last trees overlap the others' work. */
+int smcb_nuts_set_blocks_per_sm(int blocks_per_sm);
 int smcb_nuts_transition(void* handle, const double* x, const double* r, long long N, double eps, double phi,
                          int max_depth, int accrej, uint64_t seed, uint32_t iteration, uint64_t particle0,
                          double* x_new, double* r_new, double* A_old, double* B_old, double* A_new, double* B_new,

@@ -20,6 +20,7 @@ std::string& last_error_ref() {
     return s;
 }
 std::atomic<long long> g_launches{0};
+static thread_local int g_nuts_blocks_per_sm = 0;   // smcb_nuts_set_blocks_per_sm
 
 int device_sm_count() {
     static int n = 0;
@@ -217,6 +218,12 @@ int smcb_combine_logp(const double* A, const double* B, double phi, long long N,
     return check_launch("combine_logp_kernel");
 }
 
+int smcb_nuts_set_blocks_per_sm(int blocks_per_sm) {
+    SMCB_REQUIRE(blocks_per_sm >= 0, "blocks_per_sm must be >= 0 (0 = as many as fit)");
+    g_nuts_blocks_per_sm = blocks_per_sm;
+    return 0;
+}
+
 int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long long* bytes) {
     SMCB_REQUIRE(handle && bytes && N >= 0, "bad argument");
     SMCB_REQUIRE(max_depth >= 1 && max_depth <= 10, "max_depth must be in [1, 10] (reference: MAX_TREE_DEPTH = 10)");
@@ -267,6 +274,7 @@ int smcb_nuts_transition(void* handle, const double* x, const double* r, long lo
     a.x_new = x_new; a.r_new = r_new; a.A_old = A_old; a.B_old = B_old; a.A_new = A_new; a.B_new = B_new;
     a.ke_old = ke_old; a.ke_new = ke_new; a.n_leapfrog = n_leapfrog; a.accepted = accepted; a.depth = depth;
     a.accept_stat = accept_stat;
+    a.blocks_per_sm = g_nuts_blocks_per_sm;
     a.A_in = A_in; a.B_in = B_in; a.g_in = g_in; a.g_new = g_new;
     a.ws = (double*)workspace;
     cudaStream_t st = (cudaStream_t)stream;

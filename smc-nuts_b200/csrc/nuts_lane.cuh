@@ -74,6 +74,7 @@ struct NutsArgs {
     double* ws;           // workspace: lanes * ws_doubles(D, max_depth)
     unsigned long long* queue;  // work-queue head, zeroed before launch
     void* exchange;             // tail compaction: one Lane<M> per thread of the grid (nuts_launch.cuh)
+    int blocks_per_sm;          // cap on resident CTAs per SM (0: as many as fit)
 };
 
 // 16-byte pair, the unit of every access to the per-lane workspace record (LDG.128 / STG.128)

@@ -9,8 +9,11 @@
 
 namespace smcb {
 
-// Tuning knob for experiments (tools/quick_time.py): cap on resident CTAs per SM of the NUTS kernel.
-inline int blocks_per_sm_cap() {
+// Cap on resident CTAs per SM of the NUTS kernel: the caller's request (NutsArgs::blocks_per_sm, set through
+// smcb_nuts_set_blocks_per_sm -- the chunked host path runs several launches side by side, each on a share of every
+// SM), else the tuning knob for experiments (tools/quick_time.py), else none.
+inline int blocks_per_sm_cap(int requested) {
+    if (requested > 0) return requested;
     const char* e = getenv("SMCB_NUTS_BLOCKS_PER_SM");
     const int v = e ? atoi(e) : 0;
     return v > 0 ? v : 1 << 20;
@@ -226,13 +229,13 @@ __global__ void combine_logp_kernel(const double* __restrict__ A, const double* 
 }
 
 template <class M>
-static long long nuts_blocks(const Model* mdl, long long N, size_t smem, int* occ_out) {
+static long long nuts_blocks(const Model* mdl, long long N, size_t smem, int* occ_out, int requested = 0) {
     const int NT = LaunchCfg<M>::NT;
     auto kern = nuts_transition_kernel<M>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) return -1;
-    if (occ > blocks_per_sm_cap()) occ = blocks_per_sm_cap();
+    if (occ > blocks_per_sm_cap(requested)) occ = blocks_per_sm_cap(requested);
     long long blocks = (long long)device_sm_count() * occ;
     const long long need = (N * M::GROUP + NT - 1) / NT;
     if (blocks > need) blocks = need;
@@ -257,7 +260,7 @@ static int launch_nuts(const Model* mdl, NutsArgs a, long long ws_bytes, cudaStr
     const int NT = LaunchCfg<M>::NT;
     const int staged = M::staged_doubles(mdl->desc);
     const size_t smem = nuts_smem_bytes<M>(mdl->desc);
-    const long long blocks = nuts_blocks<M>(mdl, a.N, smem, nullptr);
+    const long long blocks = nuts_blocks<M>(mdl, a.N, smem, nullptr, a.blocks_per_sm);
     if (blocks < 0) return fail("smcb_nuts_transition", "kernel does not fit on an SM");
     M probe(mdl->desc, nullptr);
     const int rec = nuts_ws_doubles(probe.nloc(), a.max_depth, a.g_new != nullptr);

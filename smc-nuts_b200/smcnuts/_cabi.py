@@ -27,6 +27,7 @@ _SIGS = {
     "smcb_logp_grad": [_vp, _vp, _ll, _d, _vp, _vp, _vp, _vp],
     "smcb_combine_logp": [_vp, _vp, _d, _ll, _vp, _vp],
     "smcb_nuts_workspace_bytes": [_vp, _ll, _i, ctypes.POINTER(_ll)],
+    "smcb_nuts_set_blocks_per_sm": [_i],
     "smcb_nuts_transition": [_vp, _vp, _vp, _ll, _d, _d, _i, _i, _u64, _u32, _u64] + [_vp] * 16 + [_vp, _ll, _vp],
     "smcb_normals": [_u64, _u32, _u32, _u64, _ll, _i, _vp, _vp],
     "smcb_uniforms": [_u64, _u32, _u32, _u64, _ll, _u32, _vp, _vp],

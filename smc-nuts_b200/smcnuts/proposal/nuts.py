@@ -50,8 +50,12 @@ class NUTSProposal:
     PIPELINE_MIN_PARTICLES = 1 << 16
     # Chunk sizes as fractions of N: small first and last chunks keep the exposed head (first H2D) and tail (last
     # D2H) short, few large chunks in between keep the per-launch tail cost low (measured: tools/e2e_time.py)
-    PIPELINE_FRACTIONS = (1, 3, 3, 1)
-    PIPELINE_STREAMS = 3
+    PIPELINE_FRACTIONS = (1, 2, 3, 2, 1)
+    PIPELINE_STREAMS = 4
+    # resident CTAs per SM of each chunk's launch (0 = all that fit: the launches then run one after the other).
+    # MEASURED (B200, tools/e2e_time.py, N = 2^20 arma): launches side by side on a quarter of every SM each are slower
+    # (4.0-4.1 ms against 3.48 ms): the block scheduler does not spread a 148-CTA grid one CTA per SM.
+    PIPELINE_BLOCKS_PER_SM = 0
 
     def rvs(self, x_cond, r_cond, phi: float = 1.0):
         """Propagate particles through one NUTS transition each.  numpy in -> numpy out; CUDA tensors stay put.
@@ -99,6 +103,7 @@ class NUTSProposal:
         cur = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(cur)
+        _cabi.call("smcb_nuts_set_blocks_per_sm", int(self.PIPELINE_BLOCKS_PER_SM))
         for c in range(nchunk):
             lo, hi = bounds[c], bounds[c + 1]
             if hi == lo:
@@ -116,6 +121,7 @@ class NUTSProposal:
                 self._launch(x, r, o, lo, hi, phi, self.iteration, None, wss[c % nstream], s.cuda_stream)
                 xo_h[lo:hi].copy_(o["x_new"][lo:hi], non_blocking=True)
                 ro_h[lo:hi].copy_(o["r_new"][lo:hi], non_blocking=True)
+        _cabi.call("smcb_nuts_set_blocks_per_sm", 0)
         for s in streams:
             cur.wait_stream(s)
         cur.synchronize()
