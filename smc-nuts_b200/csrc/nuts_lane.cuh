@@ -156,6 +156,27 @@ struct Lane {
     }
 
     // ---- vector <-> record, two doubles (16 bytes) per access
+    // The wide records of the staged group kernels (8-26 coordinates per lane: the Gaussian tensor-core kernels) go to
+    // L2 only (ld/st.global.cg): 256 lanes x ~10 KB of records cannot live in an SM's L1 anyway, and streaming them
+    // through it evicted the kernel's register spills, whose reloads then showed up as long-scoreboard stalls on the
+    // bookkeeping scalars (ncu, round 2).  MEASURED (B200, D = 100): 78.6 -> 71.4 ms at N = 2^20, 20.5 -> 18.7 ms at 2^18.
+    // Not for the one-lane models: their ~1 KB records DO live in L1 (PRMwCD one-lane kernel, 6000 particles: 6x slower).
+#ifndef SMCB_WIDE_RECORDS_CG
+#define SMCB_WIDE_RECORDS_CG 1
+#endif
+    static constexpr bool kCg = (SMCB_WIDE_RECORDS_CG != 0) && M::STAGE;
+    SMCB_HD static void st2(double* p, const D2& t) {
+#if defined(__CUDA_ARCH__)
+        if constexpr (kCg) { __stcg(reinterpret_cast<double2*>(p), make_double2(t.x, t.y)); return; }
+#endif
+        *reinterpret_cast<D2*>(p) = t;
+    }
+    SMCB_HD static D2 ld2(const double* p) {
+#if defined(__CUDA_ARCH__)
+        if constexpr (kCg) { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); D2 t; t.x = v.x; t.y = v.y; return t; }
+#endif
+        return *reinterpret_cast<const D2*>(p);
+    }
     SMCB_HD void stv(double* p, const double (&v)[DM]) const {
         const int n_ = (M::STATIC_NL ? M::STATIC_NL : nl);
 #pragma unroll
@@ -163,14 +184,14 @@ struct Lane {
             D2 t;
             t.x = v[i];
             t.y = (i + 1 < n_) ? v[i + 1 < DM ? i + 1 : i] : 0.0;
-            *reinterpret_cast<D2*>(p + i) = t;
+            st2(p + i, t);
         }
     }
     SMCB_HD void ldv(const double* p, double (&v)[DM]) const {
         const int n_ = (M::STATIC_NL ? M::STATIC_NL : nl);
 #pragma unroll
         SMCB_PAIRS(i) {
-            const D2 t = *reinterpret_cast<const D2*>(p + i);
+            const D2 t = ld2(p + i);
             v[i] = t.x;
             if (i + 1 < n_) v[i + 1 < DM ? i + 1 : i] = t.y;
         }
@@ -280,8 +301,16 @@ struct Lane {
 
     // ---- shared-memory staging of a stored edge (M::STAGE)
     static constexpr bool kStage = M::STAGE;
-    SMCB_HD void stage_from_regs() {   // the active edge (the leaf just stored) -> staging row
-        stv(stg, xa); stv(stg + nlp, ra);
+    SMCB_HD void stage_from_regs() {   // the active edge (the leaf just stored) -> staging row (shared memory: plain stores)
+#pragma unroll
+        SMCB_PAIRS(i) {
+            const int j = i + 1 < DM ? i + 1 : i;
+            D2 tx, tr;
+            tx.x = xa[i]; tx.y = (i + 1 < DM) ? xa[j] : 0.0;
+            tr.x = ra[i]; tr.y = (i + 1 < DM) ? ra[j] : 0.0;
+            *reinterpret_cast<D2*>(stg + i) = tx;
+            *reinterpret_cast<D2*>(stg + nlp + i) = tr;
+        }
     }
     // start copying x[nlp] r[nlp] at c (workspace, contiguous) into the staging row; nothing waits here
     SMCB_HD void stage_issue(const double* c) {
@@ -347,16 +376,16 @@ struct Lane {
             double* og = other_g();
 #pragma unroll
             SMCB_PAIRS(i) {
-                const D2 tg = *reinterpret_cast<const D2*>(og + i);
+                const D2 tg = ld2(og + i);
                 const D2 tx = *reinterpret_cast<const D2*>(stg + i);
                 const D2 tr = *reinterpret_cast<const D2*>(stg + nlp + i);
                 D2 mx, mr, mg;
                 mx.x = xa[i]; mr.x = ra[i]; mg.x = ga[i];
                 const int j = i + 1 < DM ? i + 1 : i;
                 mx.y = xa[j]; mr.y = ra[j]; mg.y = ga[j];
-                *reinterpret_cast<D2*>(other_x() + i) = mx;
-                *reinterpret_cast<D2*>(other_r() + i) = mr;
-                *reinterpret_cast<D2*>(og + i) = mg;
+                st2(other_x() + i, mx);
+                st2(other_r() + i, mr);
+                st2(og + i, mg);
                 xa[i] = tx.x; ra[i] = tr.x; ga[i] = tg.x;
                 if (i + 1 < DM) { xa[j] = tx.y; ra[j] = tr.y; ga[j] = tg.y; }
             }
