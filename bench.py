@@ -52,8 +52,13 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the NUTS kernel, from `ncu --set full` captures under
 # profiles/ (keyed by workload and particles per GPU); not measured live -> "traffic_live": false in the line
 TRAFFIC = {
-    ("arma", 1 << 20): (364820992, "profiles/r1b_nuts_arma_details.csv: 108.7 MB read + 256.2 MB written (algorithmic: 184 MB "
-                                    "of particle rows and scalars; the rest is the per-lane tree workspace leaving L2)"),
+    ("arma", 1 << 20): (502095616, "ncu --set full capture of round 2 (profiles/r2_nuts_arma_details.csv, tools/r2_batch22.sh): 121.8 MB read "
+                                    "+ 380.3 MB written (algorithmic: 222 MB of particle rows and scalars; the rest is the per-lane tree "
+                                    "workspace leaving L2)"),
+    ("gauss", 1 << 18): (16656124000, "ncu --set full capture of round 2 (profiles/r2_nuts_gauss100_details.csv): 3.29 GB read + 13.36 GB "
+                                       "written at N = 2^18 (algorithmic 0.84 GB: the 10 KB per-lane tree records do not fit in L2)"),
+    ("PRMwCD", 1 << 17): (1948797000, "ncu --set full capture of round 2 (profiles/r2_nuts_prm_group_details.csv): 0.18 GB read + 1.76 GB "
+                                       "written at N = 2^17"),
 }
 
 
