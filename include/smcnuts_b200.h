@@ -50,6 +50,11 @@ int smcb_model_create(int kind, const double* host_data, long long n, int dim, v
  * kernel templates).  Replaces the generic half of bridgestan.py:13-26 (any Stan program handed to BridgeStan):
  * smcnuts/model/stan_codegen.py translates a Stan program into the struct.  host_data[n] is the plug-in's data blob. */
 int smcb_model_create_plugin(const char* so_path, const double* host_data, long long n, void** handle);
+/* Diagonal metric of the NUTS proposal for this model: with scale[dim] set (host array; NULL restores the identity metric
+ * of nuts.py:162-175), smcb_nuts_transition runs identity-metric NUTS on z = x / scale, i.e. NUTS with the mass matrix
+ * diag(1 / scale^2) (README.md:66-67 "future updates").  The caller passes z and gets z back (smcb_scale_rows converts);
+ * the by-products A, B stay the x-space split log density. */
+int smcb_model_set_scale(void* handle, const double* host_scale);
 int smcb_model_destroy(void* handle);
 int smcb_model_dim(void* handle);
 /* Host-only test hook (no GPU work): the tensor-core fragment packing of the PRMwCD NUTS kernel (csrc/models.cuh,
@@ -203,6 +208,8 @@ int smcb_gather_rows(const double* x, const int64_t* idx, long long M, int D, do
 /* out[i][d] = Stan's constraining transform of x[i][d] (bridgestan.py:93-120 calls param_constrain per particle).
  * table (device, 3*D doubles): per coordinate kind (0 identity, 1 lower: lo + exp u, 2 upper: hi - exp u, 3 both:
  * lo + (hi - lo) inv_logit u), lo, hi.  Used for generated models; the built-in ones fuse exp-on-last into the moments. */
+/* out[i][d] = x[i][d] * scale[d] (inverse = 0) or x[i][d] / scale[d] (inverse = 1); scale is a device array of D doubles */
+int smcb_scale_rows(const double* x, long long N, int D, const double* scale, int inverse, double* out, void* stream);
 int smcb_constrain_rows(const double* x, long long N, int D, const double* table, double* out, void* stream);
 
 /* ---- estimators (estimate.py:79-95 with constrain fused, bridgestan.py:93-120) */

@@ -174,7 +174,13 @@ class GaussTarget(_Target):
     `constrained_dim`, so Estimate takes the unconstrained branch (estimate.py:25-28).
     """
 
-    def __init__(self, dim=100, rho=0.9):
+    def __init__(self, dim=100, rho=0.9, precision=None):
+        if precision is not None:          # any symmetric positive definite precision matrix
+            P = np.asarray(precision, dtype=np.float64)
+            self.dim = P.shape[0]
+            self.P = 0.5 * (P + P.T)
+            self.Sigma = np.linalg.inv(self.P)
+            return
         self.dim = dim
         idx = np.arange(dim)
         self.Sigma = rho ** np.abs(idx[:, None] - idx[None, :])

@@ -255,9 +255,20 @@ typedef struct {
     uint64_t seed, particle, draw;
     uint32_t iter;
     long n_leapfrog;
+    const double* scale;   /* diagonal metric (NULL: identity, the reference): NUTS runs on z = x / scale */
     double H0, accept_sum; /* NUTS acceptance statistic (step-size adaptation; not in the reference): sum over the
                               leaves of min(1, exp(joint - joint_0)) */
 } Ctx;
+
+/* the model seen from the sampler: pi_z(z) = pi_x(scale * z), grad_z = scale * grad_x (identity when scale == NULL) */
+static double ctx_eval(const Ctx* c, const double* z, double* grad) {
+    if (!c->scale) return model_eval(c->m, z, c->phi, grad);
+    double x[MAXD];
+    for (int d = 0; d < c->D; ++d) x[d] = z[d] * c->scale[d];
+    double lp = model_eval(c->m, x, c->phi, grad);
+    for (int d = 0; d < c->D; ++d) grad[d] = grad[d] * c->scale[d];
+    return lp;
+}
 
 static double next_uniform(Ctx* c) { return stream_uniform(c->seed, c->iter, 0u, c->particle, c->draw++); }
 
@@ -291,7 +302,7 @@ static void build_tree(Ctx* c, const double* x, const double* r, const double* g
         double xn[MAXD], rn[MAXD], gn[MAXD];
         for (int d = 0; d < D; ++d) rn[d] = r[d] + half * g[d];
         for (int d = 0; d < D; ++d) xn[d] = x[d] + full * rn[d];
-        double lp = model_eval(c->m, xn, c->phi, gn);
+        double lp = ctx_eval(c, xn, gn);
         for (int d = 0; d < D; ++d) rn[d] = rn[d] + half * gn[d];
         c->n_leapfrog++;
         double joint = lp - 0.5 * dot(rn, rn, D);
@@ -334,7 +345,7 @@ static void nuts_one(Ctx* c, const double* x0, const double* r0, double* xo, dou
     const int D = c->D;
     const size_t sz = sizeof(double) * (size_t)D;
     double g0[MAXD];
-    double logp = model_eval(c->m, x0, c->phi, g0);
+    double logp = ctx_eval(c, x0, g0);
     double H0 = logp - 0.5 * dot(r0, r0, D);
     c->H0 = H0; c->accept_sum = 0.0;
     if (g_devmath) {
@@ -381,6 +392,10 @@ void orc_nuts_batch_stat(void* h, const double* x, const double* r, long N, doub
                          uint64_t seed, uint32_t iter, uint64_t particle0, int accrej, double* x_new, double* r_new,
                          double* lp_old, double* lp_new, int* n_leapfrog, int* accepted, int* depth_out,
                          double* accept_stat, int nthreads);
+void orc_nuts_batch_metric(void* h, const double* x, const double* r, long N, double eps, double phi, int max_depth,
+                           uint64_t seed, uint32_t iter, uint64_t particle0, int accrej, double* x_new, double* r_new,
+                           double* lp_old, double* lp_new, int* n_leapfrog, int* accepted, int* depth_out,
+                           double* accept_stat, const double* scale, int nthreads);
 
 /* NUTSProposal.rvs (nuts.py:34-56) and, when accrej != 0, NUTSProposalWithAccRej.rvs
  * (nuts_acc_rej.py:27-52) + hmc_accept_reject (utils.py:22-34).
@@ -397,15 +412,31 @@ void orc_nuts_batch_stat(void* h, const double* x, const double* r, long N, doub
                          uint64_t seed, uint32_t iter, uint64_t particle0, int accrej, double* x_new, double* r_new,
                          double* lp_old, double* lp_new, int* n_leapfrog, int* accepted, int* depth_out,
                          double* accept_stat, int nthreads) {
+    orc_nuts_batch_metric(h, x, r, N, eps, phi, max_depth, seed, iter, particle0, accrej, x_new, r_new, lp_old, lp_new,
+                          n_leapfrog, accepted, depth_out, accept_stat, 0, nthreads);
+}
+
+/* same with a diagonal metric: x and x_new are in x-space, the transition runs on z = x / scale (scale == NULL: identity) */
+void orc_nuts_batch_metric(void* h, const double* x, const double* r, long N, double eps, double phi, int max_depth,
+                           uint64_t seed, uint32_t iter, uint64_t particle0, int accrej, double* x_new, double* r_new,
+                           double* lp_old, double* lp_new, int* n_leapfrog, int* accepted, int* depth_out,
+                           double* accept_stat, const double* scale, int nthreads) {
     const Model* m = (const Model*)h;
     const int D = m->dim;
     (void)nthreads;
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1)
     for (long i = 0; i < N; ++i) {
-        Ctx c = {m, D, max_depth, eps, phi, 0.0, seed, particle0 + (uint64_t)i, 0, iter, 0, 0.0, 0.0};
+        Ctx c = {m, D, max_depth, eps, phi, 0.0, seed, particle0 + (uint64_t)i, 0, iter, 0, scale, 0.0, 0.0};
         double lp0, lps;
         int dep;
-        nuts_one(&c, x + i * D, r + i * D, x_new + i * D, r_new + i * D, &lp0, &lps, &dep);
+        if (scale) {
+            double z0[MAXD];
+            for (int d = 0; d < D; ++d) z0[d] = x[i * D + d] / scale[d];
+            nuts_one(&c, z0, r + i * D, x_new + i * D, r_new + i * D, &lp0, &lps, &dep);
+            for (int d = 0; d < D; ++d) x_new[i * D + d] = x_new[i * D + d] * scale[d];
+        } else {
+            nuts_one(&c, x + i * D, r + i * D, x_new + i * D, r_new + i * D, &lp0, &lps, &dep);
+        }
         int acc = 1;
         if (accrej) {
             const double *xc = x + i * D, *rc = r + i * D;

@@ -22,7 +22,7 @@ OUT_DIR = HERE / "smcnuts" / "_lib"
 OUT = OUT_DIR / "libsmcnuts_b200.so"
 OUT_PARITY = OUT_DIR / "libsmcnuts_b200_parity.so"
 PARITY_FLAGS = ["-DSMCB_PARITY=1", "-fmad=false"]
-SOURCES = ["nuts_kernel.cu", "weights.cu", "resample.cu", "gauss_lkernel.cu"]
+SOURCES = ["nuts_kernel.cu", "nuts_kernel_scaled.cu", "weights.cu", "resample.cu", "gauss_lkernel.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]  # IEEE FP64 everywhere; no fast-math

@@ -61,6 +61,7 @@ struct Model {
     ModelDesc desc;
     double* d_data;
     PluginVT* vt = nullptr;   // non-null: a generated model living in its own shared object
+    double* d_scale = nullptr; // device copy of the diagonal metric (smcb_model_set_scale)
 };
 
 #if defined(SMCB_PLUGIN_TU)

@@ -46,6 +46,7 @@ struct ModelDesc {
     int T;               // arma: series length; PRMwCD: number of observations
     double q;            // PRMwCD: exponent of the exponential-power prior
     const double* data;  // device (or, in tests/hostsim, host) pointer
+    const double* scale; // [dim] diagonal metric (nullable): NUTS then runs on z = x / scale (ScaledModel below)
 };
 
 // ---------------------------------------------------------------------------------------------- arma
@@ -533,5 +534,36 @@ inline void pack_gauss_fragments(const double* P, int D, int nt8, double* out) {
                 out[((size_t)nt * KK + kk) * 32 + l] = (k < D && col < D) ? P[(size_t)k * D + col] : 0.0;
             }
 }
+
+// ---------------------------------------------------------------------------------------------- diagonal metric
+// NUTS with a diagonal mass matrix M = diag(1 / scale^2) is NUTS with the identity metric on z = x / scale:
+// pi_z(z) = pi_x(scale * z) up to a constant, grad_z = scale * grad_x.  Wrapping the model keeps the lane code (leapfrog,
+// U-turn test, kinetic energy with standard-normal momenta) untouched; A and B stay the x-space split log density.
+// The reference's mass matrix is the identity (nuts.py:162-175); README.md:66-67 lists mass-matrix adaptation under
+// future updates.  Instantiated only for the opt-in path (csrc/nuts_kernel_scaled.cu).
+template <class M>
+struct ScaledModel : M {
+    const double* scale;
+    int d_;
+    SMCB_HD explicit ScaledModel(const ModelDesc& d, const double* staged) : M(d, staged), scale(d.scale), d_(d.dim) {}
+    SMCB_HD void eval(const double (&z)[M::NLOC], double phi, double& A, double& B, double (&g)[M::NLOC]) const {
+        double x[M::NLOC], s[M::NLOC];
+#if defined(SMCB_WARP_CODE) && defined(__CUDA_ARCH__)
+        const int sub = (M::GROUP == 1) ? 0 : (int)(threadIdx.x % M::GROUP);
+#else
+        const int sub = 0;
+#endif
+        const int n = M::STATIC_NL ? M::STATIC_NL : this->nloc();
+#pragma unroll
+        for (int i = 0; i < (M::STATIC_NL ? M::STATIC_NL : n); ++i) {
+            const int c = (M::GROUP == 1) ? i : sub + M::GROUP * i;
+            s[i] = (c < d_) ? SMCB_LDG(&scale[c]) : 1.0;
+            x[i] = z[i] * s[i];
+        }
+        M::eval(x, phi, A, B, g);
+#pragma unroll
+        for (int i = 0; i < (M::STATIC_NL ? M::STATIC_NL : n); ++i) g[i] *= s[i];
+    }
+};
 
 }  // namespace smcb

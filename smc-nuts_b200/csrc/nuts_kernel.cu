@@ -11,7 +11,7 @@
 #include <cstring>
 #include <vector>
 
-#include "nuts_launch.cuh"
+#include "nuts_builtin.cuh"
 
 namespace smcb {
 
@@ -33,43 +33,13 @@ int device_sm_count() {
     return n;
 }
 
-#ifndef SMCB_ARMA_MIN_BLOCKS
-#define SMCB_ARMA_MIN_BLOCKS 4
-#endif
-template <> struct LaunchCfg<ArmaModel> { static constexpr int NT = 128, MIN_BLOCKS = SMCB_ARMA_MIN_BLOCKS; };
-template <> struct LaunchCfg<PrmModel> { static constexpr int NT = 128, MIN_BLOCKS = 2; };
-template <> struct LaunchCfg<GaussModel> { static constexpr int NT = 128, MIN_BLOCKS = 1; };
-// PrmModelG, MEASURED (N = 2^20): 4 CTAs/SM at 118 registers 130.5 ms; 3 CTAs/SM 140+ ms; 5 CTAs/SM (96 registers, spills) 132-152 ms
-template <int T8> struct LaunchCfg<PrmModelG<T8>> { static constexpr int NT = 128, MIN_BLOCKS = 4; };
-constexpr int kPrmTiles = 13;   // PrmModelG instantiation: 81..104 observations (the shipped PRMwCD has 100)
-
-#if SMCB_ALIGN_PARITY == 2   // A/B experiments: also for the one-lane-per-particle kernels
-template <> struct AlignCfg<ArmaModel> { static constexpr bool ON = true; };
-template <> struct AlignCfg<PrmModel> { static constexpr bool ON = true; };
-#endif
-
-template <int NT8> struct StageOffset<GaussModelG<NT8>> { static int of(const ModelDesc& d) { return d.dim * d.dim; } };
-template <int T8> struct StageOffset<PrmModelG<T8>> { static int of(const ModelDesc& d) { return PrmModel::HDR + d.T * PrmModel::ROW; } };
-
-// PRMwCD runs on the tensor-core group kernel when the observation count fits the instantiated tile count
-// (SMCB_PRM_SCALAR=1 forces the one-lane-per-particle kernel: A/B experiments and the parity test of the two)
-// MEASURED (B200, tools/ab_time.py PRMwCD 16..20, fixed inputs): the group kernel wins at every size -- 13.2 vs 30.9 ms at
-// N = 2^16, 23.2 vs 36.8 ms at 2^17 (its trip latency is ~4x shorter, and the 2047-leapfrog trees set the makespan of a
-// small shard), 140.2 vs 150.7 ms at 2^20 -- once its tile loop is rolled so that the kernel fits the instruction cache.
-static bool prm_use_group(const ModelDesc& d, long long N) {
-    const char* e = getenv("SMCB_PRM_SCALAR");   // 1: one lane per particle (A/B experiments, parity test of the two)
-    (void)N;
-    return PrmModelG<kPrmTiles>::fits(d) && !(e && atoi(e) != 0);
+__global__ void combine_logp_kernel(const double* __restrict__ A, const double* __restrict__ B, double phi,
+                                    long long N, double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double lp = A[i] + phi * B[i];
+        out[i] = is_finite(lp) ? lp : neg_inf();
+    }
 }
-
-// Gaussian: tensor-core group kernel for D <= 104, one-lane-per-particle fallback above (SMCB_GAUSS_SCALAR=1 forces the
-// fallback: parity test of the two)
-static bool gauss_force_scalar() {
-    const char* e = getenv("SMCB_GAUSS_SCALAR");
-    return e && atoi(e) != 0;
-}
-#define SMCB_GAUSS_DISPATCH(D, CALL_G, CALL_PLAIN) \
-    (gauss_force_scalar() ? CALL_PLAIN : (D) <= 8 ? CALL_G(1) : (D) <= 16 ? CALL_G(2) : (D) <= 32 ? CALL_G(4) : (D) <= 64 ? CALL_G(8) : (D) <= 104 ? CALL_G(13) : CALL_PLAIN)
 
 }  // namespace smcb
 
@@ -172,9 +142,25 @@ int smcb_model_create_plugin(const char* so_path, const double* host_data, long 
     return 0;
 }
 
+int smcb_model_set_scale(void* handle, const double* host_scale) {
+    SMCB_REQUIRE(handle, "null argument");
+    Model* m = (Model*)handle;
+    if (!host_scale) {                       // back to the identity metric
+        m->desc.scale = nullptr;
+        return 0;
+    }
+    for (int d = 0; d < m->desc.dim; ++d)
+        SMCB_REQUIRE(host_scale[d] > 0.0 && host_scale[d] < 1e300, "scale entries must be positive and finite");
+    if (!m->d_scale) SMCB_CUDA(cudaMalloc(&m->d_scale, sizeof(double) * (size_t)m->desc.dim));
+    SMCB_CUDA(cudaMemcpy(m->d_scale, host_scale, sizeof(double) * (size_t)m->desc.dim, cudaMemcpyHostToDevice));
+    m->desc.scale = m->d_scale;
+    return 0;
+}
+
 int smcb_model_destroy(void* handle) {
     if (!handle) return 0;
     Model* m = (Model*)handle;
+    if (m->d_scale) cudaFree(m->d_scale);
     if (m->vt) {
         dlclose(m->vt->dl);
         delete m->vt;
@@ -235,6 +221,12 @@ int smcb_nuts_workspace_bytes(void* handle, long long N, int max_depth, long lon
         *bytes = b;
         return 0;
     }
+    if (m->desc.scale) {
+        b = nuts_ws_bytes_scaled(m, N, max_depth);
+        if (b < 0) return fail("smcb_nuts_workspace_bytes", "occupancy query failed");
+        *bytes = b;
+        return 0;
+    }
     switch (m->desc.kind) {
         case kArma: b = nuts_ws_bytes<ArmaModel>(m, N, max_depth); break;
         case kPRMwCD:
@@ -283,6 +275,7 @@ int smcb_nuts_transition(void* handle, const double* x, const double* r, long lo
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
+    if (m->desc.scale) return launch_nuts_scaled(m, a, workspace_bytes, st);
     switch (m->desc.kind) {
         case kArma: return launch_nuts<ArmaModel>(m, a, workspace_bytes, st);
         case kPRMwCD:

@@ -46,6 +46,9 @@ static size_t nuts_smem_bytes(const ModelDesc& d) {
 }
 
 template <class M> struct StageOffset { static int of(const ModelDesc&) { return 0; } };
+// the diagonal-metric wrapper launches like the model it wraps
+template <class M> struct LaunchCfg<ScaledModel<M>> : LaunchCfg<M> {};
+template <class M> struct StageOffset<ScaledModel<M>> : StageOffset<M> {};
 
 
 // Model data (y[200]; the PRMwCD table or its tensor-core fragments; the Gaussian B-fragments) is staged once per CTA into shared memory,
@@ -220,13 +223,6 @@ __global__ void __launch_bounds__(128) logp_grad_kernel(ModelDesc md, const doub
     }
 }
 
-__global__ void combine_logp_kernel(const double* __restrict__ A, const double* __restrict__ B, double phi,
-                                    long long N, double* __restrict__ out) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-        const double lp = A[i] + phi * B[i];
-        out[i] = is_finite(lp) ? lp : neg_inf();
-    }
-}
 
 template <class M>
 static long long nuts_blocks(const Model* mdl, long long N, size_t smem, int* occ_out, int requested = 0) {

@@ -32,10 +32,12 @@
     const char* smcb_plugin_last_error(void) { return smcb::last_error_ref().c_str(); }                                  \
     long long smcb_plugin_nuts_workspace_bytes(const smcb::ModelDesc* d, long long N, int max_depth) {                   \
         smcb::Model m{*d, nullptr};                                                                                      \
+        if (d->scale) return smcb::nuts_ws_bytes<smcb::ScaledModel<MODEL>>(&m, N, max_depth);                            \
         return smcb::nuts_ws_bytes<MODEL>(&m, N, max_depth);                                                             \
     }                                                                                                                    \
     int smcb_plugin_nuts_transition(const smcb::ModelDesc* d, const smcb::NutsArgs* a, long long ws_bytes, void* st) {   \
         smcb::Model m{*d, nullptr};                                                                                      \
+        if (d->scale) return smcb::launch_nuts<smcb::ScaledModel<MODEL>>(&m, *a, ws_bytes, (cudaStream_t)st);            \
         return smcb::launch_nuts<MODEL>(&m, *a, ws_bytes, (cudaStream_t)st);                                             \
     }                                                                                                                    \
     int smcb_plugin_logp_grad(const smcb::ModelDesc* d, const double* x, long long N, double phi, double* A, double* B,  \

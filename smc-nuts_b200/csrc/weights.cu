@@ -637,6 +637,16 @@ __global__ void constrain_rows_kernel(const double* __restrict__ x, long long n_
     }
 }
 
+// out[i][d] = x[i][d] * scale[d] (inverse = 0) or x[i][d] / scale[d] (inverse = 1): the change of variables of the
+// diagonal-metric NUTS path (ScaledModel, models.cuh) at the kernel's boundaries
+__global__ void scale_rows_kernel(const double* __restrict__ x, long long n_elem, int D, const double* __restrict__ scale,
+                                  int inverse, double* __restrict__ out) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_elem; e += (long long)gridDim.x * blockDim.x) {
+        const double s = scale[(int)(e % D)];
+        out[e] = inverse ? x[e] / s : x[e] * s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ FP64 probe
 __global__ void probe_fp64_kernel(int iters, double* sink) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -922,6 +932,13 @@ int smcb_weighted_moment(const double* x, const double* wn, long long N, int D, 
     weighted_moment_kernel<<<stride_grid(N * D, kRedThreads * 4, 4), kRedThreads, 0, st>>>(x, wn, N, D, constrain, center,
                                                                                         power, out, (double*)workspace, used);
     return check_launch("weighted_moment_kernel");
+}
+
+int smcb_scale_rows(const double* x, long long N, int D, const double* scale, int inverse, double* out, void* stream) {
+    SMCB_REQUIRE(x && scale && out && N >= 0 && D >= 1, "bad argument");
+    if (N == 0) return 0;
+    scale_rows_kernel<<<stride_grid(N * D, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, N * D, D, scale, inverse, out);
+    return check_launch("scale_rows_kernel");
 }
 
 int smcb_constrain_rows(const double* x, long long N, int D, const double* table, double* out, void* stream) {

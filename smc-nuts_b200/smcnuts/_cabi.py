@@ -21,6 +21,7 @@ _u64, _u32 = ctypes.c_uint64, ctypes.c_uint32
 _SIGS = {
     "smcb_model_create": [_i, _vp, _ll, _i, ctypes.POINTER(_vp)],
     "smcb_model_create_plugin": [ctypes.c_char_p, _vp, _ll, ctypes.POINTER(_vp)],
+    "smcb_model_set_scale": [_vp, _vp],
     "smcb_model_destroy": [_vp],
     "smcb_model_dim": [_vp],
     "smcb_debug_pack_prm": [_vp, _i, _i, _vp, _ll],
@@ -76,6 +77,7 @@ _SIGS = {
     "smcb_sum_int32": [_vp, _ll, _vp, _vp, _vp],
     "smcb_sum_f64": [_vp, _ll, _vp, _vp, _vp],
     "smcb_constrain_rows": [_vp, _ll, _i, _vp, _vp, _vp],
+    "smcb_scale_rows": [_vp, _ll, _i, _vp, _i, _vp, _vp],
     "smcb_fast_exp": [_vp, _ll, _vp, _vp],
     "smcb_fast_log": [_vp, _ll, _vp, _vp],
     "smcb_probe_fp64": [_i, _i, _i, _vp, _vp],

@@ -53,6 +53,21 @@ class DeviceModel:
         except Exception:
             pass
 
+    # ---- diagonal metric of the NUTS proposal (README.md:66-67 "future updates" of the reference; identity by default)
+    metric_scale = None      # host array [dim] or None
+    _scale_dev = None
+
+    def set_metric_scale(self, scale):
+        """NUTS on this model then uses the mass matrix diag(1 / scale^2), i.e. identity-metric NUTS on z = x / scale
+        (csrc/models.cuh::ScaledModel).  None restores the reference's identity metric."""
+        if scale is None:
+            _cabi.call("smcb_model_set_scale", self._h, None)
+            self.metric_scale = self._scale_dev = None
+            return
+        sc = np.ascontiguousarray(dev.to_numpy(scale), dtype=np.float64).reshape(self.dim)
+        _cabi.call("smcb_model_set_scale", self._h, sc.ctypes.data)
+        self.metric_scale, self._scale_dev = sc, dev.to_device(sc)
+
     # ---- device-native entry points (torch CUDA tensors)
     def split(self, x, grad_phi=None):
         """(A, B[, grad]) with A = log prior + log Jacobian, B = log likelihood; grad = d(A + grad_phi*B)/dx."""

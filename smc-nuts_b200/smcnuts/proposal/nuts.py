@@ -67,7 +67,8 @@ class NUTSProposal:
         D = self.target.dim
         host_in = dev.is_host(x_cond) or not x_cond.is_cuda
         n = (x_cond.size if dev.is_host(x_cond) else x_cond.numel()) // D if host_in else 0
-        if host_in and n >= self.PIPELINE_MIN_PARTICLES and (dev.is_host(r_cond) or not r_cond.is_cuda):
+        scaled = getattr(self.target, "_scale_dev", None) is not None      # diagonal metric: the simple path converts x <-> z
+        if host_in and not scaled and n >= self.PIPELINE_MIN_PARTICLES and (dev.is_host(r_cond) or not r_cond.is_cuda):
             out = self._rvs_pipelined(x_cond, r_cond, float(phi), n)
             self.iteration += 1
             return out
@@ -131,7 +132,7 @@ class NUTSProposal:
     def _workspace_bytes(self, N):
         # the kernel variant (and its scratch) also depends on the A/B environment switches of csrc/nuts_kernel.cu
         key = (N, self.max_tree_depth, _cabi.LIB_PATH, os.environ.get("SMCB_PRM_SCALAR"), os.environ.get("SMCB_GAUSS_SCALAR"),
-               os.environ.get("SMCB_NUTS_BLOCKS_PER_SM"))
+               os.environ.get("SMCB_NUTS_BLOCKS_PER_SM"), getattr(self.target, "_scale_dev", None) is not None)
         b = self._ws_bytes.get(key)
         if b is None:
             nbytes = _cabi._ll()
@@ -171,6 +172,12 @@ class NUTSProposal:
         ws = dev.workspace("nuts", self._workspace_bytes(N))
         if self.accept_reject:
             carry, want_grad = None, False
+        scale = getattr(self.target, "_scale_dev", None)
+        if scale is not None:   # diagonal metric: the kernel works on z = x / scale (gradients there are z-space: no carry-over)
+            carry, want_grad = None, False
+            z = dev.empty(N, D)
+            _cabi.call("smcb_scale_rows", dev.ptr(x), N, D, dev.ptr(scale), 1, dev.ptr(z), dev.stream_ptr())
+            x = z
         o = self._alloc_outputs(N, D, want_grad)
         if self.record_events:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -179,6 +186,8 @@ class NUTSProposal:
         if self.record_events:
             e1.record()
             self.events.append((e0, e1))
+        if scale is not None:   # back to x-space, in place
+            _cabi.call("smcb_scale_rows", dev.ptr(o["x_new"]), N, D, dev.ptr(scale), 0, dev.ptr(o["x_new"]), dev.stream_ptr())
         self.last = o
         return o
 

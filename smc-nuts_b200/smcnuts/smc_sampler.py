@@ -26,7 +26,7 @@ class SMCSampler:
     def __init__(self, K: int, N: int, target, step_size=None, sample_proposal=None, momentum_proposal=None,
                  lkernel="forwardsLKernel", tempering=False, rng=None, forward_kernel=None, verbose=False,
                  resampling="multinomial", save_history=None, history_budget_bytes=48 << 30, shard=None,
-                 adapt_step_size=0, target_accept=0.8):
+                 adapt_step_size=0, target_accept=0.8, adapt_mass_matrix=False):
         self.K = K  # Number of iterations
         self.N = N  # Number of particles (global)
         self.target = target
@@ -54,6 +54,15 @@ class SMCSampler:
                 raise TypeError("adapt_step_size needs the device NUTS proposal (it emits the acceptance statistic)")
             forward_kernel.want_accept_stat = True
             self.step_size_adapter = DualAveragingStepSize(forward_kernel.step_size, target_accept)
+        # Diagonal mass-matrix adaptation (same README paragraph): during the first half of the adaptation window the
+        # metric follows the weighted particle variance of the unconstrained coordinates (regularised as in Stan), the
+        # dual averaging restarts whenever the metric changes; both are frozen afterwards.
+        self.adapt_mass_matrix = bool(adapt_mass_matrix)
+        if self.adapt_mass_matrix and not (self.adapt_iters and hasattr(target, "set_metric_scale")):
+            raise TypeError("adapt_mass_matrix needs adapt_step_size=K_adapt and a device model")
+        self.metric_iters = self.adapt_iters // 2 if self.adapt_mass_matrix else 0
+        self.metric_scale = None                # the frozen diagonal metric (host array) once adaptation has set one
+        self._metric_estimator = Estimate(self.target, shard=self.shard) if self.adapt_mass_matrix else None
         self.step_sizes = np.full(K, float(getattr(forward_kernel, "step_size", np.nan)))   # step size used at iteration k
         self.accept_stat = np.full(K, np.nan)   # mean NUTS acceptance statistic of iteration k (adaptation iterations only)
         seed = getattr(forward_kernel, "seed", None)
@@ -155,12 +164,33 @@ class SMCSampler:
         if self.adapt_iters and 1 <= k <= self.adapt_iters:
             self.accept_stat[k - 1] = float(self._acc_sum[k - 1].item()) / self.N
             eps = self.step_size_adapter.update(self.accept_stat[k - 1])
+            if k <= self.metric_iters:
+                self._adapt_metric()
+                # the step size that suited the old metric is rescaled by the geometric mean of the change and the dual
+                # averaging starts over from there
+                self.step_size_adapter = DualAveragingStepSize(eps * self._metric_rescale,
+                                                               self.step_size_adapter.target_accept)
+                eps = self.step_size_adapter.step_size
             if k == self.adapt_iters:
                 eps = self.step_size_adapter.averaged()
                 self.forward_kernel.want_accept_stat = False
             self.forward_kernel.step_size = eps
         if k < self.K:
             self.step_sizes[k] = self.forward_kernel.step_size
+
+    def _adapt_metric(self):
+        """scale_d = sqrt of the regularised weighted variance of unconstrained coordinate d over the current particle set
+        (Stan's shrinkage: n/(n+5) var + 1e-3 * 5/(n+5) with n = ESS)."""
+        s = self.samples
+        _, var = self._metric_estimator.return_estimate_unconstrained(s.x, s.wn)
+        var = var.cpu().numpy()
+        n = max(float(s.ess), 1.0)
+        var = np.where(np.isfinite(var) & (var > 0), var, 1.0)
+        new = np.sqrt(n / (n + 5.0) * var + 1e-3 * 5.0 / (n + 5.0))
+        old = self.target.metric_scale if self.target.metric_scale is not None else np.ones_like(new)
+        self._metric_rescale = float(np.exp(np.mean(np.log(old) - np.log(new))))
+        self.target.set_metric_scale(new)
+        self.metric_scale = new
 
     def iterate(self, k):
         """One SMC iteration, in the reference's order of operations (smc_sampler.py:109-140)."""
@@ -215,6 +245,8 @@ class SMCSampler:
 
         torch.cuda.synchronize()
         self.run_time = time() - self._start_time
+        if self.adapt_mass_matrix:      # the model object goes back to the identity metric; the adapted one is self.metric_scale
+            self.target.set_metric_scale(None)
         s.resampler.close()           # peer-mapped migration buffers (sharded runs)
         if hasattr(self.estimator, "resampler"):
             self.estimator.resampler.close()

@@ -59,6 +59,91 @@ def test_oracle_accept_stat_is_a_probability_and_falls_with_step_size():
     assert means[0] > means[1] > means[2] and means[0] > 0.97
 
 
+def test_oracle_diagonal_metric_is_nuts_on_the_rescaled_model():
+    """Diagonal metric = identity-metric NUTS on z = x / scale.  For the Gaussian the change of variables is another
+    Gaussian (precision S P S), so the oracle's metric path can be checked against its plain path on that model."""
+    D = 8
+    idx = np.arange(D)
+    P = np.linalg.inv(0.9 ** np.abs(idx[:, None] - idx[None, :]))
+    P = 0.5 * (P + P.T)
+    s = np.linspace(0.4, 2.5, D)
+    t = O.COracleTarget("gauss", precision=P)
+    tz = O.COracleTarget("gauss", precision=(s[:, None] * P) * s[None, :])
+    rng = np.random.default_rng(2)
+    x, r = rng.normal(size=(300, D)), rng.normal(size=(300, D))
+    a = t.nuts_batch(x, r, 0.1, 0.7, 8, seed=5, scale=s)
+    b = tz.nuts_batch(x / s, r, 0.1, 0.7, 8, seed=5)
+    same = a["n_leapfrog"] == b["n_leapfrog"]
+    assert same.mean() > 0.99                       # two roundings of the same trajectory
+    np.testing.assert_allclose(a["x_new"][same], b["x_new"][same] * s, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(a["lp_new"][same], b["lp_new"][same], rtol=1e-9, atol=1e-9)
+    ident = t.nuts_batch(x, r, 0.1, 0.7, 8, seed=5, scale=np.ones(D))
+    plain = t.nuts_batch(x, r, 0.1, 0.7, 8, seed=5)
+    assert np.array_equal(ident["x_new"], plain["x_new"]) and np.array_equal(ident["n_leapfrog"], plain["n_leapfrog"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,eps", [("arma", 0.02), ("PRMwCD", 0.01), ("gauss8", 0.1), ("gauss100", 0.1)])
+def test_kernel_diagonal_metric_matches_oracle(name, eps):
+    from smcnuts.distributions import StdNormal
+    from smcnuts.model.device_model import make_model
+    from smcnuts.proposal.nuts import NUTSProposal
+    if name.startswith("gauss"):
+        d = int(name[5:])
+        m, t = make_model("gauss", dim=d), O.COracleTarget("gauss", dim=d)
+    else:
+        m, t = make_model(name), O.COracleTarget(name)
+    rng = np.random.default_rng(4)
+    N, D = 2048, m.dim
+    x = rng.normal(size=(N, D)) * 0.1
+    if name == "arma":
+        x += np.array([0.0, 0.9, 0.0, -1.7])
+    r = rng.normal(size=(N, D))
+    s = np.exp(rng.uniform(-0.7, 0.7, size=D))
+    k = NUTSProposal(m, StdNormal(D), eps, rng=7, max_tree_depth=6)
+    plain, _ = k.rvs(x, r, 0.8)
+    m.set_metric_scale(s)
+    try:
+        k.iteration = 0
+        xn, rn = k.rvs(x, r, 0.8)
+        ref = t.nuts_batch(x, r, eps, 0.8, 6, seed=7, iteration=0, nthreads=4, scale=s)
+        same = k.last["n_leapfrog"].cpu().numpy() == ref["n_leapfrog"]
+        assert same.mean() > 0.97, same.mean()
+        np.testing.assert_allclose(xn[same], ref["x_new"][same], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(rn[same], ref["r_new"][same], rtol=1e-6, atol=1e-8)
+        # A / B by-products are the x-space split at the returned point
+        A, B = (v.cpu().numpy() for v in m.split(xn))
+        np.testing.assert_allclose(k.last["A_new"].cpu().numpy()[same], A[same], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(k.last["B_new"].cpu().numpy()[same], B[same], rtol=1e-9, atol=1e-7)
+    finally:
+        m.set_metric_scale(None)
+    k.iteration = 0
+    again, _ = k.rvs(x, r, 0.8)
+    assert np.array_equal(again, plain)            # identity metric restored: the reference path, bit for bit
+
+
+@pytest.mark.gpu
+def test_mass_matrix_adaptation_recovers_the_scales_of_an_anisotropic_gaussian():
+    from smcnuts.distributions import StdNormal
+    from smcnuts.model.device_model import make_model
+    from smcnuts.smc_sampler import SMCSampler
+    D = 16
+    sd = np.exp(np.linspace(-2.0, 1.0, D))                    # standard deviations from 0.14 to 2.7
+    m = make_model("gauss", precision=np.diag(1.0 / sd ** 2))
+    kw = dict(K=24, N=8192, target=m, sample_proposal=StdNormal(D), momentum_proposal=StdNormal(D),
+              lkernel="forwardsLKernel", tempering=False, rng=10)
+    s1 = SMCSampler(step_size=0.02, adapt_step_size=16, adapt_mass_matrix=True, **kw)
+    s1.sample(show_progress=False)
+    assert m.metric_scale is None                             # the model object is handed back with the identity metric
+    np.testing.assert_allclose(s1.metric_scale, sd, rtol=0.25)
+    np.testing.assert_allclose(np.sqrt(s1.variance_estimate[-1]), sd, rtol=0.35)   # importance-sampling estimate at N = 8192: noisy
+    s0 = SMCSampler(step_size=0.02, adapt_step_size=16, **kw)
+    s0.sample(show_progress=False)
+    # with the metric the step size is not held down by the narrowest coordinate: far fewer leapfrogs per transition
+    print('leapfrogs per iteration, last four: metric', s1.leapfrogs[20:], 'identity', s0.leapfrogs[20:], 'eps', s1.step_sizes[-1], s0.step_sizes[-1])
+    assert s1.leapfrogs[20:].mean() < 0.5 * s0.leapfrogs[20:].mean()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,eps", [("arma", 0.02), ("PRMwCD", 0.01), ("gauss100", 0.1)])
 def test_kernel_accept_stat_matches_oracle(name, eps):
