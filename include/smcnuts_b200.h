@@ -110,6 +110,11 @@ int smcb_reweight_forward(const double* logw, const double* lp_x, const double* 
 /* same, from the kinetic energies K2 already emitted (40 B/particle instead of 16D+24) */
 int smcb_reweight_forward_ke(const double* logw, const double* lp_x, const double* lp_xnew, const double* ke_old,
                              const double* ke_new, long long N, double* out, void* stream);
+/* the same from the split log densities emitted by smcb_nuts_transition: logp = A + phi*B (non-finite -> -inf) is formed in
+ * the kernel (samples.py:190-191 evaluates logp at phi = 1 regardless of tempering: pass phi = 1) */
+int smcb_reweight_forward_split(const double* logw, const double* A_old, const double* B_old, const double* A_new,
+                                const double* B_new, const double* ke_old, const double* ke_new, double phi, long long N,
+                                double* out, void* stream);
 /* samples.py:196 for any L-kernel: logw + lp_xnew - lp_x + L - q */
 int smcb_reweight_general(const double* logw, const double* lp_x, const double* lp_xnew, const double* L,
                           const double* q, long long N, double* out, void* stream);

@@ -214,6 +214,19 @@ __global__ void reweight_forward_ke_kernel(const double* __restrict__ logw, cons
         out[i] = logw[i] + lp_xnew[i] - lp_x[i] + (-ke_new[i]) - (-ke_old[i]);
 }
 
+// the same with logp(x) and logp(x_new) formed in place from the split densities the NUTS kernel emitted
+// (A + phi*B, non-finite -> -inf as smcb_combine_logp): one launch instead of three per SMC iteration
+__global__ void reweight_forward_split_kernel(const double* __restrict__ logw, const double* __restrict__ A_old,
+                                              const double* __restrict__ B_old, const double* __restrict__ A_new,
+                                              const double* __restrict__ B_new, const double* __restrict__ ke_old,
+                                              const double* __restrict__ ke_new, double phi, long long N,
+                                              double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double lp_x = map_lp(A_old[i] + phi * B_old[i]), lp_xnew = map_lp(A_new[i] + phi * B_new[i]);
+        out[i] = logw[i] + lp_xnew - lp_x + (-ke_new[i]) - (-ke_old[i]);
+    }
+}
+
 __global__ void reweight_general_kernel(const double* __restrict__ logw, const double* __restrict__ lp_x,
                                         const double* __restrict__ lp_xnew, const double* __restrict__ L,
                                         const double* __restrict__ q, long long N, double* __restrict__ out) {
@@ -819,6 +832,16 @@ int smcb_reweight_forward(const double* logw, const double* lp_x, const double* 
     reweight_forward_kernel<<<stride_grid(N, kRedThreads, 4), kRedThreads, smem, (cudaStream_t)stream>>>(
         logw, lp_x, lp_xnew, r, r_new, N, D, out);
     return check_launch("reweight_forward_kernel");
+}
+
+int smcb_reweight_forward_split(const double* logw, const double* A_old, const double* B_old, const double* A_new,
+                                const double* B_new, const double* ke_old, const double* ke_new, double phi, long long N,
+                                double* out, void* stream) {
+    SMCB_REQUIRE(logw && A_old && B_old && A_new && B_new && ke_old && ke_new && out && N >= 0, "bad argument");
+    if (N == 0) return 0;
+    reweight_forward_split_kernel<<<stride_grid(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(logw, A_old, B_old, A_new, B_new,
+                                                                                         ke_old, ke_new, phi, N, out);
+    return check_launch("reweight_forward_split_kernel");
 }
 
 int smcb_reweight_forward_ke(const double* logw, const double* lp_x, const double* lp_xnew, const double* ke_old,

@@ -39,6 +39,7 @@ _SIGS = {
     "smcb_affine": [_vp, _ll, _d, _d, _vp, _vp],
     "smcb_reweight_forward": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp],
     "smcb_reweight_forward_ke": [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp],
+    "smcb_reweight_forward_split": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _ll, _vp, _vp],
     "smcb_reweight_general": [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp],
     "smcb_reweight_asymptotic": [_vp, _vp, _vp, _d, _d, _ll, _vp, _vp],
     "smcb_lse_partial": [_vp, _ll, _vp, _vp, _vp],

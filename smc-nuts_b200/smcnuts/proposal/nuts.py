@@ -161,6 +161,14 @@ class NUTSProposal:
                    sl(o["ke_old"]), sl(o["ke_new"]), sl(o["n_leapfrog"]), sl(o["accepted"]), sl(o["depth"]),
                    sl(o.get("accept_stat")), sl(cA), sl(cB), sl(cg), sl(o.get("g_new")), dev.ptr(ws), ws.numel(), stream)
 
+    def prepare(self, N, D, want_grad=False):
+        """Allocate the next transition's outputs and scratch now.  The sampler calls this before its one host
+        synchronisation per iteration (the ESS read): the allocations (a dozen torch.empty calls) then do not sit
+        between that synchronisation and the kernel launch, where the GPU would idle through them."""
+        want_grad = want_grad and not self.accept_reject
+        self._prepared = ((N, D, want_grad, self.want_accept_stat), self._alloc_outputs(N, D, want_grad),
+                          dev.workspace("nuts", self._workspace_bytes(N)))
+
     def transition(self, x, r, phi=1.0, iteration=None, carry=None, want_grad=False):
         """Device entry point: returns dict of device tensors (x_new, r_new, A_old, B_old, A_new, B_new,
         ke_old, ke_new, n_leapfrog, accepted, depth[, g_new]).
@@ -169,7 +177,6 @@ class NUTSProposal:
         model evaluation of every transition; want_grad=True also returns g_new for the next call."""
         N, D = x.shape
         it = self.iteration if iteration is None else iteration
-        ws = dev.workspace("nuts", self._workspace_bytes(N))
         if self.accept_reject:
             carry, want_grad = None, False
         scale = getattr(self.target, "_scale_dev", None)
@@ -178,7 +185,11 @@ class NUTSProposal:
             z = dev.empty(N, D)
             _cabi.call("smcb_scale_rows", dev.ptr(x), N, D, dev.ptr(scale), 1, dev.ptr(z), dev.stream_ptr())
             x = z
-        o = self._alloc_outputs(N, D, want_grad)
+        prepared, self._prepared = getattr(self, "_prepared", None), None
+        if prepared is not None and prepared[0] == (N, D, want_grad, self.want_accept_stat):
+            o, ws = prepared[1], prepared[2]
+        else:
+            o, ws = self._alloc_outputs(N, D, want_grad), dev.workspace("nuts", self._workspace_bytes(N))
         if self.record_events:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

@@ -344,6 +344,10 @@ class Samples:
         the NUTS launch."""
         self._r_ready = (self.iteration, self._draw_std_normal(self.forward_kernel.momentum_proposal,
                                                                _cabi.STREAM_MOMENTUM, self.iteration))
+        if hasattr(self.forward_kernel, "prepare"):      # the transition's output buffers and scratch, for the same reason
+            can_carry = self.carry_gradients and self.TemperingScheme is None and \
+                not getattr(self.forward_kernel, "accept_reject", False)
+            self.forward_kernel.prepare(self.n_local, self.D, want_grad=can_carry)
 
     def propose_samples(self):
         """samples.py:149-158."""
@@ -384,15 +388,16 @@ class Samples:
     def _non_asympototic_reweight(self):
         """samples.py:183-196: logp at phi = 1 regardless of tempering."""
         st, n = dev.stream_ptr(), self.n_local
-        lp_x = self.target.combine(*self._split_x, 1.0)
-        lp_xnew = self.target.combine(*self._split_new, 1.0)
         out = dev.empty(n)
         fused = isinstance(self.lkernel, ForwardLKernel) and self._ke is not None and \
             dev.is_std_normal(self.forward_kernel.momentum_proposal, self.D)
-        if fused:  # L(r_new) - q(r) = -ke_new + ke_old, both emitted by the NUTS kernel
-            _cabi.call("smcb_reweight_forward_ke", dev.ptr(self.logw), dev.ptr(lp_x), dev.ptr(lp_xnew),
-                       dev.ptr(self._ke[0]), dev.ptr(self._ke[1]), n, dev.ptr(out), st)
+        if fused:  # L(r_new) - q(r) = -ke_new + ke_old, both emitted by the NUTS kernel; logp(., 1) from its split densities
+            _cabi.call("smcb_reweight_forward_split", dev.ptr(self.logw), dev.ptr(self._split_x[0]), dev.ptr(self._split_x[1]),
+                       dev.ptr(self._split_new[0]), dev.ptr(self._split_new[1]), dev.ptr(self._ke[0]), dev.ptr(self._ke[1]),
+                       1.0, n, dev.ptr(out), st)
             return out
+        lp_x = self.target.combine(*self._split_x, 1.0)
+        lp_xnew = self.target.combine(*self._split_new, 1.0)
         L = dev.to_device(self.lkernel.calculate_L(self.r_new, self.x_new))
         q = dev.to_device(self.forward_kernel.logpdf(self.r))
         _cabi.call("smcb_reweight_general", dev.ptr(self.logw), dev.ptr(lp_x), dev.ptr(lp_xnew), dev.ptr(L), dev.ptr(q),
