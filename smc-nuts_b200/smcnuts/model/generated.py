@@ -8,8 +8,10 @@ the library with smcb_model_create_plugin.  The result has the reference's targe
 No CPU fallback: without nvcc or a GPU the constructor raises.
 """
 import ctypes
+import os
 import shutil
 import subprocess
+import tempfile
 from pathlib import Path
 
 import numpy as np
@@ -25,26 +27,47 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 _KIND_CODE = {"none": 0.0, "lower": 1.0, "upper": 2.0, "both": 3.0}
 
 
+def _csrc_digest():
+    """Hash of the kernel headers a plug-in is compiled against: a cached plug-in built against other headers (another
+    NutsArgs layout, say) must never be loaded."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in sorted(p.name for p in CSRC.glob("*.cuh")):
+        h.update((CSRC / name).read_bytes())
+    return h.hexdigest()[:8]
+
+
 def build_plugin(src: stan_codegen.GeneratedSource, force=False, parity=False):
-    """Write and compile the plug-in of a generated model; returns the path of the shared object (cached by digest)."""
-    out_dir = GEN_DIR / (src.digest + ("_parity" if parity else ""))
+    """Write and compile the plug-in of a generated model; returns the path of the shared object (cached by the digests of
+    the generated text + data and of the kernel headers)."""
+    out_dir = GEN_DIR / (f"{src.digest}_{_csrc_digest()}" + ("_parity" if parity else ""))
     so = out_dir / "model.so"
     if so.exists() and not force:
         return so
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not Path(nvcc).exists():
         raise _cabi.SmcbError("nvcc not found: generated models are compiled at run time (no CPU fallback exists)")
-    out_dir.mkdir(parents=True, exist_ok=True)
-    (out_dir / "model_gen.cuh").write_text(src.text)
-    (out_dir / "plugin.cu").write_text(
-        "// GENERATED: plug-in translation unit of a Stan-subset model (smcnuts/model/generated.py)\n"
-        "#define SMCB_PLUGIN_TU 1\n#include \"nuts_plugin.cuh\"\n#include \"model_gen.cuh\"\n"
-        f"SMCB_DEFINE_PLUGIN({src.struct_name})\n")
-    flags = NVCC_FLAGS + (["-DSMCB_PARITY=1", "-fmad=false"] if parity else [])
-    cmd = [nvcc, *flags, f"-I{CSRC}", f"-I{out_dir}", str(out_dir / "plugin.cu"), "-o", str(so)]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise _cabi.SmcbError(f"nvcc failed for the generated model:\n{r.stdout}\n{r.stderr}")
+    # built in a private directory and moved into place in one step: several ranks of a sharded run (or several
+    # processes) may generate the same model at the same time
+    GEN_DIR.mkdir(parents=True, exist_ok=True)
+    work = Path(tempfile.mkdtemp(prefix=out_dir.name + ".", dir=GEN_DIR))
+    try:
+        (work / "model_gen.cuh").write_text(src.text)
+        (work / "plugin.cu").write_text(
+            "// GENERATED: plug-in translation unit of a Stan-subset model (smcnuts/model/generated.py)\n"
+            "#define SMCB_PLUGIN_TU 1\n#include \"nuts_plugin.cuh\"\n#include \"model_gen.cuh\"\n"
+            f"SMCB_DEFINE_PLUGIN({src.struct_name})\n")
+        flags = NVCC_FLAGS + (["-DSMCB_PARITY=1", "-fmad=false"] if parity else [])
+        cmd = [nvcc, *flags, f"-I{CSRC}", f"-I{work}", str(work / "plugin.cu"), "-o", str(work / "model.so")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise _cabi.SmcbError(f"nvcc failed for the generated model:\n{r.stdout}\n{r.stderr}")
+        out_dir.mkdir(parents=True, exist_ok=True)
+        for name in ("model_gen.cuh", "plugin.cu"):
+            os.replace(work / name, out_dir / name)
+        os.replace(work / "model.so", so)          # last: its presence marks the directory as complete
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
     return so
 
 
