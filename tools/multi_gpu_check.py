@@ -17,13 +17,19 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "smc-nuts_b200"))
 
 
-def run(model, kw, N, K, eps, lk, temp, resampling):
+def run(model, kw, N, K, eps, lk, temp, resampling, extra=None):
     from smcnuts.distributions import StdNormal
     from smcnuts.model.device_model import make_model
     from smcnuts.smc_sampler import SMCSampler
-    m = make_model(model, **kw)
+    if model == "generated":     # a Stan-subset program compiled into a model plug-in (every rank builds / loads the same one)
+        import json
+        from smcnuts.model.generated import GeneratedModel
+        y = json.loads((ROOT / "smc-nuts_b200/smcnuts/data/arma/arma.json").read_text())["y"]
+        m = GeneratedModel((ROOT / "tests/stan/arma11.stan").read_text(), {"T": 200, "y": y}, "arma11")
+    else:
+        m = make_model(model, **kw)
     s = SMCSampler(K=K, N=N, target=m, step_size=eps, sample_proposal=StdNormal(m.dim), momentum_proposal=StdNormal(m.dim),
-                   lkernel=lk, tempering=temp, rng=10, resampling=resampling)
+                   lkernel=lk, tempering=temp, rng=10, resampling=resampling, **(extra or {}))
     s.sample(show_progress=False)
     return s
 
@@ -35,7 +41,11 @@ def main():
              ("arma", {}, 1 << 14, 6, 0.01, "forwardsLKernel", False, "systematic"),
              ("arma", {}, 1 << 13, 5, 0.01, "asymptoticLKernel", True, "systematic"),
              ("arma", {}, 1 << 13, 5, 0.01, "asymptoticLKernel", True, "multinomial"),
-             ("gauss", {"dim": 8}, 1 << 13, 4, 0.1, "GaussianApproxLKernel", False, "systematic")]
+             ("gauss", {"dim": 8}, 1 << 13, 4, 0.1, "GaussianApproxLKernel", False, "systematic"),
+             # generated model plug-in; step-size + diagonal mass-matrix adaptation (statistics all-reduced over the shards)
+             ("generated", {}, 1 << 13, 5, 0.01, "forwardsLKernel", False, "multinomial"),
+             ("gauss", {"dim": 8}, 1 << 13, 8, 0.02, "forwardsLKernel", False, "multinomial",
+              {"adapt_step_size": 6, "adapt_mass_matrix": True})]
     # single-GPU references first (no process group yet -> ShardContext is a no-op)
     refs = [run(*c) for c in cases] if rank == 0 else None
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -58,6 +68,9 @@ def main():
             np.testing.assert_allclose(s.variance_estimate, r.variance_estimate, rtol=1e-7, atol=1e-12)
             np.testing.assert_allclose(s.acceptance_rate, r.acceptance_rate, rtol=1e-12)
             assert list(s.resampled) == list(r.resampled)
+            np.testing.assert_allclose(s.step_sizes, r.step_sizes, rtol=1e-9)
+            if r.metric_scale is not None:
+                np.testing.assert_allclose(s.metric_scale, r.metric_scale, rtol=1e-9)
             np.testing.assert_allclose(x_all, r.samples.x.cpu().numpy(), rtol=1e-9, atol=1e-12)
             print(f"case {ci} {c[0]} {c[5]} {c[7]}: ok (resampled {sum(s.resampled)}x, rows migrated in last resample: "
                   f"{int(migrated.item())}, shard {n_local})", flush=True)
