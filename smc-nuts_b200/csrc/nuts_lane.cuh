@@ -425,6 +425,24 @@ struct Lane {
 #define SMCB_NUTS_EARLY_LOADS 1
 #endif
     static constexpr bool kEarly = (SMCB_NUTS_EARLY_LOADS != 0) && DM <= 4;
+    // ... and the level-0 checkpoint (the operand of half of all U-turn tests: the first leaf of the two-leaf sub-tree the
+    // next leaf completes) is known BEFORE the model evaluation: its 2*DM doubles are loaded then and ride through the
+    // evaluation in registers, so that test never waits on memory.  MEASURED (B200, same call): arma N = 2^16 0.602 ->
+    // 0.553 ms, 2^17 0.717 -> 0.673 ms, 2^20 2.910 -> 2.864 ms (the gain is latency: it grows as the shard shrinks); the
+    // 4-lane PRMwCD kernel loses 2 % (124 registers of its 128), so one-lane models only.
+#ifndef SMCB_NUTS_PREFETCH_CK
+#define SMCB_NUTS_PREFETCH_CK 1
+#endif
+    static constexpr bool kPrefetchCk = (SMCB_NUTS_PREFETCH_CK != 0) && kEarly && G == 1;
+    double pxc[kPrefetchCk ? DM : 1], prc[kPrefetchCk ? DM : 1];
+    SMCB_HD void prefetch_ck() {
+        if constexpr (kPrefetchCk) {
+            if (phase == kLeaf && depth > 0 && (leaf & 1u)) {   // the coming leaf has an odd 0-based index: a level-0 merge follows it
+                const double* ck = slotp(get_ck(popc32(leaf - 1u)));
+                ldv(ck, pxc); ldv(ck + nlp, prc);
+            }
+        }
+    }
 
     // rows of the caller's [N, D] arrays: 16-byte accesses when the row layout allows it
     SMCB_HD void write_row(double* base, const double (&v)[DM]) const {
@@ -558,7 +576,16 @@ struct Lane {
                 for (int l = 0; l < tz; ++l) {  // nuts.py:136-148, second child = running node
                     const double* ck = slotp(get_ck(popc32(i0 - (2u << l) + 1u)));
                     double xc[kEarly ? DM : 1], rc[kEarly ? DM : 1];
-                    if constexpr (kEarly) { ldv(ck, xc); ldv(ck + nlp, rc); }
+                    if constexpr (kPrefetchCk) {
+                        if (l == 0) {   // loaded before the evaluation (prefetch_ck)
+#pragma unroll
+                            SMCB_LOCAL(i) { xc[i] = pxc[i]; rc[i] = prc[i]; }
+                        } else {
+                            ldv(ck, xc); ldv(ck + nlp, rc);
+                        }
+                    } else if constexpr (kEarly) {
+                        ldv(ck, xc); ldv(ck + nlp, rc);
+                    }
                     if constexpr (kStage) { if (l > 0) stage_issue(ck); }   // l == 0: staged when the previous leaf was stored
                     const uint32_t n1 = get_n(l);
                     const int ref1 = get_ref(l);

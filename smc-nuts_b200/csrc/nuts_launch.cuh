@@ -151,7 +151,7 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
         }
         // ---- one model evaluation per particle per trip: the initial point or one leapfrog.  The evaluation is
         //      executed by every lane (idle ones carry zeros) so that warp-wide tensor-core instructions stay legal.
-        if (lane.phase != kIdle) lane.pre_eval(a);
+        if (lane.phase != kIdle) { lane.pre_eval(a); lane.prefetch_ck(); }
         double A, B, g[M::NLOC];
         if constexpr (G > 1) __syncwarp();   // the group models issue warp-wide mma.sync.aligned: reconverge explicitly
         model.eval(lane.xa, a.phi, A, B, g);
@@ -189,7 +189,7 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
                 }
             }
             if (__all_sync(0xffffffffu, lane.phase == kIdle)) continue;   // an emptied warp only keeps the barriers
-            if (lane.phase != kIdle) lane.pre_eval(a);
+            if (lane.phase != kIdle) { lane.pre_eval(a); lane.prefetch_ck(); }
             double A, B, g[M::NLOC];
             if constexpr (G > 1) __syncwarp();
             model.eval(lane.xa, a.phi, A, B, g);

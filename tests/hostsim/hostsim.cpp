@@ -26,6 +26,7 @@ static void run(NutsArgs a, int lanes) {
             if (l.phase == kIdle) continue;
             any = true;
             l.pre_eval(a);
+            l.prefetch_ck();
             double A, B, g[M::NLOC];
             model.eval(l.xa, a.phi, A, B, g);
             l.take_grad(g);

@@ -45,7 +45,7 @@ static void run_warp_kernel(NutsArgs a, const double* staged) {
                 }
             }
             if (__all_sync(0xffffffffu, lane.phase == kIdle)) break;
-            if (lane.phase != kIdle) lane.pre_eval(a);
+            if (lane.phase != kIdle) { lane.pre_eval(a); lane.prefetch_ck(); }
             double A, B, g[M::NLOC];
             model.eval(lane.xa, a.phi, A, B, g);
             lane.take_grad(g);

@@ -234,6 +234,18 @@ def test_generated_model_runs_the_nuts_and_smc_kernels_like_the_builtin_one():
     np.testing.assert_allclose(xg[same], xr[same], rtol=1e-6, atol=1e-8)
     assert gen.constrain_kind == ref.constrain_kind
     np.testing.assert_allclose(gen.constrain(x), ref.constrain(x), rtol=1e-15)
+    # the diagonal metric goes through the plug-in as well (ScaledModel instantiated in its translation unit)
+    sc = np.array([0.5, 2.0, 1.5, 0.7])
+    gen.set_metric_scale(sc); ref.set_metric_scale(sc)
+    try:
+        kg.iteration = kr.iteration = 0
+        xg2, _ = kg.rvs(x, r, 1.0)
+        xr2, _ = kr.rvs(x, r, 1.0)
+        same2 = (kg.last["n_leapfrog"] == kr.last["n_leapfrog"]).cpu().numpy()
+        assert same2.mean() > 0.99 and not np.array_equal(xr2, xr)
+        np.testing.assert_allclose(xg2[same2], xr2[same2], rtol=1e-6, atol=1e-8)
+    finally:
+        gen.set_metric_scale(None); ref.set_metric_scale(None)
     # whole SMC run through the reference-facing constructor, model resolved by StanModel(name, model_path, data_path)
     data_path = ROOT / "smc-nuts_b200/smcnuts/data/arma/arma.json"
     sm = StanModel("arma11", str(STAN / "arma11.stan"), str(data_path))
