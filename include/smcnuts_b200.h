@@ -221,6 +221,14 @@ int smcb_constrain_rows(const double* x, long long N, int D, const double* table
 /* out[d] = sum_i wn_i * (c(x_i)_d - center_d)^power ; center may be NULL (0), power in {1, 2} */
 int smcb_weighted_moment(const double* x, const double* wn, long long N, int D, int constrain, const double* center,
                          int power, double* out, void* workspace, void* stream);
+/* Both moments in one pass about a caller-supplied centre c (device, D doubles; NULL = 0):
+ *   out2D[d] = sum_i wn_i (c(x_i)_d - c_d),  out2D[D + d] = sum_i wn_i (c(x_i)_d - c_d)^2      (D <= 128)
+ * smcb_moments12_finalize turns the (all-reduced) sums into mean = c + m1 and var = m2 - m1^2 (estimate.py:91-93: the
+ * same estimates; with c = the previous iteration's mean the subtraction loses nothing).  One read of x and wn and one
+ * collective per SMC iteration instead of two. */
+int smcb_weighted_moments12(const double* x, const double* wn, long long N, int D, int constrain, const double* center,
+                            double* out2D, void* workspace, void* stream);
+int smcb_moments12_finalize(const double* sums2D, const double* center, int D, double* mean, double* var, void* stream);
 /* smc_sampler.py:97: number of rows with ALL coordinates changed -> out_count[0] (double) */
 int smcb_count_moved(const double* x, const double* x_new, long long N, int D, double* out_count, void* workspace,
                      void* stream);

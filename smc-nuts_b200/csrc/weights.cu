@@ -549,6 +549,81 @@ __global__ void __launch_bounds__(kRedThreads) weighted_moment_kernel(const doub
     }
 }
 
+// One pass for both moments about a caller-supplied centre c (the previous iteration's mean: close to this one's, so
+// the second central moment m2 - m1^2 loses nothing to cancellation):
+//   out[d] = sum_i wn_i (c(x_i)_d - c_d),  out[D + d] = sum_i wn_i (c(x_i)_d - c_d)^2.
+// Reads x and wn once instead of twice, and a sharded run all-reduces the 2D sums in ONE collective instead of two
+// (estimate.py:91-93 computes the mean first and then the variance about it).  Same thread mapping as above.
+__global__ void __launch_bounds__(kRedThreads) weighted_moments12_kernel(const double* __restrict__ x,
+                                                                          const double* __restrict__ wn, long long N,
+                                                                          int D, int constrain,
+                                                                          const double* __restrict__ center, double* out,
+                                                                          double* ws, int threads_used) {
+    __shared__ double sh[2 * kRedThreads];
+    __shared__ bool is_last;
+    const long long total = N * D;
+    const long long gstride = (long long)gridDim.x * threads_used;
+    double a1 = 0.0, a2 = 0.0;
+    const int col = threadIdx.x % D;
+    if ((int)threadIdx.x < threads_used) {
+        const double cen = center ? center[col] : 0.0;
+        const bool do_exp = (constrain == SMCB_CONSTRAIN_EXP_LAST) && (col == D - 1);
+        long long row = (long long)blockIdx.x * (threads_used / D) + (int)threadIdx.x / D;
+        const long long rstride = gstride / D;
+        for (long long e = (long long)blockIdx.x * threads_used + threadIdx.x; e < total; e += gstride, row += rstride) {
+            double v = x[e];
+            if (do_exp) v = fast_exp(v);
+            v -= cen;
+            const double w = wn[row];
+            a1 += w * v;
+            a2 += w * (v * v);
+        }
+    }
+    sh[threadIdx.x] = a1; sh[kRedThreads + threadIdx.x] = a2;
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * D) {
+        const int c = threadIdx.x % D, which = threadIdx.x / D;
+        double s = 0.0;
+        for (int t = c; t < threads_used; t += D) s += sh[which * kRedThreads + t];
+        ws[(size_t)blockIdx.x * kRedMaxVals + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    unsigned* counter = (unsigned*)(ws + (size_t)kRedMaxBlocks * kRedMaxVals);
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double b1 = 0.0, b2 = 0.0;
+        if ((int)threadIdx.x < threads_used)
+            for (unsigned b = threadIdx.x / D; b < gridDim.x; b += threads_used / D) {
+                b1 += ((const volatile double*)ws)[(size_t)b * kRedMaxVals + col];
+                b2 += ((const volatile double*)ws)[(size_t)b * kRedMaxVals + D + col];
+            }
+        __syncthreads();
+        sh[threadIdx.x] = b1; sh[kRedThreads + threadIdx.x] = b2;
+        __syncthreads();
+        if ((int)threadIdx.x < 2 * D) {
+            const int c = threadIdx.x % D, which = threadIdx.x / D;
+            double s = 0.0;
+            for (int t = c; t < threads_used; t += D) s += sh[which * kRedThreads + t];
+            out[threadIdx.x] = s;
+        }
+        if (threadIdx.x == 0) *counter = 0;
+    }
+}
+
+// mean = c + m1, var = m2 - m1^2 from the (all-reduced) sums of the kernel above
+__global__ void moments12_finalize_kernel(const double* __restrict__ sums, const double* __restrict__ center, int D,
+                                          double* __restrict__ mean, double* __restrict__ var) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) {
+        const double m1 = sums[d], m2 = sums[D + d];
+        mean[d] = (center ? center[d] : 0.0) + m1;
+        var[d] = m2 - m1 * m1;
+    }
+}
+
 __global__ void __launch_bounds__(kRedThreads) count_moved_kernel(const double* __restrict__ x,
                                                                    const double* __restrict__ xn, long long N, int D,
                                                                    double* out, double* ws) {
@@ -969,6 +1044,24 @@ int smcb_constrain_rows(const double* x, long long N, int D, const double* table
     if (N == 0) return 0;
     constrain_rows_kernel<<<stride_grid(N * D, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, N * D, D, table, out);
     return check_launch("constrain_rows_kernel");
+}
+
+int smcb_weighted_moments12(const double* x, const double* wn, long long N, int D, int constrain, const double* center,
+                            double* out2D, void* workspace, void* stream) {
+    SMCB_REQUIRE(x && wn && out2D && workspace && N >= 0, "bad argument");
+    SMCB_REQUIRE(D >= 1 && 2 * D <= kRedThreads, "1 <= D <= 128");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (reset_counter(workspace, st)) return -1;
+    const int used = (kRedThreads / D) * D;
+    weighted_moments12_kernel<<<stride_grid(N * D, kRedThreads * 4, 4), kRedThreads, 0, st>>>(x, wn, N, D, constrain, center,
+                                                                                           out2D, (double*)workspace, used);
+    return check_launch("weighted_moments12_kernel");
+}
+
+int smcb_moments12_finalize(const double* sums2D, const double* center, int D, double* mean, double* var, void* stream) {
+    SMCB_REQUIRE(sums2D && mean && var && D >= 1, "bad argument");
+    moments12_finalize_kernel<<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums2D, center, D, mean, var);
+    return check_launch("moments12_finalize_kernel");
 }
 
 int smcb_count_moved(const double* x, const double* x_new, long long N, int D, double* out_count, void* workspace,

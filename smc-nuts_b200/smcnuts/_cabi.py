@@ -70,6 +70,8 @@ _SIGS = {
     "smcb_peer_free": [_vp],
     "smcb_gather_rows": [_vp, _vp, _ll, _i, _vp, _vp],
     "smcb_weighted_moment": [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _vp, _vp],
+    "smcb_weighted_moments12": [_vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp],
+    "smcb_moments12_finalize": [_vp, _vp, _i, _vp, _vp, _vp],
     "smcb_count_moved": [_vp, _vp, _ll, _i, _vp, _vp, _vp],
     "smcb_gaussL_sums": [_vp, _vp, _ll, _i, _vp, _vp],
     "smcb_gaussL_gram": [_vp, _vp, _ll, _i, _vp, _vp, _vp],

@@ -17,8 +17,22 @@ class Estimate:
         else:
             self._constrain = _cabi.CONSTRAIN_NONE
 
-    def return_estimate(self, x, wn):
+    def return_estimate(self, x, wn, center=None):
+        """center (device tensor [D], optional): a point near the mean, e.g. the previous iteration's estimate -- the two
+        moments then come from ONE pass over the particles and one collective (same estimates to rounding)."""
+        if center is not None and self._constrain != _cabi.CONSTRAIN_TABLE and 2 * x.shape[1] <= 256 and not dev.is_host(x):
+            return self._estimate_one_pass(x, wn, self._constrain, center)
         return self._estimate(x, wn, self._constrain)
+
+    def _estimate_one_pass(self, x, wn, constrain, center):
+        N, D = x.shape
+        sums, mean, var = dev.empty(2 * D), dev.empty(D), dev.empty(D)
+        st = dev.stream_ptr()
+        _cabi.call("smcb_weighted_moments12", dev.ptr(x), dev.ptr(wn), N, D, constrain, dev.ptr(center), dev.ptr(sums),
+                   dev.ptr(dev.reduce_ws()), st)
+        self.shard.all_reduce_sum_(sums)
+        _cabi.call("smcb_moments12_finalize", dev.ptr(sums), dev.ptr(center), D, dev.ptr(mean), dev.ptr(var), st)
+        return mean, var
 
     def return_estimate_unconstrained(self, x, wn):
         return self._estimate(x, wn, _cabi.CONSTRAIN_NONE)

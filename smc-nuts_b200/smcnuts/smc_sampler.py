@@ -197,7 +197,11 @@ class SMCSampler:
         s = self.samples
         self.phi[k] = s.phi_new
         s.normalise_weights()
-        mean_estimate, variance_estimate = self.estimator.return_estimate(s.x, s.wn)
+        if isinstance(self.estimator, Estimate):  # both moments in one pass about the previous iteration's mean
+            mean_estimate, variance_estimate = self.estimator.return_estimate(
+                s.x, s.wn, center=self._mean_dev[k - 1] if k > 0 else self._mean_dev[self.K])
+        else:
+            mean_estimate, variance_estimate = self.estimator.return_estimate(s.x, s.wn)
         s.prefetch_momentum()         # queued before the one host synchronisation of the iteration (ESS, below)
         s.calculate_ess()
         self._adapt_step_size(k)      # after the host synchronisation above: the previous iteration's statistic is ready

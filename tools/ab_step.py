@@ -21,7 +21,8 @@ from smcnuts.smc_sampler import SMCSampler  # noqa: E402
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 m = make_model("arma")
-new_prepare, new_reweight = NUTSProposal.prepare, Samples._non_asympototic_reweight
+from smcnuts.estimate.estimate import Estimate  # noqa: E402
+new_prepare, new_reweight, new_estimate = NUTSProposal.prepare, Samples._non_asympototic_reweight, Estimate.return_estimate
 
 
 def old_reweight(self):
@@ -34,10 +35,12 @@ def old_reweight(self):
     return out
 
 
-for tag, prep, rew in (("old", False, False), ("prepare", True, False), ("prepare + fused reweight", True, True), ("old", False, False),
-                       ("prepare + fused reweight", True, True)):
+for tag, prep, rew, est in (("old", False, False, False), ("prepare + fused reweight", True, True, False),
+                            ("+ one-pass moments", True, True, True), ("old", False, False, False),
+                            ("prepare + fused reweight", True, True, False), ("+ one-pass moments", True, True, True)):
     NUTSProposal.prepare = new_prepare if prep else (lambda self, N, D, want_grad=False: None)
     Samples._non_asympototic_reweight = new_reweight if rew else old_reweight
+    Estimate.return_estimate = new_estimate if est else (lambda self, x, wn, center=None: self._estimate(x, wn, self._constrain))
     s = SMCSampler(K=K, N=1 << lg, target=m, step_size=0.01, sample_proposal=StdNormal(4), momentum_proposal=StdNormal(4),
                    lkernel="forwardsLKernel", tempering=False, rng=10, save_history=False)
     s.reweight_strategy = None
