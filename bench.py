@@ -52,8 +52,8 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the NUTS kernel, from `ncu --set full` captures under
 # profiles/ (keyed by workload and particles per GPU); not measured live -> "traffic_live": false in the line
 TRAFFIC = {
-    ("arma", 1 << 20): (502095616, "ncu --set full capture of round 2 (profiles/r2_nuts_arma_details.csv, tools/r2_batch22.sh): 121.8 MB read "
-                                    "+ 380.3 MB written (algorithmic: 222 MB of particle rows and scalars; the rest is the per-lane tree "
+    ("arma", 1 << 20): (514807552, "ncu --set full capture of round 2 (profiles/r2_nuts_arma_details.csv, tools/r2_final.sh): 125.0 MB read "
+                                    "+ 389.8 MB written (algorithmic: 222 MB of particle rows and scalars; the rest is the per-lane tree "
                                     "workspace leaving L2)"),
     ("gauss", 1 << 18): (16656124000, "ncu --set full capture of round 2 (profiles/r2_nuts_gauss100_details.csv): 3.29 GB read + 13.36 GB "
                                        "written at N = 2^18 (algorithmic 0.84 GB: the 10 KB per-lane tree records do not fit in L2)"),
