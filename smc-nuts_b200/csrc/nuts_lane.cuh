@@ -161,10 +161,11 @@ struct Lane {
     // through it evicted the kernel's register spills, whose reloads then showed up as long-scoreboard stalls on the
     // bookkeeping scalars (ncu, round 2).  MEASURED (B200, D = 100): 78.6 -> 71.4 ms at N = 2^20, 20.5 -> 18.7 ms at 2^18.
     // Not for the one-lane models: their ~1 KB records DO live in L1 (PRMwCD one-lane kernel, 6000 particles: 6x slower).
-    // OPEN: with these accesses AND tail compaction (nuts_launch.cuh) the one-lane PRMwCD kernel did not terminate
-    // (tools/dbg_prm_scalar.py, gpurun_out/r2u); either alone is fine, and so was a build of the combination with two
-    // extra trip-count guards in the loops -- codegen-sensitive, cause not found.  The two are never combined: the staged
-    // models have no tail mode.
+    // (With these accesses AND tail compaction the one-lane PRMwCD kernel did not terminate: a lane state that moves to
+    // another warp is followed by L2-only loads of its record, and without a __threadfence() in front of the exchange
+    // barrier those could overtake the previous owner's L2-only stores.  The fence is there now -- nuts_launch.cuh --,
+    // found by bisecting debug builds on the GPU, gpurun_out/r2ak; with ordinary L1-cached accesses the same-SM L1 keeps
+    // the two coherent.  The staged models have no tail mode anyway.)
 #ifndef SMCB_WIDE_RECORDS_CG
 #define SMCB_WIDE_RECORDS_CG 1
 #endif

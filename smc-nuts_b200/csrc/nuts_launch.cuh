@@ -179,6 +179,9 @@ nuts_transition_kernel(NutsArgs a, int staged, int stage_offset, int rec_doubles
             if (total == 0) break;
             if (have > (total + kPerWarp - 1) / kPerWarp) {   // CTA-uniform: packing frees at least one warp
                 if (act) exch[(before + __popc(b & ((1u << group_first) - 1u))) * G + lane.sub] = lane;
+                // the new owner reads the lane's workspace record next: everything the old owner stored there (and the
+                // state above) is made visible device-wide before the barrier, whatever cache operators the accesses use
+                __threadfence();
                 __syncthreads();
                 if ((int)threadIdx.x < total * G) {
                     double* const stg = lane.stg;
