@@ -517,3 +517,36 @@ def test_resampler_end_to_end_against_oracle():
         idx = rs.last_idx.cpu().numpy()
         assert (idx != want_idx).mean() <= 1e-4
         assert np.array_equal(got, x[idx])
+
+
+@pytest.mark.parametrize("name", ["arma", "PRMwCD_scalar", "gauss8"])
+def test_nuts_ragged_sizes_and_occupancy_caps_agree_with_oracle(name, monkeypatch):
+    """Tail compaction, the work queue and the launch-shape knobs are pure scheduling: for awkward particle counts (fewer
+    particles than a warp, one more than a CTA, ...) and for every cap on resident CTAs per SM the trees are the oracle's."""
+    if name == "PRMwCD_scalar":
+        monkeypatch.setenv("SMCB_PRM_SCALAR", "1")
+    m, t = _models(name.split("_")[0])
+    eps = {"arma": 0.02, "PRMwCD_scalar": 0.01, "gauss8": 0.1}[name]
+    rng = np.random.default_rng(17)
+    D = m.dim
+    for N in (1, 2, 31, 33, 127, 129, 1000, 4097):
+        x = rng.normal(size=(N, D)) * 0.1
+        if name == "arma":
+            x += np.array([0.0, 0.9, 0.0, -1.7])
+        r = rng.normal(size=(N, D))
+        ref = t.nuts_batch(x, r, eps, 1.0, 6, seed=5, iteration=3, nthreads=4)
+        for cap in (0, 1, 3):
+            _cabi.call("smcb_nuts_set_blocks_per_sm", cap)
+            try:
+                k = NUTSProposal(m, StdNormal(D), eps, rng=5, max_tree_depth=6)
+                o = k.transition(dev.to_device(x), dev.to_device(r), 1.0, iteration=3)
+            finally:
+                _cabi.call("smcb_nuts_set_blocks_per_sm", 0)
+            nl = o["n_leapfrog"].cpu().numpy()
+            same = nl == ref["n_leapfrog"]
+            assert same.mean() >= (0.97 if N >= 100 else 0.9), (name, N, cap, same.mean())
+            np.testing.assert_allclose(o["x_new"].cpu().numpy()[same], ref["x_new"][same], rtol=1e-6, atol=1e-8)
+            if cap:
+                assert np.array_equal(nl, first) and np.array_equal(o["x_new"].cpu().numpy(), first_x)   # bit-identical across caps
+            else:
+                first, first_x = nl, o["x_new"].cpu().numpy()
