@@ -620,7 +620,8 @@ __global__ void moments12_finalize_kernel(const double* __restrict__ sums, const
     if (d < D) {
         const double m1 = sums[d], m2 = sums[D + d];
         mean[d] = (center ? center[d] : 0.0) + m1;
-        var[d] = m2 - m1 * m1;
+        const double v = m2 - m1 * m1;
+        var[d] = (v < 0.0) ? 0.0 : v;   // a sum of non-negative terms in the two-pass form: never negative there (NaN passes)
     }
 }
 
