@@ -113,7 +113,7 @@ class ClockSampler(threading.Thread):
                         self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.1 if self.nvml is not None else 0.2)
+            self._stop_evt.wait(float(os.environ.get("SMCB_BENCH_CLOCK_INTERVAL", 0.1 if self.nvml is not None else 0.2)))
 
     def stop(self):
         self._stop_evt.set()
@@ -423,16 +423,26 @@ def main():
     r_host.copy_(StdNormal(D, seed=11).rvs(n_local, iteration=0, particle0=rank * n_local))
     phi = float(smc.samples.phi_new)
     e2e_lf = 0
-    for _ in range(3):
+    # warm-up of the host path, result read included: the first call allocates the pinned staging buffers and side
+    # streams (99 ms), and the first int32 reduction of the step's result loads its kernel lazily (12-21 ms) -- measured
+    # per call with SMCB_BENCH_DEBUG=1; W device-resident steps warm neither
+    e2e_warmup = max(W, 15)
+    for _ in range(e2e_warmup):
         fk.rvs(x_host, r_host, phi)
+        int(fk.last["n_leapfrog"].sum().item())   # the result read is part of a step: its reduction kernel is loaded lazily on first use
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
     t0.record()
+    per_call = []
     for _ in range(K):
+        c0 = time.perf_counter()
         xn, rn = fk.rvs(x_host, r_host, phi)
         e2e_lf += int(fk.last["n_leapfrog"].sum().item())       # D2H read of the step's result
+        per_call.append((time.perf_counter() - c0) * 1e3)
     t1.record()
+    if os.environ.get("SMCB_BENCH_DEBUG"):
+        print("e2e per-call ms:", [round(t, 2) for t in per_call], file=sys.stderr)
     barrier()
     e2e_dt = max(t0.elapsed_time(t1) * 1e-3, time.perf_counter() - wall0 if world == 1 else 0.0)
     te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
@@ -483,7 +493,9 @@ def main():
                              f"x, r, x_new, r_new + 12 per-particle scalars), inputs larger than L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "grad-evals/s", "h2d_bytes_per_step": 2 * n_local * D * 8,
                     "d2h_bytes_per_step": 2 * n_local * D * 8 + 8, "ms_per_step": te.item() / K * 1e3,
-                    "api": "smcnuts.proposal.nuts.NUTSProposal.rvs(x_host, r_host, phi) with pinned host tensors"},
+                    "api": "smcnuts.proposal.nuts.NUTSProposal.rvs(x_host, r_host, phi) with pinned host tensors",
+                    "warmup_calls": e2e_warmup, "median_ms_per_call": float(np.median(per_call)),
+                    "max_ms_per_call": float(np.max(per_call))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "kernel": "nuts_transition_kernel", "achieved": achieved / 1e12, "peak": peak / 1e12,
                          "unit": "TFLOP/s", "frac": achieved / peak,
