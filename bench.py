@@ -78,9 +78,12 @@ class ClockSampler(threading.Thread):
                 import pynvml
                 pynvml.nvmlInit()
                 # NVML enumerates all devices: map torch's index through CUDA_VISIBLE_DEVICES when it is a plain index list
-                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-                phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
-                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+                vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+                if vis and index < len(vis) and vis[index].startswith(("GPU-", "MIG-")):
+                    self.handle = pynvml.nvmlDeviceGetHandleByUUID(vis[index].encode())
+                else:
+                    phys = int(vis[index]) if vis and index < len(vis) and vis[index].isdigit() else index
+                    self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
                 self.nvml = pynvml
             except Exception:
                 self.nvml = None
