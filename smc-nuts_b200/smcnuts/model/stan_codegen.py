@@ -20,12 +20,18 @@ What is generated
     err[t-1]) therefore work, and loops stay loops (bounds are literals: scalar data is folded at generation time).
 
 Supported subset (anything else raises StanSubsetError with the offending line):
-  blocks data / parameters / model;  int, real, vector, row_vector, array[..] (and the pre-2.33 `real y[N]` form);
-  lower/upper bounds on real parameters;  local declarations, =, +=, -=, *=, /=, `target +=`, `~`, for loops, blocks;
-  + - * / ^, unary minus, indexing, exp log log1p sqrt fabs abs square inv inv_logit log1p_exp log_sum_exp(a, b) pow
-  tanh sin cos lgamma(data only) dot_product-free scalar code;  normal, cauchy, student_t, double_exponential,
-  lognormal, exponential, gamma, inv_gamma, beta, uniform densities; poisson, poisson_log, bernoulli, bernoulli_logit,
-  binomial_logit mass functions -- scalar or vectorised over array arguments.
+  blocks data / transformed data / parameters / transformed parameters / model (generated quantities is skipped: it never
+  enters the log density; a non-empty functions block is refused);  int, real, vector, row_vector, matrix (data and
+  locals), array[..] (and the pre-2.33 `real y[N]` form);  lower/upper bounds on real parameters;  local declarations
+  with initialisers, =, +=, -=, *=, /=, `target +=`, `~`, for loops, if / else (conditions on data, loop variables or
+  parameter values; && || !), blocks;
+  + - * / ^ .* ./, unary minus, indexing, exp log log1p sqrt fabs abs square inv inv_logit log1p_exp log_sum_exp(a, b)
+  pow tanh sin cos lgamma(data only);  container-valued expressions: elementwise arithmetic and functions, matrix *
+  vector, row_vector * vector, row_vector * matrix, sum mean dot_product dot_self rep_vector rep_row_vector rep_array,
+  whole-container assignment -- lowered onto element loops and accumulator locals of the scalar subset (`lower_stmt`);
+  normal, std_normal, cauchy, student_t, double_exponential, logistic, lognormal, exponential, gamma, inv_gamma, weibull,
+  beta, uniform densities; poisson, poisson_log, bernoulli, bernoulli_logit, binomial, binomial_logit mass functions --
+  scalar or vectorised over container arguments and container-valued argument expressions.
 """
 import json
 import math
@@ -42,7 +48,7 @@ _TOKEN = re.compile(r"""
     (?P<ws>\s+|//[^\n]*|\#[^\n]*|/\*.*?\*/)
   | (?P<num>(\d+\.\d*|\.\d+|\d+)([eE][+-]?\d+)?)
   | (?P<id>[A-Za-z_][A-Za-z_0-9]*)
-  | (?P<op>\+=|-=|\*=|/=|<=|>=|==|!=|&&|\|\||[-+*/^()\[\]{},;:|<>=~'!])
+  | (?P<op>\.\*|\./|\+=|-=|\*=|/=|<=|>=|==|!=|&&|\|\||[-+*/^()\[\]{},;:|<>=~'!])
 """, re.X | re.S)
 
 
@@ -66,6 +72,7 @@ class _Parser:
     def __init__(self, text):
         self.t = _tokenize(text)
         self.i = 0
+        self.orients = {}       # variable name -> "col" (vector) | "row" (row_vector) | "mat" (matrix): how `*` treats it
 
     def peek(self, k=0):
         return self.t[self.i + k]
@@ -99,18 +106,19 @@ class _Parser:
             self.expect("{")
             if name in ("data", "parameters"):
                 blocks[name] = self.decls()
-            elif name == "model":
+            elif name in ("model", "transformed data", "transformed parameters"):
                 blocks[name] = self.stmts()
             else:
-                depth, empty = 1, True     # other blocks are accepted only when empty
+                depth, empty = 1, True
                 while depth:
                     tok = self.next()
                     depth += (tok[1] == "{") - (tok[1] == "}")
                     empty = empty and tok[1] == "}"
                     if tok[0] == "eof":
                         self.err("unterminated block")
-                if not empty:
-                    raise StanSubsetError(f"block {name!r} is outside the supported subset (data / parameters / model)")
+                # generated quantities never enter the log density (bridgestan.py:60-85 only calls log_density*): skipped
+                if not empty and name != "generated quantities":
+                    raise StanSubsetError(f"block {name!r} is outside the supported subset")
                 continue
             self.expect("}")
         for need in ("parameters", "model"):
@@ -159,15 +167,20 @@ class _Parser:
         if base == "array":
             shape += self.dims()
             base = self.next()[1]
-        if base == "matrix":
-            raise StanSubsetError(f"line {line}: matrix types are outside the supported subset (use flat arrays)")
         lo, hi = self.bounds()
-        if base in ("vector", "row_vector"):
-            shape += self.dims()
+        orient = None
+        if base in ("vector", "row_vector", "matrix"):
+            orient = {"vector": "col", "row_vector": "row", "matrix": "mat"}[base]
+            d = self.dims()
+            if len(d) != (2 if base == "matrix" else 1):
+                raise StanSubsetError(f"line {line}: {base} needs {2 if base == 'matrix' else 1} size(s)")
+            shape += d
             base = "real"
         name = self.next()
         if name[0] != "id":
             raise StanSubsetError(f"line {line}: expected a variable name, found {name[1]!r}")
+        if orient:
+            self.orients[name[1]] = orient
         shape += self.dims()          # pre-2.33 array syntax: real y[N]
         init = self.expr() if self.accept("=") else None
         self.expect(";")
@@ -203,7 +216,14 @@ class _Parser:
             hi = self.expr()
             self.expect(")")
             return ("for", var, lo, hi, [self.stmt()], line)
-        if self.peek()[1] in ("if", "while", "print", "reject", "return"):
+        if self.accept("if"):
+            self.expect("(")
+            cond = self.cond()
+            self.expect(")")
+            then = self.stmt()
+            other = self.stmt() if self.accept("else") else None
+            return ("if", cond, then, other, line)
+        if self.peek()[1] in ("while", "print", "reject", "return"):
             raise StanSubsetError(f"line {line}: statement {self.peek()[1]!r} is outside the supported subset")
         if self.peek()[1] == "target" and self.peek(1)[1] == "+=":
             self.next(); self.next()
@@ -229,6 +249,39 @@ class _Parser:
         self.expect(";")
         return ("assign", lhs, op, rhs, line)
 
+    # ---- conditions of `if`: || over && over ! over one comparison of two arithmetic expressions (or a bare expression)
+    def cond(self):
+        a = self.cond_and()
+        while self.accept("||"):
+            a = ("lor", a, self.cond_and())
+        return a
+
+    def cond_and(self):
+        a = self.cond_not()
+        while self.accept("&&"):
+            a = ("land", a, self.cond_not())
+        return a
+
+    def cond_not(self):
+        if self.accept("!"):
+            return ("lnot", self.cond_not())
+        if self.peek()[1] == "(":        # either a parenthesised condition or a parenthesised arithmetic operand
+            save = self.i
+            self.next()
+            try:
+                c = self.cond()
+                self.expect(")")
+                if self.peek()[1] in (")", "&&", "||") and c[0] in ("lor", "land", "lnot", "cmp"):
+                    return c
+            except StanSubsetError:
+                pass
+            self.i = save
+        a = self.additive(False)
+        if self.peek()[1] in ("<", ">", "<=", ">=", "==", "!="):
+            op = self.next()[1]
+            return ("cmp", op, a, self.additive(False))
+        return ("cmp", "!=", a, ("num", 0.0, True))
+
     # ---- expressions
     def expr(self, no_gt=False, no_colon=False):
         return self.additive(no_gt)
@@ -242,7 +295,7 @@ class _Parser:
 
     def multiplicative(self, no_gt):
         a = self.unary(no_gt)
-        while self.peek()[1] in ("*", "/"):
+        while self.peek()[1] in ("*", "/", ".*", "./"):
             op = self.next()[1]
             a = ("bin", op, a, self.unary(no_gt))
         return a
@@ -390,6 +443,14 @@ _DENSITIES = {
                                       _mul(_const(-0.5), _log(_mul(nu, _const(math.pi)))), _un("neg", _log(s)),
                                       _un("neg", _mul(_mul(_const(0.5), _add(nu, _const(1.0))),
                                                       _un("log1p", _div(_bin("^", _div(_sub(y, m), s), _const(2.0)), nu))))],
+    "std_normal": lambda y: [_const(-0.5 * _LOG_2PI), _mul(_const(-0.5), _bin("^", y, _const(2.0)))],
+    "logistic": lambda y, m, s: [_un("neg", _log(s)), _un("neg", _div(_sub(y, m), s)),
+                                 _mul(_const(-2.0), _un("log1p_exp", _un("neg", _div(_sub(y, m), s))))],
+    "weibull": lambda y, a, s: [_sub(_log(a), _log(s)), _mul(_sub(a, _const(1.0)), _sub(_log(y), _log(s))),
+                                _un("neg", _bin("^", _div(y, s), a))],
+    "binomial": lambda k, n, p: [_sub(_un("lgamma", _add(n, _const(1.0))),
+                                      _add(_un("lgamma", _add(k, _const(1.0))), _un("lgamma", _add(_sub(n, k), _const(1.0))))),
+                                 _mul(k, _log(p)), _mul(_sub(n, k), _un("log1p", _un("neg", p)))],
     "exponential": lambda y, b: [_log(b), _un("neg", _mul(b, y))],
     "gamma": lambda y, a, b: [_mul(a, _log(b)), _un("neg", _un("lgamma", a)), _mul(_sub(a, _const(1.0)), _log(y)), _un("neg", _mul(b, y))],
     "inv_gamma": lambda y, a, b: [_mul(a, _log(b)), _un("neg", _un("lgamma", a)), _un("neg", _mul(_add(a, _const(1.0)), _log(y))),
@@ -413,8 +474,9 @@ _UNARY_FUNCS = {"exp": "exp", "log": "log", "log1p": "log1p", "sqrt": "sqrt", "f
 class _Var:
     """A data array, parameter or model-block local."""
 
-    def __init__(self, name, kind, shape, base="real", offset=0, lower=None, upper=None, value=None):
+    def __init__(self, name, kind, shape, base="real", offset=0, lower=None, upper=None, value=None, orient=None):
         self.name, self.kind, self.shape, self.base, self.offset = name, kind, shape, base, offset
+        self.orient = orient         # "col" | "row" | "mat" | None (plain array): what `*` does with it
         self.lower, self.upper, self.value = lower, upper, value
         self.size = 1
         for s in shape:
@@ -433,8 +495,13 @@ class GeneratedSource:
 class _Gen:
     MAX_DIM = 64
 
-    def __init__(self, blocks, data, struct_name):
+    def __init__(self, blocks, data, struct_name, orients=None):
         self.blocks, self.struct_name = blocks, struct_name
+        self.orients = orients or {}
+        self.lowered = {}       # id(statement) -> its scalar-subset replacement (list of statements) or None
+        self.fresh = 0
+        self.decl_init = {}     # id(declaration with an initialiser) -> its assignment statement
+        self.outer_pre = None   # while a statement is being lowered: where its loop-invariant scalar reductions go
         self.data_in = dict(data)
         self.vars = {}          # name -> _Var
         self.loop_vars = []     # stack of (name, c_name)
@@ -602,6 +669,288 @@ class _Gen:
                         raise StanSubsetError(f"density arguments of different lengths ({n} and {v.shape[0]})")
                     n = v.shape[0]
         return n
+
+
+    # ---- whole-container expressions: shapes, and their lowering onto the scalar subset ---------------------------------
+    # A statement that uses vectors / matrices as values (elementwise arithmetic, matrix * vector, row_vector * vector,
+    # sum / mean / dot_product / dot_self / rep_vector, densities of vector expressions) is rewritten into element loops
+    # and accumulator locals of the scalar subset, which the differentiation machinery below already handles.
+    _REDUCTIONS = ("sum", "mean", "dot_product", "dot_self")
+    _REPS = ("rep_vector", "rep_row_vector", "rep_array")
+
+    def is_loop_var(self, name):
+        return any(name == lv for lv, _ in self.loop_vars)
+
+    def shape(self, e):
+        """-> (dims tuple, orientation of a 1-d result: "col" | "row" | None, or "mat")"""
+        k = e[0]
+        if k == "num":
+            return (), None
+        if k == "var" or k == "idx":
+            base, idx = (e, []) if k == "var" else (e[1], e[2])
+            if base[0] != "var":
+                raise StanSubsetError("only named variables can be indexed")
+            if self.is_loop_var(base[1]):
+                return (), None
+            v = self.vars.get(base[1])
+            if v is None:
+                raise StanSubsetError(f"line {base[2]}: unknown variable {base[1]!r}")
+            rest = tuple(v.shape[len(idx):])
+            if len(idx) > len(v.shape):
+                raise StanSubsetError(f"line {base[2]}: {v.name} has {len(v.shape)} dimension(s), indexed with {len(idx)}")
+            if not rest:
+                return (), None
+            if v.orient == "mat":
+                return rest, ("mat" if len(rest) == 2 else "row")
+            return rest, (v.orient if len(rest) == 1 else None)
+        if k == "neg":
+            return self.shape(e[1])
+        if k == "bin":
+            (da, oa), (db, ob) = self.shape(e[2]), self.shape(e[3])
+            op = e[1]
+            if not da:
+                if db and op in ("/", "^"):
+                    raise StanSubsetError(f"scalar {op} container is outside the supported subset (use ./ or a loop)")
+                return db, ob
+            if not db:
+                return da, oa
+            if op == "*":
+                if oa == "mat" and ob == "col" and da[1] == db[0]:
+                    return (da[0],), "col"
+                if oa == "row" and ob == "col" and da == db:
+                    return (), None
+                if oa == "row" and ob == "mat" and da[0] == db[0]:
+                    return (db[1],), "row"
+                raise StanSubsetError("`*` between these containers is outside the supported subset (supported: matrix * vector, "
+                                      "row_vector * vector, row_vector * matrix; elementwise products are `.*`)")
+            if op in ("+", "-", ".*", "./"):
+                if da != db:
+                    raise StanSubsetError(f"operands of {op} have different sizes ({da} and {db})")
+                return da, oa
+            raise StanSubsetError(f"operator {op} between two containers is outside the supported subset")
+        if k == "call":
+            name, args = e[1], e[2]
+            if name in self._REDUCTIONS or re.fullmatch(r"\w+_(lpdf|lpmf|log)", name):
+                return (), None
+            if name in self._REPS and len(args) == 2:
+                n, _ = self.int_expr(args[1])
+                if n is None:
+                    raise StanSubsetError(f"line {e[3]}: the size of {name} must be a constant")
+                return (n,), {"rep_vector": "col", "rep_row_vector": "row", "rep_array": None}[name]
+            shapes = [self.shape(a) for a in args]
+            big = [sh for sh in shapes if sh[0]]
+            if big and any(sh[0] != big[0][0] for sh in big):
+                raise StanSubsetError(f"line {e[3]}: arguments of {name} have different sizes")
+            return big[0] if big else ((), None)
+        raise StanSubsetError(f"unsupported expression {e!r}")
+
+    def fresh_name(self, prefix):
+        self.fresh += 1
+        return f"{prefix}__{self.fresh}"       # Stan identifiers cannot end in two underscores: no collisions
+
+    def reduce(self, n, term_of, pre, line):
+        """acc = sum over k = 1..n of term_of(k), emitted as scalar-subset statements appended to `pre` -> the accumulator"""
+        acc, kv = self.fresh_name("r"), self.fresh_name("k")
+        inner = []
+        term = term_of(("var", kv, line), inner)
+        body = inner + [("assign", ("var", acc, line), "+=", term, line)]
+        pre.append(("decl", (acc, "real", [], None, None, ("num", 0.0, True), line), line))
+        pre.append(("for", kv, ("num", 1.0, True), ("num", float(n), True), [("block", body, line)], line))
+        return ("var", acc, line)
+
+    def lower(self, e, ix, pre, line=0):
+        """Scalar-subset expression for element `ix` (one index expression per dimension of shape(e)) of `e`.
+        Statements the value needs first (accumulator loops) are appended to `pre`; those of a SCALAR sub-expression do
+        not depend on the element, so they go to the statement level (`outer_pre`) and run once, before any element loop."""
+        k = e[0]
+        dims, orient = self.shape(e)
+        if len(ix) != len(dims):
+            raise StanSubsetError(f"line {line}: a container of {len(dims)} dimension(s) is used where {len(ix)} are expected")
+        if not dims and self.outer_pre is not None:
+            pre = self.outer_pre
+        if k == "num":
+            return e
+        if k == "var":
+            return ("idx", e, list(ix)) if ix else e
+        if k == "idx":
+            return ("idx", e[1], list(e[2]) + list(ix)) if ix else e
+        if k == "neg":
+            return ("neg", self.lower(e[1], ix, pre, line))
+        if k == "bin":
+            op, a, b = e[1], e[2], e[3]
+            (da, oa), (db, ob) = self.shape(a), self.shape(b)
+            if op == "*" and da and db:
+                if oa == "mat" and ob == "col":      # (X v)[i] = sum_k X[i, k] v[k]
+                    return self.reduce(da[1], lambda kk, p2: ("bin", "*", self.lower(a, [ix[0], kk], p2, line),
+                                                               self.lower(b, [kk], p2, line)), pre, line)
+                if oa == "row" and ob == "col":      # r * v = sum_k r[k] v[k]
+                    return self.reduce(da[0], lambda kk, p2: ("bin", "*", self.lower(a, [kk], p2, line),
+                                                               self.lower(b, [kk], p2, line)), pre, line)
+                # row_vector * matrix: (r X)[j] = sum_k r[k] X[k, j]
+                return self.reduce(da[0], lambda kk, p2: ("bin", "*", self.lower(a, [kk], p2, line),
+                                                           self.lower(b, [kk, ix[0]], p2, line)), pre, line)
+            return ("bin", op.lstrip("."), self.lower(a, ix if da else [], pre, line), self.lower(b, ix if db else [], pre, line))
+        if k == "call":
+            name, args, cl = e[1], e[2], e[3]
+            if name in self._REPS and len(args) == 2:
+                return self.lower(args[0], [], pre, cl)
+            if name in self._REDUCTIONS:
+                shapes = [self.shape(a)[0] for a in args]
+                if len(args) != (2 if name == "dot_product" else 1) or any(len(d) != 1 for d in shapes) or len(set(shapes)) != 1:
+                    raise StanSubsetError(f"line {cl}: {name} takes {'two' if name == 'dot_product' else 'one'} one-dimensional "
+                                          f"container(s) of equal size")
+                n = shapes[0][0]
+
+                def term(kk, p2):
+                    x = self.lower(args[0], [kk], p2, cl)
+                    if name == "dot_product":
+                        return ("bin", "*", x, self.lower(args[1], [kk], p2, cl))
+                    return ("bin", "*", x, x) if name == "dot_self" else x
+                total = self.reduce(n, term, pre, cl)
+                return ("bin", "/", total, ("num", float(n), False)) if name == "mean" else total
+            m = re.fullmatch(r"(\w+?)_(lpdf|lpmf|log)", name)
+            if m and m.group(1) in _DENSITIES:
+                shapes = [self.shape(a)[0] for a in args]
+                big = [d for d in shapes if d]
+                if big:                               # a vectorised density inside a larger expression: sum over the elements
+                    if any(len(d) != 1 or d != big[0] for d in big):
+                        raise StanSubsetError(f"line {cl}: density arguments must be one-dimensional containers of equal size")
+                    return self.reduce(big[0][0], lambda kk, p2: ("call", name, [self.lower(a, [kk] if d else [], p2, cl)
+                                                                                 for a, d in zip(args, shapes)], cl), pre, cl)
+                return ("call", name, [self.lower(a, [], pre, cl) for a in args], cl)
+            return ("call", name, [self.lower(a, ix if self.shape(a)[0] else [], pre, cl) for a in args], cl)
+        raise StanSubsetError(f"unsupported expression {e!r}")
+
+    def is_plain(self, e):
+        """Expressions the scalar machinery takes as they are: scalars without container operations inside, and whole
+        one-dimensional variables (the vectorised density arguments of target_terms)."""
+        dims, _ = self.shape(e)
+        if dims:
+            return e[0] == "var" and len(dims) == 1
+        saved, self.outer_pre = self.outer_pre, []
+        try:
+            return self.lower(e, [], self.outer_pre) == e and not self.outer_pre
+        finally:
+            self.outer_pre = saved
+
+    def element_loops(self, dims, body_of, line):
+        """Nested `for` statements over a container of shape `dims`; body_of(index expressions) -> list of statements"""
+        names = [self.fresh_name("i") for _ in dims]
+        body = body_of([("var", nm, line) for nm in names])
+        for nm, n in reversed(list(zip(names, dims))):
+            body = [("for", nm, ("num", 1.0, True), ("num", float(n), True), [("block", body, line)], line)]
+        return body
+
+    def lower_stmt(self, s):
+        key = id(s)
+        if key not in self.lowered:
+            self.lowered[key] = (s, self._lower_stmt(s))     # the statement is kept alive: ids are not reused
+        return self.lowered[key][1]
+
+    def _lower_stmt(self, s):
+        self.outer_pre = []
+        try:
+            out = self._lower_stmt_inner(s, self.outer_pre)
+        finally:
+            self.outer_pre = None
+        return out
+
+    @staticmethod
+    def _refs(e, name, out):
+        """index lists of every use of variable `name` inside expression / statement tuples"""
+        if isinstance(e, (tuple, list)):
+            if len(e) >= 2 and e[0] == "idx" and isinstance(e[1], tuple) and e[1][:2] == ("var", name):
+                out.append(list(e[2]))
+                return out
+            if len(e) >= 2 and e[0] == "var" and e[1] == name:
+                out.append([])
+                return out
+            for x in e:
+                _Gen._refs(x, name, out)
+        return out
+
+    def _lower_stmt_inner(self, s, pre):
+        kind, line = s[0], s[-1]
+        if kind == "target" or kind == "tilde":
+            if kind == "target":
+                tempered, e = self.scale_split(s[1])
+                m = re.fullmatch(r"(\w+?)_(lpdf|lpmf|log)", e[1]) if e[0] == "call" else None
+                dist, args = (m.group(1), e[2]) if (m and m.group(1) in _DENSITIES) else (None, None)
+            else:
+                tempered, dist, args = False, s[2], [s[1]] + s[3]
+
+            def rebuild(a):
+                if kind == "tilde":
+                    return ("tilde", a[0], dist, a[1:], line)
+                call = ("call", e[1], a, e[3])
+                return ("target", ("bin", "*", ("var", "phi", line), call) if tempered else call, line)
+            if dist is not None:
+                if all(self.is_plain(a) for a in args):
+                    return None
+                shapes = [self.shape(a)[0] for a in args]
+                big = [d for d in shapes if d]
+                if not big:
+                    elems = [self.lower(a, [], pre, line) for a in args]
+                    return pre + [rebuild(elems)]
+                if any(len(d) != 1 or d != big[0] for d in big):
+                    raise StanSubsetError(f"line {line}: density arguments must be one-dimensional containers of equal size")
+                scalars = [None if d else self.lower(a, [], pre, line) for a, d in zip(args, shapes)]   # once, outside the loop
+
+                def body(ix):
+                    inner = []
+                    elems = [self.lower(a, ix, inner, line) if d else sc for a, d, sc in zip(args, shapes, scalars)]
+                    return inner + [rebuild(elems)]
+                loops = self.element_loops(big[0], body, line)
+                return pre + loops
+            if kind == "tilde":
+                return None
+            e2 = self.lower(s[1], [], pre, line)
+            return None if (e2 == s[1] and not pre) else pre + [("target", e2, line)]
+        if kind == "assign":
+            _, lhs, op, rhs, _ = s
+            ldims, _ = self.shape(lhs)
+            rdims, _ = self.shape(rhs)
+            if not ldims:
+                r2 = self.lower(rhs, [], pre, line)
+                return None if (r2 == rhs and not pre) else pre + [("assign", lhs, op, r2, line)]
+            if rdims and rdims != ldims:
+                raise StanSubsetError(f"line {line}: assignment of a container of size {rdims} to one of size {ldims}")
+            name = (lhs if lhs[0] == "var" else lhs[1])[1]
+            scalar_rhs = None if rdims else self.lower(rhs, [], pre, line)
+
+            def body(ix):
+                inner = []
+                elem = self.lower(rhs, ix, inner, line) if rdims else scalar_rhs
+                # Stan evaluates the right-hand side before it assigns: inside the element loop the assigned variable
+                # may only be read at the element being written (reductions over it were hoisted ahead of the loop)
+                own = self.lower(lhs, ix, inner, line)
+                if any(r != own[2] for r in self._refs((inner, elem), name, [])):
+                    raise StanSubsetError(f"line {line}: {name!r} is assigned from a product that reads its other elements; "
+                                          f"assign to a second variable")
+                return inner + [("assign", own, op, elem, line)]
+            loops = self.element_loops(ldims, body, line)
+            return pre + loops
+        return None
+
+    # ---- conditions of `if`
+    def cond_text(self, c, line):
+        if c[0] in ("lor", "land"):
+            return f"({self.cond_text(c[1], line)} {'||' if c[0] == 'lor' else '&&'} {self.cond_text(c[2], line)})"
+        if c[0] == "lnot":
+            return f"(!{self.cond_text(c[1], line)})"
+        sides = []
+        for e in (c[2], c[3]):
+            if self.is_int_expr(e):
+                sides.append(self.int_expr(e)[1])
+            else:
+                pre = []
+                e2 = self.lower(e, [], pre, line)
+                if pre:
+                    raise StanSubsetError(f"line {line}: container operations inside a condition are outside the supported subset")
+                if self.shape(e)[0]:
+                    raise StanSubsetError(f"line {line}: a condition compares scalars")
+                sides.append(self.emit_value_and_adjoints(self.real(e2))[0])
+        return f"({sides[0]} {c[1]} {sides[1]})"
 
     # ---- emission helpers
     def emit(self, text):
@@ -830,6 +1179,30 @@ class _Gen:
     def statements(self, stmts, emit=True):
         for s in stmts:
             kind, line = s[0], s[-1]
+            low = self.lower_stmt(s)
+            if low is not None:
+                self.statements(low, emit)
+                continue
+            if kind == "if":
+                _, cond, then, other, _ = s
+                if emit:
+                    self.emit("{")
+                    self.indent += 1
+                    self.emit(f"if ({self.cond_text(cond, line)}) {{")
+                    self.indent += 1
+                self.statements([then], emit)
+                if other is not None:
+                    if emit:
+                        self.indent -= 1
+                        self.emit("} else {")
+                        self.indent += 1
+                    self.statements([other], emit)
+                if emit:
+                    self.indent -= 1
+                    self.emit("}")
+                    self.indent -= 1
+                    self.emit("}")
+                continue
             if kind == "decl":
                 name, base, shape, lo, hi, init, _ = s[1]
                 if name in self.vars and self.vars[name].kind != "local":
@@ -841,9 +1214,10 @@ class _Gen:
                         raise StanSubsetError(f"line {line}: local array sizes must be constants")
                     dims.append(dv)
                 if name not in self.vars:
-                    self.vars[name] = _Var(name, "local", dims, base)
-                if init is not None:
-                    self.statements([("assign", ("var", name, line), "=", init, line)], emit)
+                    self.vars[name] = _Var(name, "local", dims, base, orient=self.orients.get(name))
+                if init is not None:     # one statement object per declaration: its lowering is cached by identity
+                    first = self.decl_init.setdefault(id(s), ("assign", ("var", name, line), "=", init, line))
+                    self.statements([first], emit)
             elif kind == "block":
                 self.statements(s[1], emit)
             elif kind == "for":
@@ -903,7 +1277,7 @@ class _Gen:
                     n *= d
                 if len(flat) != n:
                     raise StanSubsetError(f"data {name!r}: expected {n} values, found {len(flat)}")
-                v = _Var(name, "data", dims, base, offset=len(self.blob), value=flat)
+                v = _Var(name, "data", dims, base, offset=len(self.blob), value=flat, orient=self.orients.get(name))
                 self.blob += flat
             else:
                 v = _Var(name, "data", [], base, value=(int(val) if base == "int" else float(val)))
@@ -916,7 +1290,10 @@ class _Gen:
             dims = [self.int_expr(d)[0] for d in shape]
             lov = None if lo is None else self._const_value(lo, line)
             hiv = None if hi is None else self._const_value(hi, line)
-            v = _Var(name, "param", dims, "real", offset=off, lower=lov, upper=hiv)
+            if self.orients.get(name) == "mat":
+                raise StanSubsetError(f"line {line}: matrix parameters are outside the supported subset (BridgeStan orders them "
+                                      f"column-major; declare an array of vectors)")
+            v = _Var(name, "param", dims, "real", offset=off, lower=lov, upper=hiv, orient=self.orients.get(name))
             self.vars[name] = v
             kind = "none" if (lov is None and hiv is None) else "both" if (lov is not None and hiv is not None) else \
                 "lower" if lov is not None else "upper"
@@ -927,6 +1304,21 @@ class _Gen:
         self.dim = off
         if not (1 <= self.dim <= self.MAX_DIM):
             raise StanSubsetError(f"{self.dim} unconstrained parameters; the generated kernels support 1..{self.MAX_DIM}")
+        # transformed data (integer scalars folded now, everything else computed like a parameter-free local) and
+        # transformed parameters (locals of the density; their declared bounds are validation only) run ahead of the model
+        program = []
+        for st in self.blocks.get("transformed data", []):
+            if st[0] == "decl" and st[1][1] == "int":
+                name, _, shape, _, _, init, line = st[1]
+                if shape or init is None:
+                    raise StanSubsetError(f"line {line}: transformed data integers must be scalars defined where they are declared")
+                self.vars[name] = _Var(name, "data", [], "int", value=self.int_expr(init)[0])
+                if self.vars[name].value is None:
+                    raise StanSubsetError(f"line {line}: {name!r} is not a constant")
+            else:
+                program.append(st)
+        program += self.blocks.get("transformed parameters", [])
+        self.blocks["model"] = program + self.blocks["model"]
         # activity analysis (which coordinates can each local depend on): fixpoint over the statement list
         for _ in range(64):
             self.changed = False
@@ -1039,8 +1431,9 @@ def load_data(data_path):
 def generate(stan_text, data, struct_name="GenModel"):
     """Stan program text + data dict -> GeneratedSource."""
     import hashlib
-    blocks = _Parser(stan_text).program()
-    g = _Gen(blocks, data, struct_name)
+    parser = _Parser(stan_text)
+    blocks = parser.program()
+    g = _Gen(blocks, data, struct_name, parser.orients)
     text = g.run()
     digest = hashlib.sha256((text + repr(g.blob)).encode()).hexdigest()[:16]
     return GeneratedSource(struct_name, text, g.dim, g.blob, g.param_names, g.transforms, digest)

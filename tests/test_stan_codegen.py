@@ -192,20 +192,109 @@ def test_generated_mixed_program_matches_a_numpy_restatement_and_finite_differen
         np.testing.assert_allclose(g[:, j], ((Ap + 0.45 * Bp) - (Am + 0.45 * Bm)) / (2 * eps), rtol=5e-6, atol=5e-6)
 
 
+def _fd_check(h, x, g, phi, dim, tol=5e-6):
+    eps = 1e-6
+    for j in range(dim):
+        xp, xm = x.copy(), x.copy()
+        xp[:, j] += eps; xm[:, j] -= eps
+        Ap, Bp, _ = h.split(xp, phi)
+        Am, Bm, _ = h.split(xm, phi)
+        np.testing.assert_allclose(g[:, j], ((Ap + phi * Bp) - (Am + phi * Bm)) / (2 * eps), rtol=tol, atol=tol)
+
+
+def _regression_data(rng, N=9, K=3):
+    return {"N": N, "K": K, "X": rng.normal(size=(N, K)).tolist(), "y": rng.normal(size=N).tolist()}
+
+
+def test_generated_regression_with_matrix_product_and_transformed_blocks(tmp_path):
+    """matrix * vector, transformed data (folded integer, real scalar, rep_vector), transformed parameters with a vector
+    initialiser, an elementwise product inside a density argument, generated quantities skipped."""
+    from scipy import stats
+    rng = np.random.default_rng(7)
+    data = _regression_data(rng)
+    src = SC.generate((STAN / "regression.stan").read_text(), data)
+    assert src.dim == 5 and src.param_names == ["alpha", "beta.1", "beta.2", "beta.3", "sigma"]
+    h = HostModel(src, tmp_path)
+    X, y = np.array(data["X"]), np.array(data["y"])
+
+    def restated(u):
+        alpha, beta, sigma = u[0], u[1:4], np.exp(u[4])
+        A = np.sum(-0.5 * beta ** 2) - 0.5 * (alpha / 5.0) ** 2 - sigma + u[4] - 0.5 * np.sum(np.diff(beta) ** 2)
+        mu = alpha + X @ beta
+        return A, np.sum(stats.norm.logpdf(y, mu * 1.0, sigma))
+
+    x = rng.normal(size=(40, 5)) * 0.7
+    A, B, g = h.split(x, 0.6)
+    ref = np.array([restated(u) for u in x])
+    np.testing.assert_allclose(A, ref[:, 0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(B, ref[:, 1], rtol=1e-12, atol=1e-12)
+    _fd_check(h, x, g, 0.6, 5)
+
+
+def _containers_data(rng, robust, N=8, K=3):
+    trials = rng.integers(1, 9, N)
+    return {"N": N, "K": K, "x": rng.normal(size=(N, K)).tolist(), "z": rng.integers(0, 2, N).tolist(),
+            "trials": trials.tolist(), "wins": rng.binomial(trials, 0.4).tolist(), "t": rng.normal(size=N).tolist(),
+            "robust": robust}
+
+
+@pytest.mark.parametrize("robust", [0, 1])
+def test_generated_container_expressions_match_a_numpy_restatement(tmp_path, robust):
+    """row_vector * vector, .* and ./, mean / sum / dot_self / dot_product, exp of a vector, densities of vector
+    expressions (in `target +=` and in `~`), if / else on a data flag and on parameter values, four more densities."""
+    from scipy import stats
+    from scipy.special import expit
+    rng = np.random.default_rng(11)
+    data = _containers_data(rng, robust)
+    src = SC.generate((STAN / "containers.stan").read_text(), data)
+    assert src.dim == 6
+    h = HostModel(src, tmp_path)
+    X, z, t = np.array(data["x"]), np.array(data["z"]), np.array(data["t"])
+    trials, wins = np.array(data["trials"]), np.array(data["wins"])
+
+    def restated(u):
+        b, tau, c, p = u[0:3], np.exp(u[3]), u[4], expit(u[5])
+        jac = u[3] + np.log(p) + np.log1p(-p)
+        zc = (c - 0.5) / 1.5
+        # `~` statements keep only the parameter-dependent terms
+        A = np.sum(-0.5 * (b / 2.0) ** 2) + (0.5 * (np.log(tau) - np.log(2.0)) - (tau / 2.0) ** 1.5) \
+            + (-zc - 2.0 * np.logaddexp(0.0, -zc)) + np.sum(wins * np.log(p) + (trials - wins) * np.log1p(-p)) + jac
+        eta = X @ b + c
+        loc = eta * t - eta.mean()
+        B = np.sum(stats.t.logpdf(t, 4, loc, tau)) if robust else np.sum(stats.norm.logpdf(t, loc, tau))
+        e2 = eta / (1.0 + tau)
+        A += np.sum(z * e2 - np.logaddexp(0.0, e2))
+        A += -0.5 * (b @ b) / 10 + 0.01 * np.sum(np.exp(-eta)) - 0.1 * np.sum(b ** 3)
+        A += -c if (c > 0 and not tau >= 10) else c
+        return A, B
+
+    x = rng.normal(size=(60, 6)) * 0.7
+    assert (x[:, 4] > 0).any() and (x[:, 4] < 0).any()
+    A, B, g = h.split(x, 0.35)
+    ref = np.array([restated(u) for u in x])
+    np.testing.assert_allclose(A, ref[:, 0], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(B, ref[:, 1], rtol=1e-11, atol=1e-11)
+    _fd_check(h, x, g, 0.35, 6)
+
+
 def test_unsupported_constructs_fail_loudly_with_the_line():
     ok = "data { int N; } parameters { real a; } model { a ~ normal(0, 1); }"
     assert SC.generate(ok, {"N": 3}).dim == 1
     for bad, what in [
-        ("parameters { real a; } model { if (a > 0) a ~ normal(0, 1); }", "if"),
+        ("parameters { real a; } model { while (a > 0) a ~ normal(0, 1); }", "while"),
         ("parameters { real a; } model { a ~ wishart(1, 2); }", "wishart"),
         ("parameters { matrix[2, 2] a; } model { }", "matrix"),
-        ("parameters { real a; } transformed parameters { real b; b = a; } model { }", "transformed parameters"),
+        ("functions { real f(real x) { return x; } } parameters { real a; } model { }", "functions"),
+        ("data { int N; vector[N] v; } parameters { vector[N] a; } model { target += sum(a * v); }", "elementwise products"),
+        ("data { int N; matrix[N, N] X; } parameters { vector[N] a; } model { vector[N] m = a; m = X * m; }", "second variable"),
+        ("data { int N; } parameters { vector[N] a; } model { vector[2] m; m = a; }", "size"),
         ("data { int N; } parameters { real a; } model { a ~ normal(0, 1); }", "missing from the data"),
         ("parameters { real a; } model { target += lgamma(a); }", "lgamma"),
         ("data { real phi; } parameters { real a; } model { target += exp(phi * a); }", "phi"),
     ]:
+        data = {} if "missing" in what else {"N": 3, "v": [1.0, 2.0, 3.0], "X": [[1.0, 0.0, 0.0]] * 3}
         with pytest.raises(SC.StanSubsetError, match=what):
-            SC.generate(bad, {})
+            SC.generate(bad, data)
 
 
 # ------------------------------------------------------------------------------------------------ GPU
@@ -277,3 +366,36 @@ def test_generated_logistic_model_with_bounded_parameters_samples_and_constrains
     s.sample(show_progress=False)
     est = s.mean_estimate[-1]
     assert np.all(np.isfinite(est)) and est[4] > 0 and -1 < est[5] < 2 and s.leapfrogs.sum() > 0
+
+
+@pytest.mark.gpu
+def test_generated_container_programs_run_on_the_device_like_their_host_build(tmp_path):
+    """The programs with container expressions, if / else and transformed blocks, compiled by nvcc as plug-ins: the device
+    log density and gradient equal the g++ build of the same generated text, and a tempered SMC run on the regression
+    program recovers the coefficients the data were generated from."""
+    from smcnuts.distributions import StdNormal
+    from smcnuts.model.generated import GeneratedModel
+    from smcnuts.smc_sampler import SMCSampler
+    rng = np.random.default_rng(11)
+    data = _containers_data(rng, 1)
+    m = GeneratedModel((STAN / "containers.stan").read_text(), data, "containers")
+    h = HostModel(m.source, tmp_path)
+    x = rng.normal(size=(512, 6)) * 0.7
+    for phi in (0.0, 0.35, 1.0):
+        A, B, g = h.split(x, phi)
+        np.testing.assert_allclose(m.logpdf(x, phi), A + phi * B, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(m.logpdfgrad(x, phi), g, rtol=1e-10, atol=1e-10)
+    # regression: y = 0.7 + X (1, -0.5, 0.25) + 0.3 noise, 60 observations
+    N, K = 60, 3
+    X = rng.normal(size=(N, K))
+    truth = np.array([0.7, 1.0, -0.5, 0.25])
+    y = truth[0] + X @ truth[1:] + 0.3 * rng.normal(size=N)
+    reg = GeneratedModel((STAN / "regression.stan").read_text(), {"N": N, "K": K, "X": X.tolist(), "y": y.tolist()}, "regression")
+    s = SMCSampler(K=40, N=4096, target=reg, step_size=0.03, sample_proposal=StdNormal(5), momentum_proposal=StdNormal(5),
+                   lkernel="asymptoticLKernel", tempering=True, rng=5)
+    s.sample(show_progress=False)
+    assert s.phi[-1] == 1.0
+    est = s.mean_estimate[-1]
+    # the random-walk and N(0, 1) priors shrink a little; posterior sd of a coefficient is ~0.3 / sqrt(60) = 0.04
+    np.testing.assert_allclose(est[:4], truth, atol=0.15)
+    assert 0.2 < est[4] < 0.45
