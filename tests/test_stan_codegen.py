@@ -277,6 +277,90 @@ def test_generated_container_expressions_match_a_numpy_restatement(tmp_path, rob
     _fd_check(h, x, g, 0.35, 6)
 
 
+_EIGHT_SCHOOLS = """
+data { int<lower=0> J; array[J] real y; array[J] real<lower=0> sigma; }
+parameters { real mu; real<lower=0> tau; vector[J] theta_tilde; }
+transformed parameters { vector[J] theta = mu + tau * theta_tilde; }
+model { mu ~ normal(0, 5); tau ~ cauchy(0, 5); theta_tilde ~ std_normal(); y ~ normal(theta, sigma); }
+"""
+_POISSON_GLM = """
+data { int N; int K; matrix[N, K] X; array[N] int<lower=0> y; real phi; }
+parameters { real alpha; vector[K] beta; }
+model {
+  vector[N] eta;
+  eta = X * beta;
+  eta += alpha;
+  alpha ~ normal(0, 1); beta ~ normal(0, 1);
+  target += phi * poisson_log_lpmf(y | eta);
+  target += sum(log1p_exp(beta)) - mean(beta);
+  for (n in 1:N) target += 0.01 * normal_lpdf(y[n] | X[n] * beta + alpha, 2);
+}
+"""
+_PROJECTIONS = """
+data { int N; int K; matrix[K, N] W; row_vector[K] r0; vector[N] t; real phi; }
+parameters { row_vector[K] r; real<lower=0> s; }
+model {
+  row_vector[N] proj = (r + r0) * W;
+  vector[N] v;
+  for (n in 1:N) {
+    if (n <= 2) v[n] = proj[n] * 2; else v[n] = proj[n] - sum(r .* r0);
+  }
+  target += 0.5 * normal_lpdf(t | v ./ (1 + s), rep_vector(1.5, N)) - dot_self(r);
+  target += phi * (-0.5 * dot_product(v, t) * dot_product(v, t) / 100);
+  s ~ gamma(2, 2);
+}
+"""
+
+
+@pytest.mark.parametrize("case", ["eight_schools", "poisson_glm", "projections"])
+def test_generated_idiomatic_programs_match_numpy_restatements(tmp_path, case):
+    """Programs written the way Stan users write them (non-centred eight schools; a Poisson GLM with matrix * vector, a
+    compound whole-vector assignment and a row slice of a matrix inside a loop; row_vector * matrix with if / else on the
+    loop variable and a density of a vector expression inside a larger expression)."""
+    from scipy import stats
+    from scipy.special import gammaln
+    rng = np.random.default_rng(0)
+    if case == "eight_schools":
+        y, sd = np.array([28., 8., -3., 7., -1., 1., 18., 12.]), np.array([15., 10., 16., 11., 9., 11., 10., 18.])
+        text, data, dim = _EIGHT_SCHOOLS, {"J": 8, "y": y.tolist(), "sigma": sd.tolist()}, 10
+
+        def restated(u):
+            mu, tau, tt = u[0], np.exp(u[1]), u[2:]
+            th = mu + tau * tt
+            return (-0.5 * (mu / 5) ** 2 - np.log1p((tau / 5) ** 2) + u[1] - 0.5 * np.sum(tt ** 2)
+                    - 0.5 * np.sum(((y - th) / sd) ** 2)), 0.0
+    elif case == "poisson_glm":
+        N, K = 10, 2
+        X, y = rng.normal(size=(N, K)), rng.poisson(2.0, N)
+        text, data, dim = _POISSON_GLM, {"N": N, "K": K, "X": X.tolist(), "y": y.tolist()}, 3
+
+        def restated(u):
+            a, b = u[0], u[1:]
+            eta = X @ b + a
+            A = -0.5 * a * a - 0.5 * np.sum(b * b) + np.sum(np.logaddexp(0, b)) - b.mean() \
+                + 0.01 * np.sum(stats.norm.logpdf(y, eta, 2))
+            return A, np.sum(y * eta - np.exp(eta) - gammaln(y + 1.0))
+    else:
+        W, r0, t = rng.normal(size=(2, 5)), rng.normal(size=2), rng.normal(size=5)
+        text, data, dim = _PROJECTIONS, {"N": 5, "K": 2, "W": W.tolist(), "r0": r0.tolist(), "t": t.tolist()}, 3
+
+        def restated(u):
+            r, s = u[:2], np.exp(u[2])
+            proj = (r + r0) @ W
+            v = np.where(np.arange(1, 6) <= 2, proj * 2, proj - np.sum(r * r0))
+            A = 0.5 * np.sum(stats.norm.logpdf(t, v / (1 + s), 1.5)) - r @ r + (np.log(s) - 2 * s) + u[2]
+            return A, -0.5 * (v @ t) ** 2 / 100
+    src = SC.generate(text, data)
+    assert src.dim == dim
+    h = HostModel(src, tmp_path)
+    x = np.random.default_rng(3).normal(size=(30, dim)) * 0.6
+    A, B, g = h.split(x, 0.4)
+    ref = np.array([restated(u) for u in x])
+    np.testing.assert_allclose(A, ref[:, 0], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(B, ref[:, 1], rtol=1e-11, atol=1e-11)
+    _fd_check(h, x, g, 0.4, dim)
+
+
 def test_unsupported_constructs_fail_loudly_with_the_line():
     ok = "data { int N; } parameters { real a; } model { a ~ normal(0, 1); }"
     assert SC.generate(ok, {"N": 3}).dim == 1
