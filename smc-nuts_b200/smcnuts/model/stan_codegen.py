@@ -26,11 +26,13 @@ Supported subset (anything else raises StanSubsetError with the offending line):
   with initialisers, =, +=, -=, *=, /=, `target +=`, `~`, for loops, if / else (conditions on data, loop variables or
   parameter values; && || !), blocks;
   + - * / ^ .* ./, unary minus, indexing, exp log log1p sqrt fabs abs square inv inv_logit log1p_exp log_sum_exp(a, b)
-  pow tanh sin cos lgamma(data only);  container-valued expressions: elementwise arithmetic and functions, matrix *
-  vector, row_vector * vector, row_vector * matrix, sum mean dot_product dot_self rep_vector rep_row_vector rep_array,
+  pow tanh sin cos lgamma (of data: tabulated at generation time; of parameters: differentiated with a digamma series);
+  container-valued expressions: elementwise arithmetic and functions, matrix * vector, row_vector * vector,
+  row_vector * matrix, sum mean dot_product dot_self rep_vector rep_row_vector rep_array,
   whole-container assignment -- lowered onto element loops and accumulator locals of the scalar subset (`lower_stmt`);
   normal, std_normal, cauchy, student_t, double_exponential, logistic, lognormal, exponential, gamma, inv_gamma, weibull,
-  beta, uniform densities; poisson, poisson_log, bernoulli, bernoulli_logit, binomial, binomial_logit mass functions --
+  beta, uniform densities; poisson, poisson_log, bernoulli, bernoulli_logit, binomial, binomial_logit, neg_binomial_2,
+  neg_binomial_2_log mass functions --
   scalar or vectorised over container arguments and container-valued argument expressions.
 """
 import json
@@ -460,6 +462,13 @@ _DENSITIES = {
     "uniform": lambda y, a, b: [_un("neg", _log(_sub(b, a)))],
     "poisson": lambda k, lam: [_mul(k, _log(lam)), _un("neg", lam), _un("neg", _un("lgamma", _add(k, _const(1.0))))],
     "poisson_log": lambda k, eta: [_mul(k, eta), _un("neg", _un("exp", eta)), _un("neg", _un("lgamma", _add(k, _const(1.0))))],
+    "neg_binomial_2": lambda k, mu, ph: [
+        _sub(_un("lgamma", _add(k, ph)), _un("lgamma", ph)), _un("neg", _un("lgamma", _add(k, _const(1.0)))),
+        _mul(k, _sub(_log(mu), _log(_add(mu, ph)))), _mul(ph, _sub(_log(ph), _log(_add(mu, ph))))],
+    "neg_binomial_2_log": lambda k, eta, ph: [
+        _sub(_un("lgamma", _add(k, ph)), _un("lgamma", ph)), _un("neg", _un("lgamma", _add(k, _const(1.0)))),
+        _mul(k, _sub(eta, _add(eta, _un("log1p_exp", _sub(_log(ph), eta))))),
+        _mul(ph, _sub(_log(ph), _add(eta, _un("log1p_exp", _sub(_log(ph), eta)))))],
     "bernoulli": lambda k, p: [_mul(k, _log(p)), _mul(_sub(_const(1.0), k), _un("log1p", _un("neg", p)))],
     "bernoulli_logit": lambda k, eta: [_mul(k, eta), _un("neg", _un("log1p_exp", eta))],
     "binomial_logit": lambda k, n, eta: [_sub(_un("lgamma", _add(n, _const(1.0))),
@@ -1003,8 +1012,6 @@ class _Gen:
                 if n.kind == "un":
                     text = {"neg": f"-{a[0]}", "inv_logit": f"smcgen_inv_logit({a[0]})", "log1p_exp": f"smcgen_log1p_exp({a[0]})"}.get(
                         n.op, f"{n.op}({a[0]})")
-                    if n.op == "lgamma" and n.deps:
-                        raise StanSubsetError("lgamma of a parameter-dependent argument is outside the supported subset (no digamma)")
                 elif n.op == "^":
                     text = f"sqrt({a[0]})" if _is_const(n.args[1], 0.5) else f"pow({a[0]}, {a[1]})"
                 else:
@@ -1039,6 +1046,7 @@ class _Gen:
                 push(n.args[0], {"neg": "(-1.0)", "exp": v, "log": f"(1.0 / {x})", "log1p": f"(1.0 / (1.0 + {x}))",
                                  "sqrt": f"(0.5 / {v})", "fabs": f"copysign(1.0, {x})", "tanh": f"(1.0 - {v} * {v})",
                                  "sin": f"cos({x})", "cos": f"(-sin({x}))", "inv_logit": f"({v} * (1.0 - {v}))",
+                                 "lgamma": f"smcgen_digamma({x})",
                                  "log1p_exp": f"smcgen_inv_logit({x})"}[n.op])
             elif n.op == "+":
                 push(n.args[0], None); push(n.args[1], None)
@@ -1369,6 +1377,14 @@ class _Gen:
 #define SMCGEN_HELPERS
 SMCB_HD double smcgen_inv_logit(double z) {{ return z >= 0.0 ? 1.0 / (1.0 + exp(-z)) : exp(z) / (1.0 + exp(z)); }}
 SMCB_HD double smcgen_log1p_exp(double z) {{ return (z > 0.0 ? z : 0.0) + log1p(exp(-fabs(z))); }}
+// d/dx lgamma(x) for x > 0: upward recurrence to x >= 10, then the asymptotic series (next term 691/32760 x^-12 < 3e-14)
+SMCB_HD double smcgen_digamma(double x) {{
+    double r = 0.0;
+    while (x < 10.0) {{ r -= 1.0 / x; x += 1.0; }}
+    const double f = 1.0 / (x * x);
+    return r + log(x) - 0.5 / x
+           - f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132)))));
+}}
 #endif
 struct {self.struct_name} {{
     static constexpr int DMAX = {D}, STATIC_D = {D};
