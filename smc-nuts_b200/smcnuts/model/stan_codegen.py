@@ -432,22 +432,28 @@ def _log(a):
     return _un("log", a)
 
 
+def _z(y, m, s):
+    """(y - m) / s as a product with the reciprocal scale -- Stan Math's own arithmetic (inv_sigma), and the reciprocal
+    of a parameter-only scale is computed once per evaluation instead of one division per observation"""
+    return _mul(_sub(y, m), _div(_const(1.0), s))
+
+
 _LOG_2PI, _LOG_PI = math.log(2.0 * math.pi), math.log(math.pi)
 
 # log densities as sums of terms (each a Node): Stan's definitions with every normalising constant
 _DENSITIES = {
-    "normal": lambda y, m, s: [_const(-0.5 * _LOG_2PI), _un("neg", _log(s)), _mul(_const(-0.5), _bin("^", _div(_sub(y, m), s), _const(2.0)))],
-    "cauchy": lambda y, m, s: [_const(-_LOG_PI), _un("neg", _log(s)), _un("neg", _un("log1p", _bin("^", _div(_sub(y, m), s), _const(2.0))))],
-    "double_exponential": lambda y, m, s: [_const(-math.log(2.0)), _un("neg", _log(s)), _un("neg", _div(_un("fabs", _sub(y, m)), s))],
+    "normal": lambda y, m, s: [_const(-0.5 * _LOG_2PI), _un("neg", _log(s)), _mul(_const(-0.5), _bin("^", _z(y, m, s), _const(2.0)))],
+    "cauchy": lambda y, m, s: [_const(-_LOG_PI), _un("neg", _log(s)), _un("neg", _un("log1p", _bin("^", _z(y, m, s), _const(2.0))))],
+    "double_exponential": lambda y, m, s: [_const(-math.log(2.0)), _un("neg", _log(s)), _un("neg", _mul(_un("fabs", _sub(y, m)), _div(_const(1.0), s)))],
     "lognormal": lambda y, m, s: [_const(-0.5 * _LOG_2PI), _un("neg", _log(s)), _un("neg", _log(y)),
-                                  _mul(_const(-0.5), _bin("^", _div(_sub(_log(y), m), s), _const(2.0)))],
+                                  _mul(_const(-0.5), _bin("^", _z(_log(y), m, s), _const(2.0)))],
     "student_t": lambda y, nu, m, s: [_sub(_un("lgamma", _mul(_const(0.5), _add(nu, _const(1.0)))), _un("lgamma", _mul(_const(0.5), nu))),
                                       _mul(_const(-0.5), _log(_mul(nu, _const(math.pi)))), _un("neg", _log(s)),
                                       _un("neg", _mul(_mul(_const(0.5), _add(nu, _const(1.0))),
-                                                      _un("log1p", _div(_bin("^", _div(_sub(y, m), s), _const(2.0)), nu))))],
+                                                      _un("log1p", _div(_bin("^", _z(y, m, s), _const(2.0)), nu))))],
     "std_normal": lambda y: [_const(-0.5 * _LOG_2PI), _mul(_const(-0.5), _bin("^", y, _const(2.0)))],
-    "logistic": lambda y, m, s: [_un("neg", _log(s)), _un("neg", _div(_sub(y, m), s)),
-                                 _mul(_const(-2.0), _un("log1p_exp", _un("neg", _div(_sub(y, m), s))))],
+    "logistic": lambda y, m, s: [_un("neg", _log(s)), _un("neg", _z(y, m, s)),
+                                 _mul(_const(-2.0), _un("log1p_exp", _un("neg", _z(y, m, s))))],
     "weibull": lambda y, a, s: [_sub(_log(a), _log(s)), _mul(_sub(a, _const(1.0)), _sub(_log(y), _log(s))),
                                 _un("neg", _bin("^", _div(y, s), a))],
     "binomial": lambda k, n, p: [_sub(_un("lgamma", _add(n, _const(1.0))),
@@ -510,6 +516,7 @@ class _Gen:
         self.lowered = {}       # id(statement) -> its scalar-subset replacement (list of statements) or None
         self.fresh = 0
         self.decl_init = {}     # id(declaration with an initialiser) -> its assignment statement
+        self.hoisted, self.prologue = {}, []   # expression text -> name of its once-per-evaluation constant; their definitions
         self.outer_pre = None   # while a statement is being lowered: where its loop-invariant scalar reductions go
         self.data_in = dict(data)
         self.vars = {}          # name -> _Var
@@ -965,6 +972,14 @@ class _Gen:
     def emit(self, text):
         self.lines.append("    " * self.indent + text)
 
+    def hoist(self, text):
+        """Name of the once-per-evaluation constant `text` (an expression of parameters and literals only)."""
+        nm = self.hoisted.get(text)
+        if nm is None:
+            nm = self.hoisted[text] = f"h{len(self.hoisted) + 1}"
+            self.prologue.append(f"const double {nm} = {text};")
+        return nm
+
     def new_tmp(self, prefix="t"):
         self.tmp += 1
         return f"{prefix}{self.tmp}"
@@ -996,7 +1011,11 @@ class _Gen:
         -> (value C name, [(leaf node, adjoint C text)])"""
         order = self.topo(root)
         name = {}
+        fixed = {}       # nodes built from constants and parameters at constant indices only: the same value throughout one
+        #                  evaluation, so they are computed once in the prologue of eval() and shared (log(sigma), 1 / sigma ...)
         for n in order:
+            fixed[id(n)] = (n.kind == "const" or (n.kind == "param" and n.val is not None)
+                            or (n.kind in ("un", "bin") and all(fixed[id(a)] for a in n.args)))
             if n.kind == "const":
                 name[id(n)] = self.lit(n.val)
             elif n.kind == "param":
@@ -1016,6 +1035,9 @@ class _Gen:
                     text = f"sqrt({a[0]})" if _is_const(n.args[1], 0.5) else f"pow({a[0]}, {a[1]})"
                 else:
                     text = f"{a[0]} {n.op} {a[1]}"
+                if fixed[id(n)]:
+                    name[id(n)] = self.hoist(text)
+                    continue
                 t = self.new_tmp()
                 self.emit(f"const double {t} = {text};")
                 name[id(n)] = t
@@ -1037,13 +1059,17 @@ class _Gen:
             v = name[id(n)]
             xs = [name[id(x)] for x in n.args]
 
+            def recip(k):
+                return self.hoist(f"1.0 / {xs[k]}") if fixed[id(n.args[k])] else f"(1.0 / {xs[k]})"
+
             def push(child, factor):
                 if child.deps:
                     term = a_text if factor is None else factor if a_text == "1.0" else f"{a_text} * {factor}"
                     adj.setdefault(id(child), []).append(term)
             if n.kind == "un":
                 x = xs[0]
-                push(n.args[0], {"neg": "(-1.0)", "exp": v, "log": f"(1.0 / {x})", "log1p": f"(1.0 / (1.0 + {x}))",
+                push(n.args[0], recip(0) if n.op == "log" else
+                     {"neg": "(-1.0)", "exp": v, "log1p": f"(1.0 / (1.0 + {x}))",
                                  "sqrt": f"(0.5 / {v})", "fabs": f"copysign(1.0, {x})", "tanh": f"(1.0 - {v} * {v})",
                                  "sin": f"cos({x})", "cos": f"(-sin({x}))", "inv_logit": f"({v} * (1.0 - {v}))",
                                  "lgamma": f"smcgen_digamma({x})",
@@ -1055,7 +1081,7 @@ class _Gen:
             elif n.op == "*":
                 push(n.args[0], xs[1]); push(n.args[1], xs[0])
             elif n.op == "/":
-                push(n.args[0], f"(1.0 / {xs[1]})"); push(n.args[1], f"(-{v} / {xs[1]})")
+                push(n.args[0], recip(1)); push(n.args[1], f"(-{v} * {recip(1)})")
             elif n.op == "^":
                 if _is_const(n.args[1], 0.5):
                     push(n.args[0], f"(0.5 / {v})")
@@ -1344,7 +1370,7 @@ class _Gen:
                 if v.deps:
                     self.emit(f"double d_{v.name}{dims}[{max(v.deps) + 1}]{' = {{0.0}}' if v.shape else ' = {0.0}'};")
         self.statements(self.blocks["model"], emit=True)
-        body = "\n".join(self.lines[body_start:])
+        body = "\n".join(["        " + ln for ln in self.prologue] + self.lines[body_start:])
         return self.wrap(body)
 
     def _const_value(self, e, line):
