@@ -485,6 +485,148 @@ _UNARY_FUNCS = {"exp": "exp", "log": "log", "log1p": "log1p", "sqrt": "sqrt", "f
                 "tanh": "tanh", "sin": "sin", "cos": "cos", "inv_logit": "inv_logit", "log1p_exp": "log1p_exp"}
 
 
+# ------------------------------------------------------------------------------------------------ scalar replacement
+def _walk_exprs(e, fn):
+    """fn(sub-expression) for every expression node under `e` (tuples whose first item is a node kind)"""
+    if isinstance(e, tuple) and e and isinstance(e[0], str):
+        fn(e)
+        for x in e[1:]:
+            _walk_exprs(x, fn)
+    elif isinstance(e, (list, tuple)):
+        for x in e:
+            _walk_exprs(x, fn)
+
+
+def _key(e):
+    """Structural identity of an expression, source lines left out"""
+    if isinstance(e, tuple) and e and isinstance(e[0], str):
+        if e[0] == "var":
+            return ("var", e[1])
+        if e[0] == "call":
+            return ("call", e[1], _key(e[2]))
+        return tuple(_key(x) for x in e)
+    if isinstance(e, (list, tuple)):
+        return tuple(_key(x) for x in e)
+    return e
+
+
+def _demote_arrays(stmts):
+    """Local arrays that are only ever read at the element written LAST (same index expression, no other element written
+    in between, not across loop trips) -- `mu[n] = ...; y[n] ~ normal(mu[n], s);` inside a loop -- never need to be
+    arrays: they become scalars, which keeps their values and sensitivities in registers instead of per-thread local
+    memory (whole-series ARMA at N = 2^18: see profiles/r2_generated_models_*.log).  Returns the rewritten statements."""
+    arrays, bad = {}, set()
+
+    def find_decls(ss):
+        for st in ss:
+            if st[0] == "decl" and st[1][2]:
+                name = st[1][0]
+                if name in arrays or st[1][5] is not None:
+                    bad.add(name)
+                arrays[name] = st
+            elif st[0] == "block":
+                find_decls(st[1])
+            elif st[0] == "for":
+                find_decls(st[4])
+            elif st[0] == "if":
+                find_decls([x for x in (st[2], st[3]) if x is not None])
+    find_decls(stmts)
+    if not arrays:
+        return stmts
+
+    def reads(e, last):
+        whole, indexed = [], []
+
+        def visit(x):
+            if x[0] == "idx" and x[1][0] == "var" and x[1][1] in arrays:
+                indexed.append(id(x[1]))
+                if last.get(x[1][1]) != _key(x[2]):      # the latest write went to another (or an unknown) element
+                    bad.add(x[1][1])
+            elif x[0] == "var" and x[1] in arrays:
+                whole.append(x)
+        _walk_exprs(e, visit)
+        for x in whole:                                  # a bare name that is not the base of an index: whole-container use
+            if id(x) not in indexed:
+                bad.add(x[1])
+
+    def written_in(ss, out):
+        for st in ss:
+            if st[0] == "assign":
+                lhs = st[1]
+                base = lhs if lhs[0] == "var" else lhs[1]
+                if base[0] == "var" and base[1] in arrays:
+                    out.add(base[1])
+            elif st[0] == "block":
+                written_in(st[1], out)
+            elif st[0] == "for":
+                written_in(st[4], out)
+            elif st[0] == "if":
+                written_in([x for x in (st[2], st[3]) if x is not None], out)
+        return out
+
+    def child(ss, last, repeated):
+        """a statement list that runs conditionally or repeatedly: on entry of a repeated one the elements written inside
+        hold whatever the previous trip left; on exit the parent no longer knows which element was written last"""
+        inner = dict(last)
+        touched = written_in(ss, set())
+        if repeated:
+            for v in touched:
+                inner[v] = None
+        scan(ss, inner)
+        for v in touched:
+            last[v] = None
+
+    def scan(ss, last):
+        for st in ss:
+            k = st[0]
+            if k == "decl":
+                if st[1][5] is not None:
+                    reads(st[1][5], last)
+            elif k == "block":
+                scan(st[1], last)
+            elif k == "for":
+                reads((st[2], st[3]), last)
+                child(st[4], last, True)
+            elif k == "if":
+                reads(st[1], last)
+                child([st[2]], last, False)
+                if st[3] is not None:
+                    child([st[3]], last, False)
+            elif k == "target":
+                reads(st[1], last)
+            elif k == "tilde":
+                reads((st[1], st[3]), last)
+            elif k == "assign":
+                _, lhs, op, rhs, _ = st
+                reads(rhs, last)
+                if lhs[0] == "idx" and lhs[1][0] == "var" and lhs[1][1] in arrays:
+                    reads(lhs[2], last)
+                    if op != "=":
+                        reads(lhs, last)
+                    last[lhs[1][1]] = _key(lhs[2])
+                else:
+                    reads(lhs, last)          # a whole-container assignment (or a scalar): counts as a whole use
+    scan(stmts, {})
+    names = set(arrays) - bad
+    if not names:
+        return stmts
+
+    def rewrite(e):
+        if isinstance(e, tuple) and e and isinstance(e[0], str):
+            if e[0] == "idx" and e[1][0] == "var" and e[1][1] in names:
+                return e[1]
+            if e[0] == "decl" and e[1][0] in names:
+                d = e[1]
+                return ("decl", (d[0], d[1], [], d[3], d[4], d[5], d[6]), e[2])
+            return tuple(rewrite(x) for x in e)
+        if isinstance(e, list):
+            return [rewrite(x) for x in e]
+        if isinstance(e, tuple):
+            return tuple(rewrite(x) for x in e)
+        return e
+    return rewrite(stmts)
+
+
 # ------------------------------------------------------------------------------------------------ lowering + emission
 class _Var:
     """A data array, parameter or model-block local."""
@@ -1352,7 +1494,7 @@ class _Gen:
             else:
                 program.append(st)
         program += self.blocks.get("transformed parameters", [])
-        self.blocks["model"] = program + self.blocks["model"]
+        self.blocks["model"] = _demote_arrays(program + self.blocks["model"])
         # activity analysis (which coordinates can each local depend on): fixpoint over the statement list
         for _ in range(64):
             self.changed = False

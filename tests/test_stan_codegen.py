@@ -405,6 +405,27 @@ def test_generated_densities_with_parameter_dependent_shapes_use_the_digamma_ser
     _fd_check(h, x, g, 0.8, 5, tol=2e-5)
 
 
+def test_local_arrays_become_scalars_only_when_every_read_sees_the_latest_write(tmp_path):
+    """Scalar replacement of model-block arrays (values and sensitivities in registers instead of per-thread local
+    memory): applied to `v[t] = ...; use v[t]`, refused when another element is read, when the write sits in a branch and
+    for loop-carried reads -- and the refused program still evaluates correctly."""
+    import re
+
+    def arrays(text):
+        return sorted(set(re.findall(r"double (v_\w+)\[\d+\]", SC.generate(text, {"T": 5}).text)))
+    head = "data { int T; } parameters { real a; } model { vector[T] v; "
+    reads_other = head + "v[1] = a; for (t in 2:T) { v[t] = v[1] + t; target += -v[t] * v[t]; } }"
+    assert arrays(reads_other) == ["v_v"]
+    assert arrays(head + "v[1] = a; target += -v[1] * v[1]; for (t in 2:T) { v[t] = a + t; target += -v[t] * v[t]; } }") == []
+    assert arrays(head + "for (t in 1:T) { if (t < 3) v[t] = a; else v[t] = 2 * a; target += -v[t] * v[t]; } }") == ["v_v"]
+    assert arrays(head + "v[1] = a; for (t in 2:T) { v[t] = v[t - 1] * 0.5; target += -v[t]; } }") == ["v_v"]
+    h = HostModel(SC.generate(reads_other, {"T": 5}), tmp_path)
+    x = np.linspace(-1.0, 1.0, 7)[:, None]
+    A, B, g = h.split(x, 1.0)
+    np.testing.assert_allclose(A, -sum((x[:, 0] + t) ** 2 for t in range(2, 6)), rtol=1e-14)
+    np.testing.assert_allclose(g[:, 0], -sum(2 * (x[:, 0] + t) for t in range(2, 6)), rtol=1e-14)
+
+
 def test_unsupported_constructs_fail_loudly_with_the_line():
     ok = "data { int N; } parameters { real a; } model { a ~ normal(0, 1); }"
     assert SC.generate(ok, {"N": 3}).dim == 1
