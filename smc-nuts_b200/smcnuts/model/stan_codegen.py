@@ -1547,6 +1547,7 @@ SMCB_HD double smcgen_inv_logit(double z) {{ return z >= 0.0 ? 1.0 / (1.0 + exp(
 SMCB_HD double smcgen_log1p_exp(double z) {{ return (z > 0.0 ? z : 0.0) + log1p(exp(-fabs(z))); }}
 // d/dx lgamma(x) for x > 0: upward recurrence to x >= 10, then the asymptotic series (next term 691/32760 x^-12 < 3e-14)
 SMCB_HD double smcgen_digamma(double x) {{
+    if (!(x > 0.0)) return NAN;          // Stan rejects such shapes; also keeps the recurrence below bounded (10 trips at most)
     double r = 0.0;
     while (x < 10.0) {{ r -= 1.0 / x; x += 1.0; }}
     const double f = 1.0 / (x * x);
