@@ -510,6 +510,32 @@ def _key(e):
     return e
 
 
+def _flat(ss):
+    """the statements of a list with plain blocks opened up (a block runs once, in order)"""
+    out = []
+    for st in ss:
+        out += _flat(st[1]) if st[0] == "block" else [st]
+    return out
+
+
+def _assigned_names(ss, out):
+    """names of all variables assigned anywhere under the statement list"""
+    for st in ss:
+        if st[0] == "assign":
+            base = st[1] if st[1][0] == "var" else st[1][1]
+            if base[0] == "var":
+                out.add(base[1])
+        elif st[0] == "block":
+            _assigned_names(st[1], out)
+        elif st[0] == "for":
+            _assigned_names(st[4], out)
+        elif st[0] == "if":
+            _assigned_names([x for x in (st[2], st[3]) if x is not None], out)
+        elif st[0] == "decl" and st[1][5] is not None:
+            out.add(st[1][0])
+    return out
+
+
 def _demote_arrays(stmts):
     """Local arrays that are only ever read at the element written LAST (same index expression, no other element written
     in between, not across loop trips) -- `mu[n] = ...; y[n] ~ normal(mu[n], s);` inside a loop -- never need to be
@@ -564,14 +590,23 @@ def _demote_arrays(stmts):
                 written_in([x for x in (st[2], st[3]) if x is not None], out)
         return out
 
-    def child(ss, last, repeated):
+    def child(ss, last, repeated, loop=None):
         """a statement list that runs conditionally or repeatedly: on entry of a repeated one the elements written inside
-        hold whatever the previous trip left; on exit the parent no longer knows which element was written last"""
+        hold whatever the previous trip left; on exit the parent no longer knows which element was written last.
+        The one recurrence that is tracked: `for (t in lo:hi)` whose body writes V exactly once, unconditionally, at V[t],
+        with V[lo - 1] the latest write before the loop -- then V[t - 1] is the latest write on entry of every trip."""
         inner = dict(last)
         touched = written_in(ss, set())
         if repeated:
+            flat = _flat(ss)
+            nested = written_in([st for st in flat if st[0] != "assign"], set())
             for v in touched:
                 inner[v] = None
+                tops = [st for st in flat if st[0] == "assign" and (st[1] if st[1][0] == "var" else st[1][1])[1:2] == (v,)]
+                if (loop is not None and v not in nested and len(tops) == 1 and tops[0][1][0] == "idx" and tops[0][2] == "="
+                        and _key(tops[0][1][2]) == (("var", loop[0]),) and loop[1][0] == "num"
+                        and last.get(v) == (("num", loop[1][1] - 1.0, True),)):
+                    inner[v] = (("bin", "-", ("var", loop[0]), ("num", 1.0, True)),)
         scan(ss, inner)
         for v in touched:
             last[v] = None
@@ -586,7 +621,7 @@ def _demote_arrays(stmts):
                 scan(st[1], last)
             elif k == "for":
                 reads((st[2], st[3]), last)
-                child(st[4], last, True)
+                child(st[4], last, True, loop=(st[1], st[2]))
             elif k == "if":
                 reads(st[1], last)
                 child([st[2]], last, False)
@@ -1090,6 +1125,131 @@ class _Gen:
             return pre + loops
         return None
 
+    # ---- a vectorised density over a local vector, moved to where the elements are produced ---------------------------
+    def fuse_vector_densities(self, stmts):
+        """`for (t in 2:T) { ...; err[t] = ...; }  target += phi * normal_lpdf(err | 0, sigma);` (the Stan manual's ARMA and
+        most time-series programs) stores the whole series and its sensitivities per thread only to read them back once.
+        When every element of the vector is written exactly once -- by constant-index assignments and by ONE loop that
+        assigns V[t] unconditionally -- and the other density arguments involve no model-block local, the density
+        statement is applied element by element right after each write instead; the array then usually reduces to a
+        scalar (_demote_arrays).  Only the order in which terms are added to the accumulators changes."""
+        stmts = list(stmts)
+        locals_ = {}
+        for st in stmts:
+            if st[0] == "decl":
+                locals_[st[1][0]] = st
+        all_locals = set()
+
+        def collect(ss):
+            for st in ss:
+                if st[0] == "decl":
+                    all_locals.add(st[1][0])
+                elif st[0] == "block":
+                    collect(st[1])
+                elif st[0] == "for":
+                    collect(st[4])
+                elif st[0] == "if":
+                    collect([x for x in (st[2], st[3]) if x is not None])
+        collect(stmts)
+        m = 0
+        while m < len(stmts):
+            fused = self._fuse_one(stmts, m, locals_, all_locals)
+            if fused is None:
+                m += 1
+            else:
+                stmts = fused
+                m = 0
+        return stmts
+
+    def _fuse_one(self, stmts, m, locals_, all_locals):
+        st = stmts[m]
+        line = st[-1]
+        if st[0] == "target":
+            tempered, e = self.scale_split(st[1])
+            mm = re.fullmatch(r"(\w+?)_(lpdf|lpmf|log)", e[1]) if e[0] == "call" else None
+            if not (mm and mm.group(1) in _DENSITIES):
+                return None
+            args = list(e[2])
+        elif st[0] == "tilde":
+            args = [st[1]] + list(st[3])
+        else:
+            return None
+        whole = [a for a in args if a[0] == "var" and a[1] in locals_ and len(locals_[a[1]][1][2]) == 1
+                 and locals_[a[1]][1][5] is None]
+        if len(whole) != 1:
+            return None
+        V = whole[0][1]
+        n = self.int_expr(locals_[V][1][2][0])[0]
+        if n is None:
+            return None
+        kinds = []           # per argument: "V", "container" (whole data / parameter vector: indexed too) or "scalar"
+        for a in args:
+            if a is whole[0]:
+                kinds.append("V")
+                continue
+            names = []
+            _walk_exprs(a, lambda x: names.append(x[1]) if x[0] == "var" else None)
+            if any(nm in all_locals for nm in names):
+                return None
+            v = self.vars.get(a[1]) if a[0] == "var" else None
+            if v is not None and v.shape:
+                if v.shape != [n]:
+                    return None
+                kinds.append("container")
+            else:
+                try:
+                    if self.shape(a)[0]:
+                        return None          # container-valued expression: left to the lowering pass
+                except StanSubsetError:
+                    return None
+                kinds.append("scalar")
+
+        def element(ix):
+            a2 = [("idx", a, [ix]) if k != "scalar" else a for a, k in zip(args, kinds)]
+            if st[0] == "tilde":
+                return ("tilde", a2[0], st[2], a2[1:], line)
+            call = ("call", e[1], a2, e[3])
+            return ("target", ("bin", "*", ("var", "phi", line), call) if tempered else call, line)
+        # the writes of V ahead of the statement
+        covered, out, loops = [], [], 0
+        for j, sj in enumerate(stmts[:m]):
+            if V not in _assigned_names([sj], set()):
+                out.append(sj)
+                continue
+            if (sj[0] == "assign" and sj[2] == "=" and sj[1][0] == "idx" and len(sj[1][2]) == 1 and sj[1][2][0][0] == "num"
+                    and sj[1][2][0][2]):
+                c = int(sj[1][2][0][1])
+                covered.append(c)
+                out += [sj, element(("num", float(c), True))]
+                continue
+            if sj[0] != "for":
+                return None
+            lo, hi = self.int_expr(sj[2])[0], self.int_expr(sj[3])[0]
+            if lo is None or hi is None or loops:
+                return None
+            loops += 1
+            flat = _flat(sj[4])
+            tops = [x for x in flat if x[0] == "assign" and (x[1] if x[1][0] == "var" else x[1][1])[1:2] == (V,)]
+            if (len(tops) != 1 or V in _assigned_names([x for x in flat if x[0] != "assign"], set()) or tops[0][2] != "="
+                    or tops[0][1][0] != "idx" or _key(tops[0][1][2]) != (("var", sj[1]),)):
+                return None
+            covered += list(range(lo, hi + 1))
+
+            def with_element(ss):
+                res = []
+                for x in ss:
+                    if x is tops[0]:
+                        res += [x, element(("var", sj[1], line))]
+                    elif x[0] == "block":
+                        res.append(("block", with_element(x[1]), x[2]))
+                    else:
+                        res.append(x)
+                return res
+            out.append(("for", sj[1], sj[2], sj[3], with_element(sj[4]), sj[5]))
+        if sorted(covered) != list(range(1, n + 1)):
+            return None
+        return out + stmts[m + 1:]
+
     # ---- conditions of `if`
     def cond_text(self, c, line):
         if c[0] in ("lor", "land"):
@@ -1494,7 +1654,7 @@ class _Gen:
             else:
                 program.append(st)
         program += self.blocks.get("transformed parameters", [])
-        self.blocks["model"] = _demote_arrays(program + self.blocks["model"])
+        self.blocks["model"] = _demote_arrays(self.fuse_vector_densities(program + self.blocks["model"]))
         # activity analysis (which coordinates can each local depend on): fixpoint over the statement list
         for _ in range(64):
             self.changed = False

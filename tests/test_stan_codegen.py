@@ -49,6 +49,7 @@ class HostModel:
     """The generated struct compiled for the host (the same text nvcc compiles for the device)."""
 
     def __init__(self, src, tmp_path):
+        tmp_path.mkdir(parents=True, exist_ok=True)
         (tmp_path / "model_gen.h").write_text(src.text)
         (tmp_path / "host.cpp").write_text(HOST_HARNESS)
         so = tmp_path / "libgen.so"
@@ -418,12 +419,62 @@ def test_local_arrays_become_scalars_only_when_every_read_sees_the_latest_write(
     assert arrays(reads_other) == ["v_v"]
     assert arrays(head + "v[1] = a; target += -v[1] * v[1]; for (t in 2:T) { v[t] = a + t; target += -v[t] * v[t]; } }") == []
     assert arrays(head + "for (t in 1:T) { if (t < 3) v[t] = a; else v[t] = 2 * a; target += -v[t] * v[t]; } }") == ["v_v"]
-    assert arrays(head + "v[1] = a; for (t in 2:T) { v[t] = v[t - 1] * 0.5; target += -v[t]; } }") == ["v_v"]
+    # the previous element is the latest write on entry of every trip: a rolling scalar ...
+    rolling = head + "v[1] = a; for (t in 2:T) { v[t] = v[t - 1] * 0.5 + t; target += -v[t] * v[t - 1]; } }"
+    assert arrays(rolling.replace(" * v[t - 1]", "")) == []
+    assert arrays(rolling) == ["v_v"]            # ... unless it is read again after this trip's write
+    assert arrays(head + "v[2] = a; for (t in 2:T) { v[t] = v[t - 1] * 0.5; target += -v[t]; } }") == ["v_v"]
+    hr = HostModel(SC.generate(rolling.replace(" * v[t - 1]", ""), {"T": 5}), tmp_path / "r")
     h = HostModel(SC.generate(reads_other, {"T": 5}), tmp_path)
     x = np.linspace(-1.0, 1.0, 7)[:, None]
+    Ar, _, gr = hr.split(x, 1.0)
+    v, dv, want, dwant = x[:, 0].copy(), np.ones(7), 0.0, 0.0
+    for t in range(2, 6):
+        v, dv = v * 0.5 + t, dv * 0.5
+        want, dwant = want - v, dwant - dv
+    np.testing.assert_allclose(Ar, want, rtol=1e-14)
+    np.testing.assert_allclose(gr[:, 0], dwant, rtol=1e-14)
     A, B, g = h.split(x, 1.0)
     np.testing.assert_allclose(A, -sum((x[:, 0] + t) ** 2 for t in range(2, 6)), rtol=1e-14)
     np.testing.assert_allclose(g[:, 0], -sum(2 * (x[:, 0] + t) for t in range(2, 6)), rtol=1e-14)
+
+
+def test_trailing_vectorised_density_is_fused_into_the_loop_that_fills_its_vector(tmp_path):
+    """`for (t in 2:T) { ...; resid[t] = ...; }  target += phi * normal_lpdf(resid | 0, sigma);` keeps no per-thread series:
+    the density is applied where each element is written and the vectors reduce to rolling scalars; programs where that
+    would be wrong (an argument that is a model-block local, elements written twice or not at all by the recognised
+    writes) keep their arrays -- and all of them evaluate to the same numbers."""
+    import re
+    src = SC.generate((STAN / "arma_series.stan").read_text(), _arma_data())
+    assert not re.findall(r"double v_\w+\[\d+\]", src.text)
+    h = HostModel(src, tmp_path / "series")       # one directory per library: dlopen caches by path
+    t = O.COracleTarget("arma")
+    x = np.random.default_rng(1).normal(size=(200, 4)) * 0.7
+    A, B, g = h.split(x, 0.37)
+    Ao, Bo, _, _ = t.split(x, grads=False)
+    np.testing.assert_allclose(A, Ao, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(B, Bo, rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(g, t.logpdfgrad(x, 0.37), rtol=1e-9, atol=1e-8)
+    # not fusable: the scale is a local assigned after the loop / element 1 is never written / element 2 is written twice
+    head = "data { int T; vector[T] y; } parameters { real a; real<lower=0> s; } model { vector[T] v; "
+    loop = "for (t in 2:T) { v[t] = y[t] - a * v[t - 1]; } "
+    variants = {
+        "fused": head + "v[1] = y[1]; " + loop + "target += normal_lpdf(v | 0, s); }",
+        "local scale": head + "real s2; v[1] = y[1]; " + loop + "s2 = 2 * s; target += normal_lpdf(v | 0, s2 / 2); }",
+        "twice": head + "v[1] = y[1]; v[2] = 0; " + loop + "target += normal_lpdf(v | 0, s); }",
+    }
+    data = {"T": 6, "y": np.random.default_rng(2).normal(size=6).tolist()}
+    xs = np.random.default_rng(3).normal(size=(20, 2)) * 0.5
+    results = {}
+    for name, text in variants.items():
+        sv = SC.generate(text, data)
+        assert bool(re.findall(r"double v_v\[\d+\]", sv.text)) == (name != "fused"), name
+        results[name] = HostModel(sv, tmp_path / name.replace(" ", "_")).split(xs, 1.0)
+    for name in ("local scale", "twice"):
+        for got, want in zip(results[name], results["fused"]):
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13)
+    # an element that no recognised write covers: not fused either (Stan would report the NaN element at run time)
+    assert re.findall(r"double v_v\[\d+\]", SC.generate(head + loop + "target += normal_lpdf(v | 0, s); }", data).text)
 
 
 def test_unsupported_constructs_fail_loudly_with_the_line():

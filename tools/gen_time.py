@@ -3,8 +3,8 @@
     python tools/gen_time.py [log2N] [reps]
 
 Two phrasings of the same ARMA(1,1) density: rolling scalars (tests/stan/arma11.stan) and whole-series vector locals with
-one vectorised likelihood statement at the end (the Stan manual's style), which costs per-thread local arrays of values
-and sensitivities.
+one vectorised likelihood statement at the end (tests/stan/arma_series.stan, the Stan manual's style), which costs
+per-thread local arrays of values and sensitivities unless the generator fuses the likelihood into the loop.
 """
 import json
 import sys
@@ -20,22 +20,7 @@ from smcnuts.model.device_model import make_model  # noqa: E402
 from smcnuts.model.generated import GeneratedModel  # noqa: E402
 from smcnuts.proposal.nuts import NUTSProposal  # noqa: E402
 
-WHOLE_SERIES = """
-data { int<lower=2> T; vector[T] y; real<lower=0, upper=1> phi; }
-parameters { real mu; real beta; real theta; real<lower=0> sigma; }
-model {
-  vector[T] pred;
-  vector[T] resid;
-  target += normal_lpdf(mu | 0, 10) + normal_lpdf(beta | 0, 2) + normal_lpdf(theta | 0, 2) + cauchy_lpdf(sigma | 0, 2.5);
-  pred[1] = mu + beta * mu;
-  resid[1] = y[1] - pred[1];
-  for (t in 2:T) {
-    pred[t] = mu + beta * y[t - 1] + theta * resid[t - 1];
-    resid[t] = y[t] - pred[t];
-  }
-  target += phi * normal_lpdf(resid | 0, sigma);
-}
-"""
+WHOLE_SERIES = (ROOT / "tests/stan/arma_series.stan").read_text()
 
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 18
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
