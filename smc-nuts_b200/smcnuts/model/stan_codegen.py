@@ -1381,7 +1381,10 @@ class _Gen:
             elif n.op == "-":
                 push(n.args[0], None); push(n.args[1], "(-1.0)")
             elif n.op == "*":
-                push(n.args[0], xs[1]); push(n.args[1], xs[0])
+                if n.args[0] is n.args[1]:
+                    push(n.args[0], f"(2.0 * {xs[0]})")          # a square (`^ 2` is built as x * x)
+                else:
+                    push(n.args[0], xs[1]); push(n.args[1], xs[0])
             elif n.op == "/":
                 push(n.args[0], recip(1)); push(n.args[1], f"(-{v} * {recip(1)})")
             elif n.op == "^":
