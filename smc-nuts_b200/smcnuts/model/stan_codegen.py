@@ -20,8 +20,9 @@ What is generated
     err[t-1]) therefore work, and loops stay loops (bounds are literals: scalar data is folded at generation time).
 
 Supported subset (anything else raises StanSubsetError with the offending line):
-  blocks data / transformed data / parameters / transformed parameters / model (generated quantities is skipped: it never
-  enters the log density; a non-empty functions block is refused);  int, real, vector, row_vector, matrix (data and
+  blocks functions (functions returning real, inlined at the call: no recursion, one return at the end) / data /
+  transformed data / parameters / transformed parameters / model (generated quantities is skipped: it never enters the
+  log density);  int, real, vector, row_vector, matrix (data and
   locals), array[..] (and the pre-2.33 `real y[N]` form);  lower/upper bounds on real parameters;  local declarations
   with initialisers, =, +=, -=, *=, /=, `target +=`, `~`, for loops, if / else (conditions on data, loop variables or
   parameter values; && || !), blocks;
@@ -110,6 +111,11 @@ class _Parser:
                 blocks[name] = self.decls()
             elif name in ("model", "transformed data", "transformed parameters"):
                 blocks[name] = self.stmts()
+            elif name == "functions":
+                blocks[name] = {}
+                while self.peek()[1] != "}":
+                    fname, fn = self.function()
+                    blocks[name][fname] = fn
             else:
                 depth, empty = 1, True
                 while depth:
@@ -128,6 +134,52 @@ class _Parser:
                 raise StanSubsetError(f"missing block {need!r}")
         blocks.setdefault("data", [])
         return blocks
+
+    # ---- user-defined functions: name -> (return type, [(argument name, kind)], body statements, line);  kind is "int",
+    #      "real" or "container" (vector / row_vector / array: bound by name at the call)
+    def unsized_type(self):
+        self.accept("data")
+        dims = 0
+        if self.accept("array"):
+            self.expect("[")
+            dims = 1
+            while self.accept(","):
+                dims += 1
+            self.expect("]")
+        base = self.next()[1]
+        if base not in ("int", "real", "vector", "row_vector", "matrix", "void"):
+            self.err(f"unsupported type {base!r} in a function signature")
+        if self.accept("["):                  # pre-2.33: real[] x
+            dims += 1
+            while self.accept(","):
+                dims += 1
+            self.expect("]")
+        return base, dims
+
+    def function(self):
+        line = self.peek()[2]
+        rbase, rdims = self.unsized_type()
+        name = self.next()
+        if name[0] != "id":
+            self.err("expected a function name")
+        if rbase != "real" or rdims:
+            raise StanSubsetError(f"line {line}: function {name[1]!r}: only functions returning real are supported")
+        if name[1].endswith(("_lp", "_rng", "_lpdf", "_lpmf")):
+            raise StanSubsetError(f"line {line}: function {name[1]!r}: _lp / _rng / _lpdf / _lpmf functions are outside the subset")
+        self.expect("(")
+        params = []
+        while self.peek()[1] != ")":
+            base, dims = self.unsized_type()
+            arg = self.next()[1]
+            if base == "matrix":
+                raise StanSubsetError(f"line {line}: function {name[1]!r}: matrix arguments are outside the supported subset")
+            params.append((arg, "container" if (dims or base in ("vector", "row_vector")) else base))
+            self.accept(",")
+        self.expect(")")
+        self.expect("{")
+        body = self.stmts()
+        self.expect("}")
+        return name[1], ("real", params, body, line)
 
     # ---- declarations: (name, base, shape[list of expr], lower, upper, init)
     _TYPES = ("int", "real", "vector", "row_vector", "array", "matrix")
@@ -225,7 +277,11 @@ class _Parser:
             then = self.stmt()
             other = self.stmt() if self.accept("else") else None
             return ("if", cond, then, other, line)
-        if self.peek()[1] in ("while", "print", "reject", "return"):
+        if self.accept("return"):
+            e = self.expr()
+            self.expect(";")
+            return ("return", e, line)
+        if self.peek()[1] in ("while", "print", "reject"):
             raise StanSubsetError(f"line {line}: statement {self.peek()[1]!r} is outside the supported subset")
         if self.peek()[1] == "target" and self.peek(1)[1] == "+=":
             self.next(); self.next()
@@ -692,6 +748,19 @@ class _Gen:
         self.orients = orients or {}
         self.lowered = {}       # id(statement) -> its scalar-subset replacement (list of statements) or None
         self.fresh = 0
+        self.functions = blocks.get("functions", {})
+        self.inline_depth = 0
+        calls = {}
+        for fname, fn in self.functions.items():
+            found = set()
+            _walk_exprs(fn[2], lambda x, found=found: found.add(x[1]) if x[0] == "call" and x[1] in self.functions else None)
+            calls[fname] = found
+
+        def reaches(a, b, seen):
+            return any(c == b or (c not in seen and reaches(c, b, seen | {c})) for c in calls[a])
+        for fname, fn in self.functions.items():
+            if reaches(fname, fname, {fname}):
+                raise StanSubsetError(f"line {fn[3]}: recursive function {fname!r} is outside the supported subset")
         self.decl_init = {}     # id(declaration with an initialiser) -> its assignment statement
         self.hoisted, self.prologue = {}, []   # expression text -> name of its once-per-evaluation constant; their definitions
         self.outer_pre = None   # while a statement is being lowered: where its loop-invariant scalar reductions go
@@ -923,7 +992,7 @@ class _Gen:
             raise StanSubsetError(f"operator {op} between two containers is outside the supported subset")
         if k == "call":
             name, args = e[1], e[2]
-            if name in self._REDUCTIONS or re.fullmatch(r"\w+_(lpdf|lpmf|log)", name):
+            if name in self._REDUCTIONS or name in self.functions or re.fullmatch(r"\w+_(lpdf|lpmf|log)", name):
                 return (), None
             if name in self._REPS and len(args) == 2:
                 n, _ = self.int_expr(args[1])
@@ -1001,6 +1070,8 @@ class _Gen:
                     return ("bin", "*", x, x) if name == "dot_self" else x
                 total = self.reduce(n, term, pre, cl)
                 return ("bin", "/", total, ("num", float(n), False)) if name == "mean" else total
+            if name in self.functions:
+                return self.lower(self.inline(name, args, pre, cl), [], pre, cl)
             m = re.fullmatch(r"(\w+?)_(lpdf|lpmf|log)", name)
             if m and m.group(1) in _DENSITIES:
                 shapes = [self.shape(a)[0] for a in args]
@@ -1124,6 +1195,110 @@ class _Gen:
             loops = self.element_loops(ldims, body, line)
             return pre + loops
         return None
+
+    # ---- user-defined functions are inlined at the call ---------------------------------------------------------------
+    def inline(self, name, args, pre, line):
+        """Statements of the body (locals and loop variables renamed apart, arguments bound) appended to `pre`;
+        -> the expression the function returns.  Integer arguments and plain names are substituted, other real arguments
+        are evaluated once into a fresh local, container arguments must be variables (bound by name)."""
+        rtype, params, body, fline = self.functions[name]
+        if len(args) != len(params):
+            raise StanSubsetError(f"line {line}: {name} takes {len(params)} argument(s)")
+        if self.inline_depth >= 8:
+            raise StanSubsetError(f"line {line}: recursive function {name!r} is outside the supported subset")
+        if not body or body[-1][0] != "return":
+            raise StanSubsetError(f"line {fline}: function {name!r} must end in its only return statement")
+        env = {}
+        for (pname, kind), a in zip(params, args):
+            if kind == "container":
+                if not self.shape(a)[0]:
+                    raise StanSubsetError(f"line {line}: argument {pname!r} of {name} must be a container")
+                if a[0] not in ("var", "idx"):      # a container expression: materialised into a fresh local first
+                    dims, orient = self.shape(a)
+                    if len(dims) != 1:
+                        raise StanSubsetError(f"line {line}: argument {pname!r} of {name}: only one-dimensional expressions")
+                    tmp = self.fresh_name(pname)
+                    if orient:
+                        self.orients[tmp] = orient
+                    pre.append(("decl", (tmp, "real", [("num", float(dims[0]), True)], None, None, a, line), line))
+                    a = ("var", tmp, line)
+                env[pname] = a
+            elif kind == "int" or a[0] in ("num", "var"):
+                if kind == "int" and not self.is_int_expr(a):
+                    raise StanSubsetError(f"line {line}: argument {pname!r} of {name} must be an integer constant expression")
+                env[pname] = a
+            else:
+                tmp = self.fresh_name(pname)
+                pre.append(("decl", (tmp, "real", [], None, None, a, line), line))
+                env[pname] = ("var", tmp, line)
+
+        def rename_decls(ss):
+            for st in ss:
+                if st[0] == "decl":
+                    env[st[1][0]] = ("var", self.fresh_name(st[1][0]), st[2])
+                    if st[1][0] in self.orients:
+                        self.orients[env[st[1][0]][1]] = self.orients[st[1][0]]
+                elif st[0] == "block":
+                    rename_decls(st[1])
+                elif st[0] == "for":
+                    rename_decls(st[4])
+                elif st[0] == "if":
+                    rename_decls([x for x in (st[2], st[3]) if x is not None])
+                elif st[0] == "return" and st is not body[-1]:
+                    raise StanSubsetError(f"line {st[-1]}: function {name!r}: early returns are outside the supported subset")
+                elif st[0] in ("target", "tilde"):
+                    raise StanSubsetError(f"line {st[-1]}: function {name!r} must not touch the target")
+        rename_decls(body)
+
+        def sub(e, env):
+            if isinstance(e, tuple) and e and isinstance(e[0], str):
+                if e[0] == "var":
+                    return env.get(e[1], e)
+                if e[0] == "idx" and e[1][0] == "var" and e[1][1] in env:
+                    base = env[e[1][1]]
+                    idx = [sub(x, env) for x in e[2]]
+                    if base[0] == "idx":             # the argument was a slice, x[n]: its indices come first
+                        return ("idx", base[1], list(base[2]) + idx)
+                    return ("idx", base, idx)
+                if e[0] == "decl":
+                    d = e[1]
+                    return ("decl", (env[d[0]][1], d[1], [sub(x, env) for x in d[2]], None, None,
+                                     None if d[5] is None else sub(d[5], env), d[6]), e[2])
+                if e[0] == "for":
+                    inner = dict(env)
+                    inner[e[1]] = ("var", self.fresh_name(e[1]), e[5])
+                    return ("for", inner[e[1]][1], sub(e[2], env), sub(e[3], env), sub(e[4], inner), e[5])
+                if e[0] == "call":
+                    return ("call", e[1], [sub(x, env) for x in e[2]], e[3])
+                return tuple(sub(x, env) for x in e)
+            if isinstance(e, list):
+                return [sub(x, env) for x in e]
+            return e
+        def declare(ss):          # the returned expression is analysed before these statements are processed
+            for st in ss:
+                if st[0] == "decl":
+                    nm, _, shp = st[1][0], st[1][1], st[1][2]
+                    dims = [self.int_expr(d)[0] for d in shp]
+                    if any(d is None for d in dims):
+                        raise StanSubsetError(f"line {st[-1]}: local array sizes must be constants")
+                    self.vars.setdefault(nm, _Var(nm, "local", dims, st[1][1], orient=self.orients.get(nm)))
+                elif st[0] == "block":
+                    declare(st[1])
+                elif st[0] == "for":
+                    self.loop_vars.append((st[1], st[1]))
+                    declare(st[4])
+                    self.loop_vars.pop()
+                elif st[0] == "if":
+                    declare([x for x in (st[2], st[3]) if x is not None])
+        self.inline_depth += 1
+        try:
+            new = sub(body[:-1], env)
+            declare([x for x in pre if x[0] == "decl"])      # temporaries of the arguments
+            declare(new)
+            pre += new
+            return sub(body[-1][1], env)
+        finally:
+            self.inline_depth -= 1
 
     # ---- a vectorised density over a local vector, moved to where the elements are produced ---------------------------
     def fuse_vector_densities(self, stmts):

@@ -477,6 +477,58 @@ def test_trailing_vectorised_density_is_fused_into_the_loop_that_fills_its_vecto
     assert re.findall(r"double v_v\[\d+\]", SC.generate(head + loop + "target += normal_lpdf(v | 0, s); }", data).text)
 
 
+_FUNCTIONS = """
+functions {
+  real huber(real r, real k) {
+    real a = fabs(r);
+    real out;
+    if (a <= k) out = 0.5 * r * r; else out = k * (a - 0.5 * k);
+    return out;
+  }
+  real wsum(vector v, vector w, int n) {
+    real acc = 0;
+    for (i in 1:n) acc += v[i] * w[i];
+    return acc / n;
+  }
+  real twice(real x) { return 2 * huber(x, 1.0); }
+}
+data { int N; vector[N] y; vector[N] w; real phi; }
+parameters { real m; real<lower=0> s; vector[N] z; }
+model {
+  z ~ std_normal();
+  s ~ exponential(1);
+  for (n in 1:N) { target += phi * (-huber((y[n] - m) / s, 1.5)); target += -log(s); }
+  target += -0.1 * wsum(z, w, N) - 0.01 * twice(m) + 0.001 * wsum(z .* z, w, N);
+}
+"""
+
+
+def test_user_defined_functions_are_inlined(tmp_path):
+    """Functions returning real: scalar arguments given as expressions, an integer size, containers bound by name and
+    a container expression materialised first, if / else and a loop in the body, a function calling another one."""
+    rng = np.random.default_rng(0)
+    N = 5
+    data = {"N": N, "y": rng.normal(size=N).tolist(), "w": rng.random(N).tolist()}
+    src = SC.generate(_FUNCTIONS, data)
+    y, w = np.array(data["y"]), np.array(data["w"])
+
+    def hub(r, k):
+        return 0.5 * r * r if abs(r) <= k else k * (abs(r) - 0.5 * k)
+
+    def restated(u):
+        m, s, z = u[0], np.exp(u[1]), u[2:]
+        A = -0.5 * np.sum(z * z) - s + u[1] - N * np.log(s) - 0.1 * np.sum(z * w) / N - 0.01 * 2 * hub(m, 1.0) \
+            + 0.001 * np.sum(z * z * w) / N
+        return A, -sum(hub((y[n] - m) / s, 1.5) for n in range(N))
+    h = HostModel(src, tmp_path)
+    x = rng.normal(size=(30, 2 + N)) * 0.8
+    A, B, g = h.split(x, 0.6)
+    ref = np.array([restated(u) for u in x])
+    np.testing.assert_allclose(A, ref[:, 0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(B, ref[:, 1], rtol=1e-12, atol=1e-12)
+    _fd_check(h, x, g, 0.6, 2 + N, tol=2e-5)
+
+
 def test_unsupported_constructs_fail_loudly_with_the_line():
     ok = "data { int N; } parameters { real a; } model { a ~ normal(0, 1); }"
     assert SC.generate(ok, {"N": 3}).dim == 1
@@ -484,7 +536,10 @@ def test_unsupported_constructs_fail_loudly_with_the_line():
         ("parameters { real a; } model { while (a > 0) a ~ normal(0, 1); }", "while"),
         ("parameters { real a; } model { a ~ wishart(1, 2); }", "wishart"),
         ("parameters { matrix[2, 2] a; } model { }", "matrix"),
-        ("functions { real f(real x) { return x; } } parameters { real a; } model { }", "functions"),
+        ("functions { vector f(vector x) { return x; } } parameters { real a; } model { }", "returning real"),
+        ("functions { real f(real x) { if (x > 0) return x; return -x; } } parameters { real a; } model { target += f(a); }",
+         "early returns"),
+        ("functions { real f(real x) { return f(x); } } parameters { real a; } model { target += f(a); }", "recursive"),
         ("data { int N; vector[N] v; } parameters { vector[N] a; } model { target += sum(a * v); }", "elementwise products"),
         ("data { int N; matrix[N, N] X; } parameters { vector[N] a; } model { vector[N] m = a; m = X * m; }", "second variable"),
         ("data { int N; } parameters { vector[N] a; } model { vector[2] m; m = a; }", "size"),
