@@ -529,6 +529,23 @@ def test_user_defined_functions_are_inlined(tmp_path):
     _fd_check(h, x, g, 0.6, 2 + N, tol=2e-5)
 
 
+def test_generated_prm_kernel_program_matches_the_oracle(tmp_path):
+    """The second shipped model re-phrased (log-rate accumulator, poisson_log, pow): against the oracle's PRMwCD density."""
+    data = json.loads((ROOT / "smc-nuts_b200/smcnuts/data/PRMwCD/PRMwCD.json").read_text())
+    data.pop("phi")
+    src = SC.generate((STAN / "prm_kernel.stan").read_text(), data)
+    t = O.COracleTarget("PRMwCD")
+    assert src.dim == t.dim == 13
+    h = HostModel(src, tmp_path)
+    x = np.random.default_rng(1).normal(size=(200, 13)) * 0.7
+    for phi in (0.0, 0.37, 1.0):
+        A, B, g = h.split(x, phi)
+        Ao, Bo, _, _ = t.split(x, grads=False)
+        np.testing.assert_allclose(A, Ao, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(B, Bo, rtol=1e-12, atol=1e-10)
+        np.testing.assert_allclose(g, t.logpdfgrad(x, phi), rtol=1e-9, atol=1e-8)
+
+
 def test_unsupported_constructs_fail_loudly_with_the_line():
     ok = "data { int N; } parameters { real a; } model { a ~ normal(0, 1); }"
     assert SC.generate(ok, {"N": 3}).dim == 1
