@@ -1506,7 +1506,8 @@ class _Gen:
             else:
                 a = [name[id(x)] for x in n.args]
                 if n.kind == "un":
-                    text = {"neg": f"-{a[0]}", "inv_logit": f"smcgen_inv_logit({a[0]})", "log1p_exp": f"smcgen_log1p_exp({a[0]})"}.get(
+                    text = {"neg": f"-{a[0]}", "inv_logit": f"smcgen_inv_logit({a[0]})", "log1p_exp": f"smcgen_log1p_exp({a[0]})",
+                            "exp": f"smcb::fast_exp({a[0]})"}.get(
                         n.op, f"{n.op}({a[0]})")
                 elif n.op == "^":
                     text = f"sqrt({a[0]})" if _is_const(n.args[1], 0.5) else f"pow({a[0]}, {a[1]})"
