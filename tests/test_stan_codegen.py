@@ -546,6 +546,23 @@ def test_generated_prm_kernel_program_matches_the_oracle(tmp_path):
         np.testing.assert_allclose(g, t.logpdfgrad(x, phi), rtol=1e-9, atol=1e-8)
 
 
+def test_builtin_device_functions_are_only_used_for_the_shipped_program_text():
+    """StanModel("arma", path, ...) runs the hand-tuned device function only when the file IS the reference's program
+    (comments and white space aside); an edited file of the same name goes through the generator."""
+    import sys
+    sys.path.insert(0, str(ROOT / "smc-nuts_b200"))
+    from smcnuts.model.bridgestan import _BUILTIN_DIGESTS, program_digest
+    a = "data { int T; } // c\nparameters { real mu; } /* block\n comment */ model { mu ~ normal(0, 1); }"
+    assert program_digest(a) == program_digest("data{int T;}\n\nparameters{real mu;}model{mu~normal(0,1);}  # tail")
+    assert program_digest(a) != program_digest(a.replace("normal(0, 1)", "normal(0, 2)"))
+    assert program_digest((STAN / "arma_series.stan").read_text()) != _BUILTIN_DIGESTS["arma"]
+    if REF_MODELS.exists():
+        for name, digest in _BUILTIN_DIGESTS.items():
+            text = (REF_MODELS / name / f"{name}.stan").read_text()
+            assert program_digest(text) == digest
+            assert program_digest(text.replace("2.5", "3.5").replace("1.3", "1.4")) != digest
+
+
 def test_unsupported_constructs_fail_loudly_with_the_line():
     ok = "data { int N; } parameters { real a; } model { a ~ normal(0, 1); }"
     assert SC.generate(ok, {"N": 3}).dim == 1
@@ -670,3 +687,17 @@ def test_generated_container_programs_run_on_the_device_like_their_host_build(tm
     # the random-walk and N(0, 1) priors shrink a little; posterior sd of a coefficient is ~0.3 / sqrt(60) = 0.04
     np.testing.assert_allclose(est[:4], truth, atol=0.15)
     assert 0.2 < est[4] < 0.45
+
+
+@pytest.mark.gpu
+def test_stanmodel_with_a_rephrased_arma_file_goes_through_the_generator_and_agrees_with_the_builtin():
+    from smcnuts.model.bridgestan import StanModel
+    data_path = ROOT / "smc-nuts_b200/smcnuts/data/arma/arma.json"
+    edited = StanModel("arma", str(STAN / "arma_series.stan"), str(data_path))     # same name, another program text
+    builtin = StanModel("arma", "no_such_file.stan", str(data_path))
+    assert edited.resolved == "generated" and builtin.resolved == "builtin"
+    x = np.random.default_rng(3).normal(size=(256, 4)) * 0.05 + np.array([0.0, 0.9, 0.0, -1.7])
+    for phi in (0.25, 1.0):
+        np.testing.assert_allclose(edited.logpdf(x, phi), builtin.logpdf(x, phi), rtol=1e-11)
+        np.testing.assert_allclose(edited.logpdfgrad(x, phi), builtin.logpdfgrad(x, phi), rtol=1e-9, atol=1e-8)
+    np.testing.assert_allclose(edited.constrain(x), builtin.constrain(x), rtol=1e-15)
