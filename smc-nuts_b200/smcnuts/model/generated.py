@@ -86,7 +86,10 @@ class GeneratedModel(DeviceModel):
                    ctypes.byref(h))
         self._h = h
         self.param_names = list(self.source.param_names)
-        self.constrained_dim = self.dim          # no transformed parameters / generated quantities in the subset
+        # BridgeStan's constrain() appends transformed parameters and generated quantities (bridgestan.py:24,93-120 of the
+        # reference: param_num(include_tp=True, include_gq=True)); here they enter the density (transformed parameters) or
+        # are skipped (generated quantities) but are NOT appended: estimates cover the declared parameters only
+        self.constrained_dim = self.dim
         kinds = [t[0] for t in self.source.transforms]
         if all(k == "none" for k in kinds):
             self.constrain_kind = _cabi.CONSTRAIN_NONE
@@ -103,7 +106,8 @@ class GeneratedModel(DeviceModel):
         return cls(Path(model_path).read_text(), stan_codegen.load_data(data_path), name or Path(model_path).stem)
 
     def constrain(self, x, include_tparams=True, include_gqs=True):
-        """Stan's constraining transforms (bridgestan.py:93-120), one kernel for the whole particle array."""
+        """Stan's constraining transforms of the declared parameters (bridgestan.py:93-120), one kernel for the whole
+        particle array; `include_tparams` / `include_gqs` are accepted and ignored (see __init__)."""
         xd = dev.to_device(x).reshape(-1, self.dim)
         if self._table_dev is None:
             self._table_dev = dev.to_device(self._table_host.ravel())
