@@ -27,7 +27,7 @@ Supported subset (anything else raises StanSubsetError with the offending line):
   with initialisers, =, +=, -=, *=, /=, `target +=`, `~`, for loops, if / else (conditions on data, loop variables or
   parameter values; && || !), blocks;
   + - * / ^ .* ./, unary minus, indexing, exp log log1p sqrt fabs abs square inv inv_logit log1p_exp log_sum_exp(a, b)
-  pow tanh sin cos lgamma (of data: tabulated at generation time; of parameters: differentiated with a digamma series);
+  pow fmin fmax tanh sin cos lgamma (of data: tabulated at generation time; of parameters: differentiated with a digamma series);
   container-valued expressions: elementwise arithmetic and functions, matrix * vector, row_vector * vector,
   row_vector * matrix, sum mean dot_product dot_self rep_vector rep_row_vector rep_array,
   whole-container assignment -- lowered onto element loops and accumulator locals of the scalar subset (`lower_stmt`);
@@ -441,6 +441,8 @@ def _fold(op, x, y):
             return x * y
         if op == "/":
             return x / y if y != 0 else (math.nan if x == 0 else math.copysign(math.inf, x))
+        if op in ("fmin", "fmax"):
+            return min(x, y) if op == "fmin" else max(x, y)
         r = x ** y
         return r if isinstance(r, float) else math.nan
     except (OverflowError, ZeroDivisionError, ValueError):
@@ -880,6 +882,8 @@ class _Gen:
             return _div(_const(1.0), self.real(args[0]))
         if name == "pow" and len(args) == 2:
             return _bin("^", self.real(args[0]), self.real(args[1]))
+        if name in ("fmin", "fmax") and len(args) == 2:
+            return _bin(name, self.real(args[0]), self.real(args[1]))
         if name == "log_sum_exp" and len(args) == 2:
             a, b = self.real(args[0]), self.real(args[1])
             return _add(a, _un("log1p_exp", _sub(b, a)))
@@ -1511,6 +1515,8 @@ class _Gen:
                         n.op, f"{n.op}({a[0]})")
                 elif n.op == "^":
                     text = f"sqrt({a[0]})" if _is_const(n.args[1], 0.5) else f"pow({a[0]}, {a[1]})"
+                elif n.op in ("fmin", "fmax"):
+                    text = f"{n.op}({a[0]}, {a[1]})"
                 else:
                     text = f"{a[0]} {n.op} {a[1]}"
                 if fixed[id(n)]:
@@ -1563,6 +1569,9 @@ class _Gen:
                     push(n.args[0], xs[1]); push(n.args[1], xs[0])
             elif n.op == "/":
                 push(n.args[0], recip(1)); push(n.args[1], f"(-{v} * {recip(1)})")
+            elif n.op in ("fmin", "fmax"):       # the gradient follows the selected argument (the first one on ties)
+                first = f"({xs[0]} {'<=' if n.op == 'fmin' else '>='} {xs[1]})"
+                push(n.args[0], f"({first} ? 1.0 : 0.0)"); push(n.args[1], f"({first} ? 0.0 : 1.0)")
             elif n.op == "^":
                 if _is_const(n.args[1], 0.5):
                     push(n.args[0], f"(0.5 / {v})")

@@ -490,7 +490,7 @@ functions {
     for (i in 1:n) acc += v[i] * w[i];
     return acc / n;
   }
-  real twice(real x) { return 2 * huber(x, 1.0); }
+  real twice(real x) { return 2 * huber(x, 1.0) + fmax(x, 0.3) - fmin(x * x, 2.0); }
 }
 data { int N; vector[N] y; vector[N] w; real phi; }
 parameters { real m; real<lower=0> s; vector[N] z; }
@@ -517,7 +517,8 @@ def test_user_defined_functions_are_inlined(tmp_path):
 
     def restated(u):
         m, s, z = u[0], np.exp(u[1]), u[2:]
-        A = -0.5 * np.sum(z * z) - s + u[1] - N * np.log(s) - 0.1 * np.sum(z * w) / N - 0.01 * 2 * hub(m, 1.0) \
+        A = -0.5 * np.sum(z * z) - s + u[1] - N * np.log(s) - 0.1 * np.sum(z * w) / N \
+            - 0.01 * (2 * hub(m, 1.0) + max(m, 0.3) - min(m * m, 2.0)) \
             + 0.001 * np.sum(z * z * w) / N
         return A, -sum(hub((y[n] - m) / s, 1.5) for n in range(N))
     h = HostModel(src, tmp_path)
