@@ -54,6 +54,8 @@ def test_oracle_densities_equal_bridgestan(name):
 @pytest.mark.parametrize("fixture", ["regression", "containers", "logistic", "mixed"])
 def test_generated_models_equal_bridgestan(tmp_path, fixture):
     """The Stan-subset generator against Stan itself on the fixtures of tests/stan (values and gradients)."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
     import test_stan_codegen as T
     rng = np.random.default_rng(11)
     data = {"regression": lambda: T._regression_data(rng), "containers": lambda: T._containers_data(rng, 1),
