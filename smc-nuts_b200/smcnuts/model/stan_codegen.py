@@ -46,6 +46,11 @@ class StanSubsetError(NotImplementedError):
     pass
 
 
+# Statement-level restructuring (a vectorised density fused into the loop that fills its vector, arrays reduced to rolling
+# scalars).  tests/test_stan_fuzz.py switches it off to compare both forms of random programs; results must not change.
+RESTRUCTURE = True
+
+
 # ------------------------------------------------------------------------------------------------ tokenizer
 _TOKEN = re.compile(r"""
     (?P<ws>\s+|//[^\n]*|\#[^\n]*|/\*.*?\*/)
@@ -1842,7 +1847,8 @@ class _Gen:
             else:
                 program.append(st)
         program += self.blocks.get("transformed parameters", [])
-        self.blocks["model"] = _demote_arrays(self.fuse_vector_densities(program + self.blocks["model"]))
+        program += self.blocks["model"]
+        self.blocks["model"] = _demote_arrays(self.fuse_vector_densities(program)) if RESTRUCTURE else program
         # activity analysis (which coordinates can each local depend on): fixpoint over the statement list
         for _ in range(64):
             self.changed = False

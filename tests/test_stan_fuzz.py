@@ -118,3 +118,94 @@ def test_random_programs_match_numpy_and_finite_differences(tmp_path, seed):
         fd = ((Ap + 0.6 * Bp) - (Am + 0.6 * Bm)) / (2 * eps)
         scale = 1.0 + np.abs(fd)
         np.testing.assert_allclose(grad[:, j] / scale, fd / scale, rtol=0, atol=2e-5, err_msg=text)
+
+
+class LoopGen:
+    """Random recurrence programs: two model-block vectors filled by pre-loop writes and one loop (each element written
+    exactly once, unconditionally or in both branches of an if), read at [t - 1], [1] and -- after this trip's write --
+    [t]; consumed by vectorised densities after the loop.  Only defined elements are ever read."""
+
+    def __init__(self, rng):
+        self.rng = rng
+
+    def pick(self, xs):
+        return xs[int(self.rng.integers(len(xs)))]
+
+    def expr(self, readable, depth=2):
+        r = self.rng.random()
+        if depth <= 0 or r < 0.35:
+            return self.pick(readable + ["a", "b", "y[t]", "0.3"])
+        if r < 0.75:
+            return f"({self.expr(readable, depth - 1)} {self.pick(['+', '-', '*'])} {self.expr(readable, depth - 1)})"
+        return f"{self.pick(['tanh', 'sin', 'inv_logit'])}({self.expr(readable, depth - 1)})"
+
+    def program(self):
+        rng = self.rng
+        lines = ["vector[T] v;", "vector[T] w;"]
+        pre = ["a", "b", "y[1]", "0.3"]
+        lines.append("v[1] = " + self.pick(pre) + " * 0.5;")
+        lines.append("w[1] = " + self.pick(pre + ["v[1]"]) + " - 0.2;")
+        if rng.random() < 0.3:
+            lines.append("target += -0.01 * square(v[1] - w[1]);")
+        body, written = [], set()
+        order = ["v", "w"] if rng.random() < 0.5 else ["w", "v"]
+        slots = [order[0], "use", order[1], "use"]
+        for what in slots:
+            readable = ["v[t - 1]", "w[t - 1]", "v[1]"] + [f"{x}[t]" for x in written]
+            readable = [r.replace("y[t]", "y[t]") for r in readable]
+            if what == "use":
+                if rng.random() < 0.6:
+                    body.append(f"target += -0.01 * square({self.expr(readable)});")
+                continue
+            rhs = f"0.5 * {self.expr(readable)}"
+            if rng.random() < 0.3:
+                body.append(f"if (t <= 3) {what}[t] = {rhs}; else {what}[t] = 0.4 * {self.expr(readable)};")
+            else:
+                body.append(f"{what}[t] = {rhs};")
+            written.add(what)
+        lines.append("for (t in 2:T) {")
+        lines += ["  " + b for b in body]
+        lines.append("}")
+        for vec in ("v", "w"):
+            r = rng.random()
+            if r < 0.4:
+                lines.append(f"target += phi * normal_lpdf({vec} | 0, 1 + s);")
+            elif r < 0.6:
+                lines.append(f"{vec} ~ normal(y, 1 + s);")
+            elif r < 0.8:
+                lines.append(f"target += -0.1 * dot_self({vec});")
+            else:
+                lines.append(f"target += -0.1 * square({vec}[T]);")
+        if rng.random() < 0.3:
+            lines.append("target += normal_lpdf(v | w, 2);")      # two model-block vectors: never fused
+        return ("data { int T; vector[T] y; real phi; }\nparameters { real a; real b; real<lower=0> s; }\nmodel {\n  "
+                + "\n  ".join(lines) + "\n}\n")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_restructured_recurrence_programs_equal_their_plain_form(tmp_path, seed):
+    """Differential test of the statement-level passes: every random recurrence program is generated with and without the
+    restructuring (fusion of trailing vectorised densities, arrays reduced to rolling scalars); values and gradients of
+    both builds must agree, and across the seeds the passes must actually fire."""
+    import re
+    rng = np.random.default_rng(5000 + seed)
+    text = LoopGen(rng).program()
+    data = {"T": 6, "y": rng.normal(size=6).tolist()}
+    x = rng.normal(size=(16, 3)) * 0.5
+    out = {}
+    for flag in (True, False):
+        T.SC.RESTRUCTURE = flag
+        try:
+            src = T.SC.generate(text, data)
+        finally:
+            T.SC.RESTRUCTURE = True
+        out[flag] = (T.HostModel(src, tmp_path / str(flag)).split(x, 0.7), len(re.findall(r"double v_[vw]\[\d+\]", src.text)))
+    assert out[False][1] == 2, text
+    for got, want in zip(out[True][0], out[False][0]):
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, err_msg=text)
+    test_restructured_recurrence_programs_equal_their_plain_form.fired += out[True][1] < 2
+    if seed == 11:
+        assert test_restructured_recurrence_programs_equal_their_plain_form.fired >= 3
+
+
+test_restructured_recurrence_programs_equal_their_plain_form.fired = 0
