@@ -456,6 +456,36 @@ def main():
     e2e_val = le.item() / te.item()
     clk = clocks.stop() if rank == 0 else None
 
+    # ---------------------------------------------------------------- extra key at N > 1: the same iteration, weak scaling
+    # (the workload's particle count PER GPU); `value` above stays the strong-scaling number of the stated configuration
+    weak = None
+    if world > 1 and args.scaling == "strong":
+        n_weak = 1 << log2n
+        del xn, rn
+        smc_w = SMCSampler(K=W + K, N=n_weak * world, target=m, step_size=eps, sample_proposal=StdNormal(D),
+                           momentum_proposal=StdNormal(D), lkernel=lk, tempering=temp, rng=10, resampling=args.resampling,
+                           save_history=(lk == "asymptoticLKernel"))
+        smc_w.begin()
+        for k in range(W):
+            smc_w.iterate(k)
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for k in range(W, W + K):
+            smc_w.iterate(k)
+        w1.record()
+        barrier()
+        tw = torch.tensor([w0.elapsed_time(w1) * 1e-3], dtype=torch.float64, device="cuda")
+        lw = smc_w._lf[W:W + K].sum().reshape(1).clone()
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lw, op=dist.ReduceOp.SUM)
+        weak = {"value": lw.item() / tw.item(), "unit": "grad-evals/s", "ms_per_step": tw.item() / K * 1e3,
+                "particles_per_gpu": n_weak, "particles_global": n_weak * world,
+                "note": "same steps and warm-up, device-timed, max over ranks; divide by n_gpus x the N = 1 value for the "
+                        "weak-scaling efficiency"}
+        smc_w.samples.resampler.close()
+        del smc_w
+
     # ---------------------------------------------------------------- cpu_baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -510,6 +540,7 @@ def main():
                          "flop_per_eval": flop_per_eval, "evals": evals, "kernel_s": nuts_dt,
                          "kernel_share_of_step": nuts_dt / dt, **extra_roofline},
             "sharded_check": sharded_check,
+            "weak": weak,
             "cpu_baseline": cpu,
             "clocks": clk,
             "history_bytes": hist,
