@@ -24,7 +24,7 @@ Supported subset (anything else raises StanSubsetError with the offending line):
   transformed data / parameters / transformed parameters / model (generated quantities is skipped: it never enters the
   log density);  int, real, vector, row_vector, matrix (data and
   locals), array[..] (and the pre-2.33 `real y[N]` form);  lower/upper bounds on real parameters;  local declarations
-  with initialisers, =, +=, -=, *=, /=, `target +=`, `~`, for loops, if / else (conditions on data, loop variables or
+  with initialisers, =, +=, -=, *=, /=, `target +=`, `~`, for and while loops, if / else (conditions on data, loop variables or
   parameter values; && || !), blocks;
   + - * / ^ .* ./, unary minus, indexing, exp log log1p sqrt fabs abs square inv inv_logit log1p_exp log_sum_exp(a, b)
   pow fmin fmax tanh sin cos lgamma (of data: tabulated at generation time; of parameters: differentiated with a digamma series);
@@ -286,7 +286,12 @@ class _Parser:
             e = self.expr()
             self.expect(";")
             return ("return", e, line)
-        if self.peek()[1] in ("while", "print", "reject"):
+        if self.accept("while"):
+            self.expect("(")
+            cond = self.cond()
+            self.expect(")")
+            return ("while", cond, self.stmt(), line)
+        if self.peek()[1] in ("print", "reject"):
             raise StanSubsetError(f"line {line}: statement {self.peek()[1]!r} is outside the supported subset")
         if self.peek()[1] == "target" and self.peek(1)[1] == "+=":
             self.next(); self.next()
@@ -592,6 +597,8 @@ def _assigned_names(ss, out):
             _assigned_names(st[1], out)
         elif st[0] == "for":
             _assigned_names(st[4], out)
+        elif st[0] == "while":
+            _assigned_names([st[2]], out)
         elif st[0] == "if":
             _assigned_names([x for x in (st[2], st[3]) if x is not None], out)
         elif st[0] == "decl" and st[1][5] is not None:
@@ -617,6 +624,8 @@ def _demote_arrays(stmts):
                 find_decls(st[1])
             elif st[0] == "for":
                 find_decls(st[4])
+            elif st[0] == "while":
+                find_decls([st[2]])
             elif st[0] == "if":
                 find_decls([x for x in (st[2], st[3]) if x is not None])
     find_decls(stmts)
@@ -649,6 +658,8 @@ def _demote_arrays(stmts):
                 written_in(st[1], out)
             elif st[0] == "for":
                 written_in(st[4], out)
+            elif st[0] == "while":
+                written_in([st[2]], out)
             elif st[0] == "if":
                 written_in([x for x in (st[2], st[3]) if x is not None], out)
         return out
@@ -685,6 +696,11 @@ def _demote_arrays(stmts):
             elif k == "for":
                 reads((st[2], st[3]), last)
                 child(st[4], last, True, loop=(st[1], st[2]))
+            elif k == "while":
+                for v in written_in([st[2]], set()):      # the condition of a later trip sees what the body wrote
+                    last[v] = None
+                reads(st[1], last)
+                child([st[2]], last, True)
             elif k == "if":
                 reads(st[1], last)
                 child([st[2]], last, False)
@@ -1251,6 +1267,8 @@ class _Gen:
                     rename_decls(st[1])
                 elif st[0] == "for":
                     rename_decls(st[4])
+                elif st[0] == "while":
+                    rename_decls([st[2]])
                 elif st[0] == "if":
                     rename_decls([x for x in (st[2], st[3]) if x is not None])
                 elif st[0] == "return" and st is not body[-1]:
@@ -1297,6 +1315,8 @@ class _Gen:
                     self.loop_vars.append((st[1], st[1]))
                     declare(st[4])
                     self.loop_vars.pop()
+                elif st[0] == "while":
+                    declare([st[2]])
                 elif st[0] == "if":
                     declare([x for x in (st[2], st[3]) if x is not None])
         self.inline_depth += 1
@@ -1332,6 +1352,8 @@ class _Gen:
                     collect(st[1])
                 elif st[0] == "for":
                     collect(st[4])
+                elif st[0] == "while":
+                    collect([st[2]])
                 elif st[0] == "if":
                     collect([x for x in (st[2], st[3]) if x is not None])
         collect(stmts)
@@ -1729,6 +1751,16 @@ class _Gen:
                 if emit:
                     self.indent -= 1
                     self.emit("}")
+                    self.indent -= 1
+                    self.emit("}")
+                continue
+            if kind == "while":      # the condition is re-evaluated at the top of every trip
+                if emit:
+                    self.emit("while (true) {")
+                    self.indent += 1
+                    self.emit(f"if (!{self.cond_text(s[1], line)}) break;")
+                self.statements([s[2]], emit)
+                if emit:
                     self.indent -= 1
                     self.emit("}")
                 continue
