@@ -24,7 +24,8 @@ Supported subset (anything else raises StanSubsetError with the offending line):
   transformed data / parameters / transformed parameters / model (generated quantities is skipped: it never enters the
   log density);  int, real, vector, row_vector, matrix (data and
   locals), array[..] (and the pre-2.33 `real y[N]` form);  lower/upper bounds on real parameters;  local declarations
-  with initialisers, =, +=, -=, *=, /=, `target +=`, `~`, for and while loops, if / else (conditions on data, loop variables or
+  with initialisers, =, +=, -=, *=, /=, `target +=`, `~`, for and while loops, print (ignored), reject (the density becomes -inf, which is what the
+  reference makes of a Stan exception), if / else (conditions on data, loop variables or
   parameter values; && || !), blocks;
   + - * / ^ .* ./, unary minus, indexing, exp log log1p sqrt fabs abs square inv inv_logit log1p_exp log_sum_exp(a, b)
   pow fmin fmax tanh sin cos lgamma (of data: tabulated at generation time; of parameters: differentiated with a digamma series);
@@ -54,6 +55,7 @@ RESTRUCTURE = True
 # ------------------------------------------------------------------------------------------------ tokenizer
 _TOKEN = re.compile(r"""
     (?P<ws>\s+|//[^\n]*|\#[^\n]*|/\*.*?\*/)
+  | (?P<str>"[^"\n]*")
   | (?P<num>(\d+\.\d*|\.\d+|\d+)([eE][+-]?\d+)?)
   | (?P<id>[A-Za-z_][A-Za-z_0-9]*)
   | (?P<op>\.\*|\./|\+=|-=|\*=|/=|<=|>=|==|!=|&&|\|\||[-+*/^()\[\]{},;:|<>=~'!])
@@ -291,6 +293,18 @@ class _Parser:
             cond = self.cond()
             self.expect(")")
             return ("while", cond, self.stmt(), line)
+        if self.peek()[1] in ("print", "reject") and self.peek(1)[1] == "(":
+            what = self.next()[1]
+            depth = 0
+            while True:                       # the message (strings and expressions) is not evaluated
+                tok = self.next()
+                depth += (tok[1] == "(") - (tok[1] == ")")
+                if tok[0] == "eof":
+                    self.err(f"unterminated {what}")
+                if depth == 0:
+                    break
+            self.expect(";")
+            return (what, line)
         if self.peek()[1] in ("print", "reject"):
             raise StanSubsetError(f"line {line}: statement {self.peek()[1]!r} is outside the supported subset")
         if self.peek()[1] == "target" and self.peek(1)[1] == "+=":
@@ -1753,6 +1767,12 @@ class _Gen:
                     self.emit("}")
                     self.indent -= 1
                     self.emit("}")
+                continue
+            if kind == "print":      # output statements do not touch the density
+                continue
+            if kind == "reject":     # Stan throws; the reference maps the exception to logp = -inf (bridgestan.py:47-49)
+                if emit:
+                    self.emit("ok = false;")
                 continue
             if kind == "while":      # the condition is re-evaluated at the top of every trip
                 if emit:

@@ -610,11 +610,20 @@ def test_while_loops_with_value_dependent_trip_counts(tmp_path):
     _fd_check(h, x, g, 1.0, 2, tol=2e-5)
 
 
+def test_print_is_ignored_and_reject_maps_to_minus_infinity(tmp_path):
+    """bridgestan.py:47-49 of the reference turns a Stan exception into logp = -inf; reject() does the same here."""
+    text = ('parameters { real a; } model { print("a = ", a, " (debug)"); '
+            'if (a > 1.5) reject("a too large: ", a); a ~ normal(0, 1); }')
+    h = HostModel(SC.generate(text, {}), tmp_path)
+    A, B, g = h.split(np.array([[0.3], [2.0]]), 1.0)
+    assert A[0] == -0.5 * 0.3 ** 2 and A[1] == -np.inf and g[0, 0] == -0.3
+
+
 def test_unsupported_constructs_fail_loudly_with_the_line():
     ok = "data { int N; } parameters { real a; } model { a ~ normal(0, 1); }"
     assert SC.generate(ok, {"N": 3}).dim == 1
     for bad, what in [
-        ("parameters { real a; } model { print(a); }", "print"),
+        ("parameters { real a; } model { a ~ normal(0, 1) T[0, ]; }", "truncation"),
         ("parameters { real a; } model { a ~ wishart(1, 2); }", "wishart"),
         ("parameters { matrix[2, 2] a; } model { }", "matrix"),
         ("functions { vector f(vector x) { return x; } } parameters { real a; } model { }", "returning real"),
