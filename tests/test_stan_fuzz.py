@@ -186,7 +186,7 @@ class LoopGen:
 def test_restructured_recurrence_programs_equal_their_plain_form(tmp_path, seed):
     """Differential test of the statement-level passes: every random recurrence program is generated with and without the
     restructuring (fusion of trailing vectorised densities, arrays reduced to rolling scalars); values and gradients of
-    both builds must agree, and across the seeds the passes must actually fire."""
+    both builds must agree."""
     import re
     rng = np.random.default_rng(5000 + seed)
     text = LoopGen(rng).program()
@@ -203,9 +203,16 @@ def test_restructured_recurrence_programs_equal_their_plain_form(tmp_path, seed)
     assert out[False][1] == 2, text
     for got, want in zip(out[True][0], out[False][0]):
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, err_msg=text)
-    test_restructured_recurrence_programs_equal_their_plain_form.fired += out[True][1] < 2
-    if seed == 11:
-        assert test_restructured_recurrence_programs_equal_their_plain_form.fired >= 3
 
 
-test_restructured_recurrence_programs_equal_their_plain_form.fired = 0
+def test_the_restructuring_fires_on_the_random_recurrence_programs():
+    """The differential test above is only worth something if the passes do change programs: count them (generation
+    only, nothing is compiled)."""
+    import re
+    fired = 0
+    for seed in range(12):
+        rng = np.random.default_rng(5000 + seed)
+        text = LoopGen(rng).program()
+        src = T.SC.generate(text, {"T": 6, "y": rng.normal(size=6).tolist()})
+        fired += len(re.findall(r"double v_[vw]\[\d+\]", src.text)) < 2
+    assert fired >= 3, fired
