@@ -1775,9 +1775,11 @@ class _Gen:
                     self.emit("ok = false;")
                 continue
             if kind == "while":      # the condition is re-evaluated at the top of every trip
-                if emit:
-                    self.emit("while (true) {")
+                if emit:     # a loop that never ends would hang every lane of the device: after 2^24 trips the density is -inf
+                    trip = self.new_tmp("trip")
+                    self.emit(f"for (int {trip} = 0; ; ++{trip}) {{")
                     self.indent += 1
+                    self.emit(f"if ({trip} >= (1 << 24)) {{ ok = false; break; }}")
                     self.emit(f"if (!{self.cond_text(s[1], line)}) break;")
                 self.statements([s[2]], emit)
                 if emit:
