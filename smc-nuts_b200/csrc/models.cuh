@@ -50,6 +50,10 @@ struct ModelDesc {
 };
 
 // ---------------------------------------------------------------------------------------------- arma
+#ifndef SMCB_ARMA_UNROLL
+#define SMCB_ARMA_UNROLL 8     // A/B on B200 (profiles/r2_ab_arma_unroll.log)
+#endif
+constexpr int kArmaUnroll = SMCB_ARMA_UNROLL;
 struct ArmaModel {
     static constexpr int DMAX = 4;
     static constexpr int STATIC_D = 4;
@@ -98,7 +102,7 @@ struct ArmaModel {
         // One DFMA per loop-carried chain and step (e, d_mu, d_beta, d_theta) plus four accumulator DFMAs: the
         // y-only part of nu[t] is formed off the critical path, so a single warp keeps the FP64 pipe busy.
         const double ntheta = -theta;
-#pragma unroll 8
+#pragma unroll kArmaUnroll
         for (int t = 1; t < T; ++t) {
             const double yt = y[t];
             const double c = yt - (mu + beta * ylag);       // y[t] - (mu + beta*y[t-1]); independent of the chains
